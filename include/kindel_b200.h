@@ -1,0 +1,180 @@
+/* kindel_b200.h -- C ABI of the B200-native pileup/consensus engine (libkindel_b200.so).
+ *
+ * The reference (bede/kindel v1.2.1) is pure Python and has no FFI of its own; its seam for this
+ * path is three Python callables:
+ *     parse_records(ref_id, ref_len, records)          reference kindel/kindel.py:21-128
+ *     consensus(weight)                                reference kindel/kindel.py:369-381
+ *     consensus_sequence(weights, insertions, ...)     reference kindel/kindel.py:384-430
+ * The entry points below are what a ctypes/cffi binding inside the reference's
+ * `kindel/kindel.py` would call in place of those loops (the stub is shown in INTEGRATION.md;
+ * the shipped host side that does exactly that is kindel_b200/kindel.py).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *   - every function returns a kdl_status (0 = ok).  Nothing here allocates device memory except
+ *     the kdl_ctx_* host-buffer path, which owns a growable workspace inside its context.
+ *   - "device" entry points take DEVICE pointers and only enqueue work on `stream` (asynchronous;
+ *     the caller synchronises).  "host" entry points (kdl_ctx_*) take HOST pointers, do the
+ *     host->device copies, the kernels and the device->host copies themselves and return when the
+ *     results are in the caller's buffers.
+ *   - re-entrant per stream, no global mutable state.
+ *
+ * Data layout (all little-endian)
+ *   reads, in the reference's iteration order (grouped by contig in first-seen order, file order
+ *   inside a contig; records failing `mapped and len(seq) > 1`, kindel.py:43-46, already dropped):
+ *     ref_start[n]   int32   0-based reference cursor at walk start (= SAM POS - 1; -1 if POS == 0)
+ *     seq_off[n]     uint32  offset of the read's packed bases in `seq4`, in 4-byte words
+ *     l_seq[n]       int32   low 31 bits: SEQ length.  bit 31 (KDL_COMPLEX) set = needs the general
+ *                            CIGAR walk; clear = "simple" read: exactly one M/=/X op, in bounds,
+ *                            and then the low bits hold that op's length (<= SEQ length)
+ *     cig_off[n+1]   uint32  prefix offsets into `cigar`
+ *     cigar[n_ops]   uint32  BAM encoding  len << 4 | op,  op index into "MIDNSHP=X"
+ *     seq4[...]      uint8   BAM nibble encoding "=ACMGRSVTWYHKDBN", high nibble first, every
+ *                            read starting on a 4-byte boundary
+ *   contigs:
+ *     contig_read_off[n_contigs+1] int64  reads of contig c are [off[c], off[c+1])
+ *     contig_len[n_contigs]        int32  reference length L_c
+ *     contig_slot[n_contigs]       int64  first table slot of contig c; it owns L_c + 1 slots
+ *   count table: counts[KDL_NCOL][n_slots] int32, column-major (one contiguous array per column):
+ *     0-4  weights A,C,G,T,N          (kindel.py:29,49-54)
+ *     5    deletions                  (kindel.py:39,59-62)
+ *     6    insertion events (total)   (kindel.py:38,55-58; the string-keyed dict is rebuilt from
+ *                                      the event list below)
+ *     7    clip_starts   8 clip_ends  (kindel.py:36-37,66,75)
+ *     9-13 clip_start_weights A,C,G,T,N   14-18 clip_end_weights A,C,G,T,N (kindel.py:30-35,67-81)
+ *   insertion events: ins_events[n_events][4] int32 = (slot, read, q_off, len), event k of the j-th
+ *     listed read stored at row evt_off[j] + k  (deterministic, reference iteration order).
+ */
+#ifndef KINDEL_B200_H
+#define KINDEL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KDL_ABI_VERSION 1
+#define KDL_NCOL 19
+#define KDL_NVOTE_COL 7 /* columns 0..6 are all the vote needs */
+#define KDL_COMPLEX 0x80000000u
+
+enum kdl_col {
+    KDL_W_A = 0, KDL_W_C, KDL_W_G, KDL_W_T, KDL_W_N,
+    KDL_DEL = 5, KDL_INS = 6, KDL_CLIP_STARTS = 7, KDL_CLIP_ENDS = 8,
+    KDL_CSW_A = 9, KDL_CEW_A = 14
+};
+
+typedef enum kdl_status {
+    KDL_OK = 0,
+    KDL_ERR_INVALID_ARG = 1,
+    KDL_ERR_CUDA = 2,
+    KDL_ERR_NO_DEVICE = 3,
+    /* data errors, mirroring the exceptions the reference raises: */
+    KDL_ERR_INDEX = 10, /* IndexError: walk ran off the contig / off SEQ (kindel.py:51,52,61) */
+    KDL_ERR_KEY = 11    /* KeyError: base outside A,C,G,T,N used in an M or S op (kindel.py:52,72,79) */
+} kdl_status;
+
+/* Flattened read batch.  Pointers are device pointers for the device entry points and host
+ * pointers for the kdl_ctx_* entry points. */
+typedef struct kdl_batch {
+    int64_t n_reads;
+    int64_t n_ops;       /* entries in cigar */
+    int64_t seq4_bytes;  /* bytes in seq4 (multiple of 4) */
+    const int32_t* ref_start;
+    const uint32_t* seq_off;
+    const int32_t* l_seq;
+    const uint32_t* cig_off;
+    const uint32_t* cigar;
+    const uint8_t* seq4;
+    int32_t n_contigs;
+    int32_t reads_sorted; /* 1 = ref_start is non-decreasing inside every contig */
+    const int64_t* contig_read_off;
+    const int32_t* contig_len;
+    const int64_t* contig_slot;
+    /* complex reads (bit 31 of l_seq set), ascending read index; may be NULL when n_complex == 0 */
+    int64_t n_complex;
+    const uint32_t* complex_idx; /* [n_complex] */
+    const uint32_t* evt_off;     /* [n_complex+1] running count of I ops before each listed read */
+} kdl_batch;
+
+/* Error report written by the pileup (device memory, 4 x int32, zero it before the call):
+ *   [0] != 0 : some read hit a data error; call kdl_diagnose for the exact first one. */
+typedef struct kdl_diag {
+    int32_t status;    /* KDL_OK, KDL_ERR_INDEX or KDL_ERR_KEY */
+    int32_t reserved;
+    int64_t read;      /* index of the first offending read in iteration order */
+    int32_t nibble;    /* for KDL_ERR_KEY: BAM nibble code of the offending base */
+    int32_t op_index;  /* CIGAR op at which the walk failed */
+} kdl_diag;
+
+int kdl_abi_version(void);
+const char* kdl_status_string(int status);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+int64_t kdl_launch_count(void);
+
+/* K1 -- pileup.  Replaces the loop at kindel/kindel.py:40-81.
+ * Adds every read's contribution to `counts` (caller zeroes it first, so several batches -- or
+ * several read shards -- can accumulate into one table) and writes the insertion event rows.
+ * err_flag: device int32[4], caller-zeroed; [0] becomes non-zero if any read raised. */
+int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t* ins_events,
+               int32_t* err_flag, void* stream);
+
+/* Exact first error in reference iteration order (only needed when err_flag[0] != 0).
+ * `diag_dev`: device kdl_diag, written asynchronously. */
+int kdl_diagnose(const kdl_batch* batch, kdl_diag* diag_dev, void* stream);
+
+/* K2 -- per-position vote.  Replaces kindel/kindel.py:402-424 + 369-381 for every slot.
+ * calls[s] : bits 0-2 = emitted base (0..4 = A,C,G,T,N; a tie emits N), bits 4-5 = change code
+ *            (0 none, 1 'D' -> nothing emitted, 2 'N' -> 'N' emitted, 3 'I' -> insertion string
+ *            precedes the base).  min_depth_ceil = ceil(min_depth). */
+int kdl_vote(const int32_t* counts, int64_t n_slots, int64_t min_depth_ceil, uint8_t* calls,
+             void* stream);
+
+/* Derived per-position columns of the `alignment` tuple (kindel/kindel.py:83-96) + the ACGT depth
+ * used by build_report (kindel.py:450).  out[5][n_slots] int32: consensus_depth, clip_start_depth,
+ * clip_end_depth, clip_depth, acgt_depth. */
+int kdl_derive(const int32_t* counts, int64_t n_slots, int32_t* out, void* stream);
+
+/* Fused cross-GPU count reduction + vote: sums the 7 vote columns of `n_peers`
+ * tables that live on this and on peer GPUs (peer pointers mapped with CUDA IPC / P2P), votes on
+ * slots [slot_lo, slot_hi) and writes calls for that range; optionally stores the reduced
+ * columns into reduced[7][n_slots] (may be NULL). */
+int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n_slots,
+                   int64_t slot_lo, int64_t slot_hi, int64_t min_depth_ceil, uint8_t* calls,
+                   int32_t* reduced, void* stream);
+
+/* ---- host-buffer path (what a cgo/JNI/ctypes caller without its own CUDA runtime uses) ---- */
+typedef struct kdl_ctx kdl_ctx;
+
+int kdl_ctx_create(int device, kdl_ctx** out);
+void kdl_ctx_destroy(kdl_ctx* ctx);
+
+/* batch holds HOST pointers.  Outputs (host, caller-allocated, any may be NULL to skip):
+ *   calls_out[n_slots] uint8, counts_out[KDL_NCOL][n_slots] int32,
+ *   ins_events_out[n_events][4] int32.  diag_out is always filled.
+ * Returns KDL_OK, or KDL_ERR_INDEX / KDL_ERR_KEY with diag_out describing the first offender. */
+int kdl_ctx_consensus(kdl_ctx* ctx, const kdl_batch* batch, int64_t n_slots, int64_t n_events,
+                      int64_t min_depth_ceil, uint8_t* calls_out, int32_t* counts_out,
+                      int32_t* ins_events_out, kdl_diag* diag_out);
+
+/* device time (ms) of the last kdl_ctx_consensus call, H2D / kernels / D2H, from CUDA events */
+int kdl_ctx_last_timing(kdl_ctx* ctx, float* h2d_ms, float* kernel_ms, float* d2h_ms);
+
+/* ---- host-side BAM record gather (no GPU involved; kindel_b200/csrc/bam_host.cpp) ----
+ * Replaces the simplesam -> `samtools view` text round trip of kindel/kindel.py:136-145 for .bam
+ * input.  `bam` is the INFLATED byte stream; first_record = offset of the first alignment record.
+ *   kdl_bam_count: per_contig[n_ref][4] int64 = records seen, kept (mapped and l_seq > 1), CIGAR
+ *                  ops kept, packed-SEQ 4-byte words kept; first_seen[n_ref] = rank or -1;
+ *                  totals[4] = records, kept, contigs seen, bytes consumed.
+ *   kdl_bam_fill : cursors[n_ref][3] int64 = next read / op / seq-word index per contig. */
+int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
+                  int64_t* per_contig, int32_t* first_seen, int64_t* totals);
+int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
+                 int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
+                 uint32_t* cig_start, uint32_t* cigar, uint8_t* seq4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KINDEL_B200_H */

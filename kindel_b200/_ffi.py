@@ -1,0 +1,114 @@
+"""ctypes binding of libkindel_b200.so (the C ABI in include/kindel_b200.h).
+
+There is no fallback: if the shared library is missing it is built in-tree with nvcc
+(`kindel_b200.build`); if that fails, importing the engine raises.  Nothing in this package computes
+a pileup or a vote on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+c_i32p = C.POINTER(C.c_int32)
+c_u32p = C.POINTER(C.c_uint32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+KDL_NCOL = 19
+KDL_NVOTE_COL = 7
+KDL_COMPLEX = 0x80000000
+KDL_OK = 0
+KDL_ERR_INDEX = 10
+KDL_ERR_KEY = 11
+
+
+class KdlBatch(C.Structure):
+    _fields_ = [
+        ("n_reads", C.c_int64),
+        ("n_ops", C.c_int64),
+        ("seq4_bytes", C.c_int64),
+        ("ref_start", C.c_void_p),
+        ("seq_off", C.c_void_p),
+        ("l_seq", C.c_void_p),
+        ("cig_off", C.c_void_p),
+        ("cigar", C.c_void_p),
+        ("seq4", C.c_void_p),
+        ("n_contigs", C.c_int32),
+        ("reads_sorted", C.c_int32),
+        ("contig_read_off", C.c_void_p),
+        ("contig_len", C.c_void_p),
+        ("contig_slot", C.c_void_p),
+        ("n_complex", C.c_int64),
+        ("complex_idx", C.c_void_p),
+        ("evt_off", C.c_void_p),
+    ]
+
+
+class KdlDiag(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32),
+        ("reserved", C.c_int32),
+        ("read", C.c_int64),
+        ("nibble", C.c_int32),
+        ("op_index", C.c_int32),
+    ]
+
+
+# every symbol include/kindel_b200.h declares, with its prototype
+_PROTOTYPES = {
+    "kdl_abi_version": (C.c_int, []),
+    "kdl_status_string": (C.c_char_p, [C.c_int]),
+    "kdl_launch_count": (C.c_int64, []),
+    "kdl_pileup": (C.c_int, [C.POINTER(KdlBatch), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_diagnose": (C.c_int, [C.POINTER(KdlBatch), C.c_void_p, C.c_void_p]),
+    "kdl_vote": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "kdl_derive": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "kdl_vote_peers": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "kdl_ctx_destroy": (None, [C.c_void_p]),
+    "kdl_ctx_consensus": (C.c_int, [C.c_void_p, C.POINTER(KdlBatch), C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(KdlDiag)]),
+    "kdl_ctx_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "kdl_bam_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_bam_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if needed) the engine library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build_engine()
+    lib = C.CDLL(path)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.kdl_abi_version() != 1:
+        raise RuntimeError("libkindel_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def status_string(code: int) -> str:
+    return load().kdl_status_string(code).decode()
+
+
+def check(code: int, what: str = "") -> None:
+    if code != KDL_OK:
+        raise RuntimeError("kindel_b200 %s failed: %s (status %d)" % (what, status_string(code), code))

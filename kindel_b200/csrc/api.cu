@@ -1,0 +1,146 @@
+// api.cu -- the C ABI declared in include/kindel_b200.h (unity build of the kernel files).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kdl_common.cuh"
+#include "pileup_general.cu"
+#include "pileup_simple.cu"
+#include "vote.cu"
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+inline int grid_for(long long items, int per_block, int cap) {
+    long long g = (items + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+inline int check_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError() == cudaSuccess ? KDL_OK : KDL_ERR_CUDA;
+}
+
+int validate_batch(const kdl_batch* b) {
+    if (!b || b->n_reads < 0 || b->n_contigs < 0) return KDL_ERR_INVALID_ARG;
+    if (b->n_reads > 0 && (!b->ref_start || !b->seq_off || !b->l_seq || !b->cig_off || !b->seq4 ||
+                           !b->contig_read_off || !b->contig_len || !b->contig_slot))
+        return KDL_ERR_INVALID_ARG;
+    if (b->n_complex > 0 && (!b->complex_idx || !b->evt_off || !b->cigar)) return KDL_ERR_INVALID_ARG;
+    return KDL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kdl_abi_version(void) { return KDL_ABI_VERSION; }
+
+const char* kdl_status_string(int status) {
+    switch (status) {
+        case KDL_OK: return "ok";
+        case KDL_ERR_INVALID_ARG: return "invalid argument";
+        case KDL_ERR_CUDA: return "CUDA error";
+        case KDL_ERR_NO_DEVICE: return "no CUDA device";
+        case KDL_ERR_INDEX: return "IndexError: read walks off the contig or off its SEQ";
+        case KDL_ERR_KEY: return "KeyError: base outside A,C,G,T,N in an M or S op";
+        default: return "unknown status";
+    }
+}
+
+int64_t kdl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t* ins_events,
+               int32_t* err_flag, void* stream) {
+    int rc = validate_batch(batch);
+    if (rc != KDL_OK) return rc;
+    if (!counts || !err_flag || n_slots <= 0) return KDL_ERR_INVALID_ARG;
+    if (batch->n_reads == 0) return KDL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cap = sm_count() * 8;
+    if (batch->n_reads > batch->n_complex) {
+        const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
+        kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
+        if ((rc = check_launch()) != KDL_OK) return rc;
+    }
+    if (batch->n_complex > 0) {
+        const int grid = grid_for(batch->n_complex, 8, cap);
+        kdl::pileup_general_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events, err_flag);
+        if ((rc = check_launch()) != KDL_OK) return rc;
+    }
+    return KDL_OK;
+}
+
+int kdl_diagnose(const kdl_batch* batch, kdl_diag* diag_dev, void* stream) {
+    int rc = validate_batch(batch);
+    if (rc != KDL_OK) return rc;
+    if (!diag_dev) return KDL_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    kdl::diagnose_init_kernel<<<1, 1, 0, st>>>(diag_dev);
+    if ((rc = check_launch()) != KDL_OK) return rc;
+    if (batch->n_reads > 0) {
+        const long long grid = (batch->n_reads + 255) / 256;
+        kdl::diagnose_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, diag_dev);
+        if ((rc = check_launch()) != KDL_OK) return rc;
+    }
+    kdl::diagnose_final_kernel<<<1, 1, 0, st>>>(diag_dev);
+    return check_launch();
+}
+
+int kdl_vote(const int32_t* counts, int64_t n_slots, int64_t min_depth_ceil, uint8_t* calls,
+             void* stream) {
+    if (!counts || !calls || n_slots <= 0 || (n_slots & 3)) return KDL_ERR_INVALID_ARG;
+    kdl::Peers none;
+    none.n = 0;
+    const long long quads = n_slots / 4;
+    const long long grid = (quads + 255) / 256;
+    kdl::vote_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        counts, none, n_slots, 0, n_slots, min_depth_ceil, calls, nullptr);
+    return check_launch();
+}
+
+int kdl_derive(const int32_t* counts, int64_t n_slots, int32_t* out, void* stream) {
+    if (!counts || !out || n_slots <= 0) return KDL_ERR_INVALID_ARG;
+    const long long grid = (n_slots + 255) / 256;
+    kdl::derive_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(counts, n_slots, out);
+    return check_launch();
+}
+
+int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n_slots,
+                   int64_t slot_lo, int64_t slot_hi, int64_t min_depth_ceil, uint8_t* calls,
+                   int32_t* reduced, void* stream) {
+    if (!peer_counts || n_peers < 1 || n_peers > 16 || !calls || n_slots <= 0 || (n_slots & 3) ||
+        slot_lo < 0 || slot_hi > n_slots || (slot_lo & 3) || (slot_hi & 3))
+        return KDL_ERR_INVALID_ARG;
+    if (slot_hi <= slot_lo) return KDL_OK;
+    kdl::Peers peers;
+    peers.n = n_peers;
+    for (int p = 0; p < n_peers; ++p) {
+        if (!peer_counts[p]) return KDL_ERR_INVALID_ARG;
+        peers.tab[p] = peer_counts[p];
+    }
+    const long long quads = (slot_hi - slot_lo) / 4;
+    const long long grid = (quads + 255) / 256;
+    kdl::vote_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        nullptr, peers, n_slots, slot_lo, slot_hi, min_depth_ceil, calls, reduced);
+    return check_launch();
+}
+
+}  // extern "C"
+
+#include "host_ctx.inl"

@@ -1,0 +1,120 @@
+// vote.cu -- K2: per-position majority vote; K2d: derived depth columns; K2p: fused cross-GPU
+// count reduction + vote over NVLink peer memory.
+//
+// K2 restates, for every table slot at once, the body of consensus_sequence
+// (kindel/kindel.py:402-424) with consensus() (kindel.py:369-381) inlined.  It is a pure streaming
+// kernel: 7 int32 columns in (28 B/slot), one call byte out; each thread owns 4 consecutive slots
+// (128-bit loads per column, one 32-bit store), the look-ahead depth `aligned_depth_next`
+// (kindel.py:405-410) comes from the neighbouring lane by shuffle, the last lane of a warp reads
+// it.  Slot ref_len of every contig holds zero in the weight columns, which is exactly the
+// reference's `except IndexError: aligned_depth_next = 0` at the last position, so the kernel
+// needs no contig table.
+#include "kdl_common.cuh"
+
+namespace kdl {
+
+struct Peers {
+    const int32_t* tab[16];
+    int n;
+};
+
+template <bool kPeers>
+__device__ __forceinline__ int4 load4(const int32_t* __restrict__ counts, const Peers& peers, int col,
+                                      long long n_slots, long long s) {
+    if constexpr (!kPeers) {
+        return __ldg(reinterpret_cast<const int4*>(counts + (long long)col * n_slots + s));
+    } else {
+        int4 acc = make_int4(0, 0, 0, 0);
+        for (int p = 0; p < peers.n; ++p) {
+            // peer tables are written by other GPUs: plain (coherent) loads, not the nc path
+            const int4 v = *reinterpret_cast<const int4*>(peers.tab[p] + (long long)col * n_slots + s);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        return acc;
+    }
+}
+
+template <bool kPeers>
+__device__ __forceinline__ int load1(const int32_t* __restrict__ counts, const Peers& peers, int col,
+                                     long long n_slots, long long s) {
+    if constexpr (!kPeers) {
+        return __ldg(counts + (long long)col * n_slots + s);
+    } else {
+        int acc = 0;
+        for (int p = 0; p < peers.n; ++p) acc += peers.tab[p][(long long)col * n_slots + s];
+        return acc;
+    }
+}
+
+// n_slots % 4 == 0, slot_lo % 4 == 0.  One thread = 4 slots.
+template <bool kPeers>
+__global__ void __launch_bounds__(256)
+vote_kernel(const int32_t* __restrict__ counts, Peers peers, long long n_slots, long long slot_lo,
+            long long slot_hi, long long min_depth_ceil, uint8_t* __restrict__ calls,
+            int32_t* __restrict__ reduced) {
+    const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = slot_lo + quad * 4;
+    const bool active = s < slot_hi;
+    int4 v[KDL_NVOTE_COL];
+    long long d0 = 0;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < KDL_NVOTE_COL; ++k) v[k] = load4<kPeers>(counts, peers, k, n_slots, s);
+        d0 = (long long)v[0].x + v[1].x + v[2].x + v[3].x;
+        if constexpr (kPeers) {
+            if (reduced) {
+#pragma unroll
+                for (int k = 0; k < KDL_NVOTE_COL; ++k)
+                    *reinterpret_cast<int4*>(reduced + (long long)k * n_slots + s) = v[k];
+            }
+        }
+    }
+    // depth of slot s+4 = first slot of the next lane's quad
+    long long dn = __shfl_down_sync(0xffffffffu, d0, 1);
+    if ((threadIdx.x & 31) == 31 || !active || s + 4 >= slot_hi) {
+        dn = 0;
+        if (active && s + 4 < n_slots) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dn += load1<kPeers>(counts, peers, k, n_slots, s + 4);
+        }
+    }
+    if (!active) return;
+    const long long d1 = (long long)v[0].y + v[1].y + v[2].y + v[3].y;
+    const long long d2 = (long long)v[0].z + v[1].z + v[2].z + v[3].z;
+    const long long d3 = (long long)v[0].w + v[1].w + v[2].w + v[3].w;
+    const unsigned c0 = vote_slot(v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, d1, min_depth_ceil);
+    const unsigned c1 = vote_slot(v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, d2, min_depth_ceil);
+    const unsigned c2 = vote_slot(v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, d3, min_depth_ceil);
+    const unsigned c3 = vote_slot(v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, dn, min_depth_ceil);
+    *reinterpret_cast<uint32_t*>(calls + s) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+}
+
+// Derived columns (kindel/kindel.py:83-96, :450): out[5][n_slots].
+__global__ void __launch_bounds__(256)
+derive_kernel(const int32_t* __restrict__ counts, long long n_slots, int32_t* __restrict__ out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    int w[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] = __ldg(counts + (long long)k * n_slots + s);
+    int freq, raw;
+    base_vote(w[0], w[1], w[2], w[3], w[4], &freq, &raw);
+    int csd = 0, ced = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        csd += __ldg(counts + (long long)(KDL_CSW_A + k) * n_slots + s);
+        ced += __ldg(counts + (long long)(KDL_CEW_A + k) * n_slots + s);
+    }
+    out[0 * n_slots + s] = freq;  // aligned_depth - discordant_depth (kindel.py:84-89)
+    out[1 * n_slots + s] = csd;
+    out[2 * n_slots + s] = ced;
+    out[3 * n_slots + s] = csd + ced;
+    out[4 * n_slots + s] = w[0] + w[1] + w[2] + w[3];
+}
+
+template __global__ void vote_kernel<false>(const int32_t*, Peers, long long, long long, long long,
+                                            long long, uint8_t*, int32_t*);
+template __global__ void vote_kernel<true>(const int32_t*, Peers, long long, long long, long long,
+                                           long long, uint8_t*, int32_t*);
+
+}  // namespace kdl

@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py -- aligned bases / second through pileup + consensus (BASELINE.json's metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # this engine, 1 GPU
+    torchrun ... bench.py --gpus N ...                        # read-sharded over N GPUs (NCCL)
+    python bench.py --impl reference ...                      # the reference's CPU path, same metric
+
+A "step" is one pass of the hot path over one batch: zero the count table, K1 pileup over every read,
+(N > 1: sum the vote columns across ranks), K2 vote over every position.
+
+Workload (config.workload): BASELINE.json configs[3], the one the north star's targets are quoted
+on -- synthetic 5 Mb contig, 200x, 150 bp `150M` reads, coordinate-sorted, 1 % substitutions
+(6.67 M reads, 10^9 aligned bases).  For N > 1 the same data set is sharded by read blocks (strong
+scaling: total work fixed).
+
+Numbers on the JSON line:
+  value      whole-job aligned bases/s with the flattened reads already resident in HBM
+             (CUDA events on the launch stream, max over ranks).
+  e2e        the same metric through the C-ABI host-buffer call kdl_ctx_consensus: pinned HOST buffers
+             in, H2D + kernels + D2H of the call bytes inside the timed region.
+  roofline   dominant kernel (K1) against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+  cpu_baseline  the reference's algorithm on this box's host CPU, bounded sample (see --impl reference).
+Input (607 MB) is larger than L2 (126 MB), so no explicit L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "aligned bases/sec through pileup+consensus"
+UNIT = "aligned_bases/s"
+
+WORKLOADS = {
+    # name: (contig lengths, depth)
+    "cfg4_5Mb_200x": ([5_000_000], 200),
+    "cfg2_30kb_2000x": ([30_000], 2000),
+    "cfg5_64x100kb_500x": ([100_000] * 64, 500),
+    "tiny": ([200_000], 50),
+}
+
+
+def make_workload(name, rank=0, world=1):
+    """The rank's shard of the workload: a contiguous block of the coordinate-sorted reads."""
+    from kindel_b200 import bamio, synth
+
+    lens, depth = WORKLOADS[name]
+    full = synth.simple_reads(4, lens, depth)
+    if world == 1:
+        return full, full.aligned_bases
+    # contiguous read blocks inside every contig
+    keep = np.zeros(full.n_reads, dtype=bool)
+    read_off = [0]
+    for c in range(full.n_contigs):
+        lo, hi = int(full.contig_read_off[c]), int(full.contig_read_off[c + 1])
+        a = lo + (hi - lo) * rank // world
+        b = lo + (hi - lo) * (rank + 1) // world
+        keep[a:b] = True
+        read_off.append(read_off[-1] + (b - a))
+    idx = np.flatnonzero(keep)
+    words = (150 + 7) // 8
+    seq4 = full.seq4.reshape(-1, words * 4)[idx].reshape(-1)
+    n = idx.shape[0]
+    shard = bamio.finalize(full.contig_names, full.contig_len, np.array(read_off), full.ref_start[idx],
+                           np.arange(n, dtype=np.int64) * words, full.l_seq[idx], np.arange(n + 1),
+                           full.cigar[idx], seq4, n_records=n)
+    return shard, full.aligned_bases
+
+
+def algorithmic_bytes(batch):
+    """per read ceil(l_seq/2) + 4*n_cigar + 12 read-side bytes (K1);
+    per position 28 B read + 1 B written by the vote (K2)."""
+    lseq = (batch.l_seq.astype(np.int64) & 0x7FFFFFFF)
+    n_cig = np.diff(batch.cig_off.astype(np.int64))
+    k1 = int(((lseq + 1) // 2).sum() + 4 * n_cig.sum() + 12 * batch.n_reads)
+    k2 = int(batch.n_slots) * 29
+    return k1, k2
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------ CPU baselines
+def cpu_port_sample(batch, seconds_target=12.0):
+    """Reference-shaped Python port (oracle/py_oracle.py) on a bounded window of the workload:
+    the reads whose start lies in the first `window` positions, against a contig truncated there."""
+    from oracle import py_oracle
+
+    read_len = 150
+    L0 = int(batch.contig_len[0])
+    window = min(L0, 250_000)
+    hi = int(np.searchsorted(batch.ref_start[: int(batch.contig_read_off[1])], window - read_len, side="right"))
+    recs = py_oracle.records_of(batch, 0, hi)
+    bases = sum(n for r in recs for n, op in r.cigars if op in "M=X")
+    t0 = time.perf_counter()
+    p = py_oracle.pileup(window, recs)
+    py_oracle.vote(p, 1)
+    dt = time.perf_counter() - t0
+    return {"value": bases / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "oracle/py_oracle.py (reference-shaped CPython loop): %d reads / %d aligned bases over the "
+                      "first %d positions of the workload, pileup+post-pass+vote, %.1f s" % (len(recs), bases, window, dt)}
+
+
+def cpu_native_sample(batch):
+    """The C restatement (oracle/kindel_oracle.c), 1 thread, whole shard: what a compiled CPU loop does."""
+    from oracle import coracle
+
+    t0 = time.perf_counter()
+    counts, _ = coracle.pileup(batch)
+    coracle.vote(counts, 1)
+    dt = time.perf_counter() - t0
+    return {"value": batch.aligned_bases / dt, "unit": UNIT, "cores": 1, "kind": "port-native",
+            "sample": "oracle/kindel_oracle.c single thread, full workload, %.2f s" % dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    batch, total = make_workload(args.workload)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_port_sample(batch))
+    best = max(vals, key=lambda v: v["value"])
+    v = statistics.median(x["value"] for x in vals)
+    native = cpu_native_sample(batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "reference is single-threaded CPython (kindel/kindel.py:1-14)"},
+        "cpu_baseline": dict(best, value=v),
+        "cpu_native_port": native,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host": {"nproc": os.cpu_count()},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------- GPU arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    from kindel_b200 import _ffi, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _ffi.load()
+
+    batch, total_bases = make_workload(args.workload, rank, world)
+    db = engine.upload(batch, dev)
+    n_slots = batch.n_slots
+    counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
+    k1_bytes, k2_bytes = algorithmic_bytes(batch)
+
+    def step(timers=None):
+        counts.zero_()
+        if timers:
+            timers[0].record()
+        c, _ = engine.pileup(db, counts, check=False)
+        if timers:
+            timers[1].record()
+        if world > 1:
+            dist.all_reduce(counts[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM)
+        calls = engine.vote(counts, 1)
+        return calls
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.kdl_launch_count()
+    torch.cuda.synchronize()
+    ev0.record()
+    for i in range(args.steps):
+        calls = step(k1_ev[i])
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = lib.kdl_launch_count() - launches0
+    if world > 1:
+        dist.barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    k1_ms = statistics.mean(a.elapsed_time(b) for a, b in k1_ev)
+    t = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, k1_ms_max = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    value = total_bases / (ms_per_step * 1e-3)
+
+    # ---- e2e through the C-ABI host-buffer entry point, pinned host memory ----------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        ctx = engine.HostContext(local)
+        pinned = {}
+        for f in engine._FIELDS:
+            a = np.ascontiguousarray(getattr(batch, f))
+            tpin = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory() if a.size else None
+            pinned[f] = tpin
+        ptr = {f: (int(tp.data_ptr()) if tp is not None else None) for f, tp in pinned.items()}
+        struct = engine.make_struct(batch, ptr)
+        calls_host = torch.empty(n_slots, dtype=torch.uint8).pin_memory()
+        calls_np = calls_host.numpy()
+        e2e_ms = []
+        for i in range(max(2, args.warmup - 1) + args.steps):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            ctx.consensus(batch, 1, calls_out=calls_np, struct=struct)
+            wall = (time.perf_counter() - t0) * 1e3
+            tm = ctx.last_timing()
+            e2e_ms.append((tm["h2d_ms"] + tm["kernel_ms"] + tm["d2h_ms"], wall, tm))
+        e2e_ms = e2e_ms[-args.steps:]
+        dev_ms = statistics.mean(x[0] for x in e2e_ms)
+        wall_ms = statistics.mean(x[1] for x in e2e_ms)
+        tt = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        # every rank copies its own shard in and its calls out; with N > 1 this leg runs the shards
+        # concurrently but does not reduce across ranks (the reduction is in `value`'s step)
+        e2e = {"value": total_bases / (float(tt[0]) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": batch.input_bytes(), "d2h_bytes_per_step": int(n_slots) + 16,
+               "ms_per_step": float(tt[0]), "wall_ms_per_step": float(tt[1]),
+               "breakdown_ms": {k: statistics.mean(x[2][k] for x in e2e_ms) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
+               "api": "kdl_ctx_consensus (include/kindel_b200.h), pinned host buffers"}
+        ctx.close()
+
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        achieved = k1_bytes / (k1_ms_max * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": args.workload, "reads_total": None, "aligned_bases_total": int(total_bases),
+                       "sharding": "contiguous blocks of the coordinate-sorted reads" if world > 1 else "none",
+                       "reduction": "NCCL all_reduce(int32 sum) of the 7 vote columns" if world > 1 else "none",
+                       "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
+            "roofline": {"bound": "hbm", "kernel": "K1 pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms_max},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_port_sample(batch)
+            line["cpu_native_port"] = cpu_native_sample(batch)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4_5Mb_200x")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

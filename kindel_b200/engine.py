@@ -1,0 +1,212 @@
+"""Device side of the pileup/consensus engine: torch tensors as buffers, kernels through the C ABI.
+
+PyTorch is used for device memory, streams and (in `distributed.py`) the NCCL process group only;
+every count and every vote is computed by the hand-written sm_100a kernels in
+`kindel_b200/csrc/` reached through `libkindel_b200.so` (include/kindel_b200.h).  There is no CPU
+implementation behind these functions: without a CUDA device they raise.
+
+    upload(batch)              ReadBatch (host numpy) -> DeviceBatch (device tensors + kdl_batch)
+    pileup(dbatch)             K1: count table [19, n_slots] int32 + insertion events
+    vote(counts, min_depth)    K2: call byte per slot
+    derive(counts)             derived depth columns [5, n_slots]
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .bamio import NIBBLES, ReadBatch
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "kindel_b200 needs a CUDA device (B200, sm_100a): the pileup and the vote exist only as "
+            "CUDA kernels and there is no CPU fallback")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+@dataclass
+class DeviceBatch:
+    host: ReadBatch
+    device: torch.device
+    tensors: dict
+    struct: _ffi.KdlBatch
+
+    @property
+    def n_slots(self) -> int:
+        return self.host.n_slots
+
+
+def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
+    s = _ffi.KdlBatch()
+    s.n_reads = host.n_reads
+    s.n_ops = int(host.cigar.shape[0])
+    s.seq4_bytes = int(host.seq4.shape[0])
+    s.ref_start = ptr["ref_start"]
+    s.seq_off = ptr["seq_off"]
+    s.l_seq = ptr["l_seq"]
+    s.cig_off = ptr["cig_off"]
+    s.cigar = ptr["cigar"]
+    s.seq4 = ptr["seq4"]
+    s.n_contigs = host.n_contigs
+    s.reads_sorted = 1 if host.reads_sorted else 0
+    s.contig_read_off = ptr["contig_read_off"]
+    s.contig_len = ptr["contig_len"]
+    s.contig_slot = ptr["contig_slot"]
+    n_cx = int(host.complex_idx.shape[0])
+    s.n_complex = n_cx
+    s.complex_idx = ptr["complex_idx"] if n_cx else None
+    s.evt_off = ptr["evt_off"] if n_cx else None
+    return s
+
+
+_FIELDS = ("ref_start", "seq_off", "l_seq", "cig_off", "cigar", "seq4", "contig_read_off", "contig_len",
+           "contig_slot", "complex_idx", "evt_off")
+
+
+def host_struct(host: ReadBatch):
+    """kdl_batch over HOST pointers (for the kdl_ctx_* entry points).  Returns (struct, keepalive)."""
+    keep = {f: np.ascontiguousarray(getattr(host, f)) for f in _FIELDS}
+    ptr = {f: (a.ctypes.data if a.size else None) for f, a in keep.items()}
+    return make_struct(host, ptr), keep
+
+
+def upload(host: ReadBatch, device=None, non_blocking: bool = False) -> DeviceBatch:
+    device = require_cuda(device)
+    tensors = {}
+    for f in _FIELDS:
+        a = np.ascontiguousarray(getattr(host, f))
+        if a.dtype == np.uint32:  # torch has no first-class uint32 arithmetic; the bits are what matter
+            a = a.view(np.int32)
+        t = torch.from_numpy(a) if a.size else torch.zeros(4, dtype=torch.from_numpy(a).dtype)
+        tensors[f] = t.to(device, non_blocking=non_blocking)
+    ptr = {f: int(t.data_ptr()) for f, t in tensors.items()}
+    return DeviceBatch(host=host, device=device, tensors=tensors, struct=make_struct(host, ptr))
+
+
+class DataError(Exception):
+    """Carrier for the exception the reference raises on malformed input."""
+
+
+def raise_like_reference(status: int, read: int, nibble: int, op_index: int):
+    if status == _ffi.KDL_ERR_KEY:
+        raise KeyError(NIBBLES[nibble])  # e.g. KeyError('R'): kindel.py:52,72,79
+    raise IndexError("list index out of range (read %d, CIGAR op %d walks off its contig or its SEQ)"
+                     % (read, op_index))
+
+
+def pileup(dbatch: DeviceBatch, counts: torch.Tensor = None, check: bool = True):
+    """K1.  Returns (counts int32[19, n_slots], events int32[n_events, 4]) on the device.
+
+    `counts` may be passed to accumulate several batches / shards into one table.
+    With check=True the error flag is read back (one 16-byte D2H) and, if set, the exact first
+    offending read is located on the device and the reference's exception is raised."""
+    lib = _ffi.load()
+    dev = dbatch.device
+    n_slots = dbatch.n_slots
+    with torch.cuda.device(dev):
+        if counts is None:
+            counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
+        events = torch.empty((max(dbatch.host.n_events, 1), 4), dtype=torch.int32, device=dev)
+        flag = torch.zeros(4, dtype=torch.int32, device=dev)
+        rc = lib.kdl_pileup(C.byref(dbatch.struct), counts.data_ptr(), n_slots, events.data_ptr(),
+                            flag.data_ptr(), _stream_ptr(dev))
+        _ffi.check(rc, "kdl_pileup")
+        if check and int(flag[0].item()) != 0:
+            diagnose_and_raise(dbatch)
+    return counts, events[: dbatch.host.n_events]
+
+
+def diagnose_and_raise(dbatch: DeviceBatch):
+    lib = _ffi.load()
+    dev = dbatch.device
+    diag = torch.zeros(6, dtype=torch.int32, device=dev)  # sizeof(kdl_diag) == 24
+    rc = lib.kdl_diagnose(C.byref(dbatch.struct), diag.data_ptr(), _stream_ptr(dev))
+    _ffi.check(rc, "kdl_diagnose")
+    raw = diag.cpu().numpy().tobytes()
+    d = _ffi.KdlDiag.from_buffer_copy(raw)
+    if d.status:
+        raise_like_reference(d.status, d.read, d.nibble, d.op_index)
+    raise RuntimeError("pileup raised its error flag but no offending read was found")
+
+
+def vote(counts: torch.Tensor, min_depth=1) -> torch.Tensor:
+    """K2.  counts int32[>=7, n_slots] (contiguous) -> calls uint8[n_slots]."""
+    lib = _ffi.load()
+    dev = counts.device
+    n_slots = counts.shape[1]
+    with torch.cuda.device(dev):
+        calls = torch.empty(n_slots, dtype=torch.uint8, device=dev)
+        rc = lib.kdl_vote(counts.data_ptr(), n_slots, int(math.ceil(min_depth)), calls.data_ptr(),
+                          _stream_ptr(dev))
+        _ffi.check(rc, "kdl_vote")
+    return calls
+
+
+def derive(counts: torch.Tensor) -> torch.Tensor:
+    """Derived columns [5, n_slots]: consensus_depth, clip_start_depth, clip_end_depth, clip_depth,
+    acgt_depth (kindel.py:83-96, :450)."""
+    lib = _ffi.load()
+    dev = counts.device
+    n_slots = counts.shape[1]
+    with torch.cuda.device(dev):
+        out = torch.empty((5, n_slots), dtype=torch.int32, device=dev)
+        rc = lib.kdl_derive(counts.data_ptr(), n_slots, out.data_ptr(), _stream_ptr(dev))
+        _ffi.check(rc, "kdl_derive")
+    return out
+
+
+class HostContext:
+    """kdl_ctx_*: host buffers in, host buffers out (the path a non-CUDA host program binds)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _ffi.load()
+        h = C.c_void_p()
+        rc = self._lib.kdl_ctx_create(int(device), C.byref(h))
+        _ffi.check(rc, "kdl_ctx_create")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.kdl_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def consensus(self, host: ReadBatch, min_depth=1, calls_out=None, counts_out=None, events_out=None,
+                  struct=None):
+        """Runs H2D + K1 + K2 + D2H.  Returns calls (numpy uint8[n_slots])."""
+        if struct is None:
+            struct, keep = host_struct(host)
+        if calls_out is None:
+            calls_out = np.empty(host.n_slots, dtype=np.uint8)
+        diag = _ffi.KdlDiag()
+        rc = self._lib.kdl_ctx_consensus(
+            self._h, C.byref(struct), host.n_slots, host.n_events, int(math.ceil(min_depth)),
+            calls_out.ctypes.data, counts_out.ctypes.data if counts_out is not None else None,
+            events_out.ctypes.data if (events_out is not None and host.n_events) else None, C.byref(diag))
+        if rc in (_ffi.KDL_ERR_INDEX, _ffi.KDL_ERR_KEY):
+            raise_like_reference(rc, diag.read, diag.nibble, diag.op_index)
+        _ffi.check(rc, "kdl_ctx_consensus")
+        return calls_out
+
+    def last_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self._lib.kdl_ctx_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c))
+        return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}

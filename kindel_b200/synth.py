@@ -1,0 +1,195 @@
+"""Seeded synthetic alignments of the BASELINE.json shapes, built directly in the flattened layout.
+
+    simple_reads(...)    coordinate-sorted `nM` short reads over one or more random contigs
+                         (configs 2, 4, 5: 30 kb x 2000x, 5 Mb x 200x, 64 x 100 kb x 500x)
+    complex_reads(...)   indel- and soft-clip-heavy CIGARs plus a tail of edge-case reads (config 3)
+
+Reads copy the contig's bases on M segments with a substitution rate (to A/C/G/T/N uniformly);
+inserted and clipped bases are random.  Everything is vectorised numpy so the 5 Mb x 200x case
+(6.7 M reads, 10^9 aligned bases) is generated in well under a minute; generation is not part of
+any timed region.  `to_records` turns a (small) batch back into BAM-writer records so tests can
+push the same data through a real .bam file.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import bamio
+
+_CODE = np.array([1, 2, 4, 8, 15], dtype=np.uint8)  # A C G T N nibbles
+
+
+def random_contig(rng, length: int) -> np.ndarray:
+    """uint8 nibble codes (1,2,4,8) of a uniform random ACGT contig."""
+    return _CODE[rng.integers(0, 4, size=length, dtype=np.uint8)]
+
+
+def _pack_rows(nib: np.ndarray) -> np.ndarray:
+    """[n, w] nibble codes (w % 8 == 0) -> [n, w/2] packed bytes, high nibble first."""
+    return ((nib[:, 0::2] << 4) | nib[:, 1::2]).astype(np.uint8)
+
+
+def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_rate: float = 0.01,
+                 chunk: int = 1 << 18) -> bamio.ReadBatch:
+    """`read_len`M reads, uniformly placed, sorted by start inside each contig."""
+    rng = np.random.default_rng(seed)
+    contig_lens = [int(x) for x in contig_lens]
+    words = (read_len + 7) // 8
+    row_bytes = words * 4
+    ref_start_all, seq_rows, read_off = [], [], [0]
+    for L in contig_lens:
+        n = int(round(depth * L / read_len))
+        ref = random_contig(rng, L)
+        ref_pad = np.concatenate([ref, np.zeros(words * 8, dtype=np.uint8)])
+        starts = np.sort(rng.integers(0, L - read_len + 1, size=n, dtype=np.int64))
+        for s0 in range(0, n, chunk):
+            st = starts[s0:s0 + chunk]
+            idx = st[:, None] + np.arange(words * 8, dtype=np.int64)[None, :]
+            nib = ref_pad[idx]
+            nib[:, read_len:] = 0
+            if sub_rate > 0:
+                n_sub = rng.binomial(st.shape[0] * read_len, sub_rate)
+                rr = rng.integers(0, st.shape[0], size=n_sub)
+                cc = rng.integers(0, read_len, size=n_sub)
+                nib[rr, cc] = _CODE[rng.integers(0, 5, size=n_sub)]
+            seq_rows.append(_pack_rows(nib))
+        ref_start_all.append(starts)
+        read_off.append(read_off[-1] + n)
+    ref_start = np.concatenate(ref_start_all)
+    n = ref_start.shape[0]
+    seq4 = np.concatenate(seq_rows).reshape(-1)
+    seq_off = np.arange(n, dtype=np.int64) * words
+    l_seq = np.full(n, read_len, dtype=np.int64)
+    cig_off = np.arange(n + 1, dtype=np.int64)
+    cigar = np.full(n, read_len << 4, dtype=np.int64)
+    names = ["ctg%d" % i for i in range(len(contig_lens))]
+    return bamio.finalize(names, np.array(contig_lens), np.array(read_off), ref_start, seq_off, l_seq, cig_off,
+                          cigar, seq4, n_records=n)
+
+
+def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150, sub_rate: float = 0.01,
+                  edge_tail: bool = True) -> bamio.ReadBatch:
+    """Config-3 shape: per read p=0.5 leading soft clip (1-29), p=0.5 trailing soft clip (1-29),
+    0-3 indel events (I or D, length 1-4) between M segments; query length is always `read_len`.
+    With edge_tail a few hundred reads using N / = / X / H / P ops, H-then-S, clips overhanging
+    both contig ends and POS == 0 are appended (all legal for the reference, no exceptions)."""
+    rng = np.random.default_rng(seed)
+    L = int(contig_len)
+    n = int(round(depth * L / read_len))
+    lead = np.where(rng.random(n) < 0.5, rng.integers(1, 30, size=n), 0)
+    trail = np.where(rng.random(n) < 0.5, rng.integers(1, 30, size=n), 0)
+    n_ev = rng.integers(0, 4, size=n)
+    ev_is_ins = rng.random((n, 3)) < 0.5
+    ev_len = rng.integers(1, 5, size=(n, 3))
+    ev_on = np.arange(3)[None, :] < n_ev[:, None]
+    ins_total = (ev_len * (ev_is_ins & ev_on)).sum(axis=1)
+    del_total = (ev_len * (~ev_is_ins & ev_on)).sum(axis=1)
+    m_total = read_len - lead - trail - ins_total  # aligned bases
+    # split m_total into n_ev + 1 segments, each >= 10
+    cuts = np.sort(rng.random((n, 3)), axis=1)
+    cuts = np.where(ev_on, cuts, 1.0)
+    spare = m_total - 10 * (n_ev + 1)
+    bounds = np.concatenate([np.zeros((n, 1)), cuts, np.ones((n, 1))], axis=1)
+    seg = np.floor(np.diff(bounds, axis=1) * spare[:, None]).astype(np.int64)
+    seg_on = np.arange(4)[None, :] <= n_ev[:, None]
+    seg = np.where(seg_on, seg + 10, 0)
+    seg[np.arange(n), n_ev] += m_total - seg.sum(axis=1)  # rounding remainder into the last segment
+    ref_span = m_total + del_total
+    start = np.sort(rng.integers(0, np.maximum(L - ref_span.max() - 1, 1), size=n))
+
+    # ops as an [n, 9] grid: S, M0, E0, M1, E1, M2, E2, M3, S
+    op_len = np.zeros((n, 9), dtype=np.int64)
+    op_code = np.zeros((n, 9), dtype=np.int64)
+    op_len[:, 0], op_code[:, 0] = lead, 4
+    op_len[:, 8], op_code[:, 8] = trail, 4
+    for k in range(4):
+        op_len[:, 1 + 2 * k] = seg[:, k]
+    for k in range(3):
+        op_len[:, 2 + 2 * k] = np.where(ev_on[:, k], ev_len[:, k], 0)
+        op_code[:, 2 + 2 * k] = np.where(ev_is_ins[:, k], 1, 2)
+    on = op_len > 0
+    n_ops = on.sum(axis=1)
+    cigar = ((op_len << 4) | op_code)[on]
+    cig_off = np.concatenate([[0], np.cumsum(n_ops)])
+
+    # bases: random everywhere, reference copy (+ substitutions) on M segments
+    ref = random_contig(rng, L)
+    words = (read_len + 7) // 8
+    nib = _CODE[rng.integers(0, 4, size=(n, words * 8), dtype=np.uint8)]
+    nib[:, read_len:] = 0
+    consumes_q = np.isin(op_code, (0, 1, 4))
+    consumes_r = np.isin(op_code, (0, 2))
+    q_begin = np.cumsum(np.where(consumes_q, op_len, 0), axis=1) - np.where(consumes_q, op_len, 0)
+    r_begin = start[:, None] + np.cumsum(np.where(consumes_r, op_len, 0), axis=1) - np.where(consumes_r, op_len, 0)
+    for k in range(4):
+        col = 1 + 2 * k
+        ln = op_len[:, col]
+        rows = np.repeat(np.arange(n), ln)
+        within = np.arange(ln.sum()) - np.repeat(np.cumsum(ln) - ln, ln)
+        nib[rows, np.repeat(q_begin[:, col], ln) + within] = ref[np.repeat(r_begin[:, col], ln) + within]
+    n_sub = rng.binomial(n * read_len, sub_rate)
+    nib[rng.integers(0, n, size=n_sub), rng.integers(0, read_len, size=n_sub)] = _CODE[rng.integers(0, 5, size=n_sub)]
+    seq_rows = [_pack_rows(nib)]
+    ref_start = [start]
+    l_seq = [np.full(n, read_len, dtype=np.int64)]
+    cig_parts = [cigar]
+    cig_counts = [n_ops]
+
+    if edge_tail:
+        tail = []  # (pos0, [(len, op)], seq length)
+        for k in range(64):
+            p = int(rng.integers(100, L - 400))
+            tail += [
+                (p, [(20, 0), (7, 3), (30, 0)], 50),                # N is a no-op
+                (p, [(5, 5), (10, 7), (3, 8), (20, 0), (4, 5)], 33),  # H = X M H
+                (p, [(3, 5), (6, 4), (25, 0)], 31),                 # H then S: treated as right clip
+                (p, [(12, 0), (2, 6), (12, 0), (5, 4)], 29),        # P no-op, trailing S
+                (p, [(10, 0), (4, 4), (10, 0)], 24),                # mid-CIGAR S
+            ]
+        tail += [(-1, [(30, 0)], 30), (0, [(25, 4), (30, 0)], 55), (3, [(25, 4), (30, 0)], 55),
+                 (L - 20, [(20, 0), (15, 4)], 35), (L - 10, [(10, 0), (1, 1), (9, 4)], 20),
+                 (L - 5, [(5, 0), (2, 1)], 7), (L - 30, [(28, 0), (2, 2)], 28), (-1, [(3, 1), (4, 4)], 7)]
+        t_start = np.array([t[0] for t in tail], dtype=np.int64)
+        t_len = np.array([t[2] for t in tail], dtype=np.int64)
+        t_words = (int(t_len.max()) + 7) // 8
+        t_nib = _CODE[rng.integers(0, 5, size=(len(tail), t_words * 8), dtype=np.uint8)]
+        t_nib[np.arange(t_words * 8)[None, :] >= t_len[:, None]] = 0
+        packed = _pack_rows(t_nib)
+        if t_words < words:
+            packed = np.concatenate([packed, np.zeros((len(tail), (words - t_words) * 4), dtype=np.uint8)], axis=1)
+        elif t_words > words:
+            raise ValueError("edge-tail reads longer than read_len are not laid out here")
+        seq_rows.append(packed)
+        ref_start.append(t_start)
+        l_seq.append(t_len)
+        cig_parts.append(np.array([(ln << 4) | op for t in tail for ln, op in t[1]], dtype=np.int64))
+        cig_counts.append(np.array([len(t[1]) for t in tail], dtype=np.int64))
+
+    ref_start = np.concatenate(ref_start)
+    l_seq = np.concatenate(l_seq)
+    n_all = ref_start.shape[0]
+    counts = np.concatenate(cig_counts)
+    cig_off = np.concatenate([[0], np.cumsum(counts)])
+    seq4 = np.concatenate(seq_rows).reshape(-1)
+    seq_off = np.arange(n_all, dtype=np.int64) * words
+    return bamio.finalize(["ctg0"], np.array([L]), np.array([0, n_all]), ref_start, seq_off, l_seq, cig_off,
+                          np.concatenate(cig_parts), seq4, n_records=n_all)
+
+
+def to_records(batch: bamio.ReadBatch):
+    """(contigs, records) for bamio.write_bam -- small batches only (Python loop)."""
+    contigs = list(zip(batch.contig_names, (int(x) for x in batch.contig_len)))
+    recs = []
+    for c in range(batch.n_contigs):
+        for r in range(int(batch.contig_read_off[c]), int(batch.contig_read_off[c + 1])):
+            lraw = int(batch.l_seq[r])
+            words = batch.cigar[int(batch.cig_off[r]):int(batch.cig_off[r + 1])].tolist()
+            lseq = lraw & 0x7FFFFFFF if lraw < 0 else sum(w >> 4 for w in words if (w & 15) in (0, 1, 4, 7, 8))
+            base = int(batch.seq_off[r]) * 4
+            by = batch.seq4[base:base + (lseq + 1) // 2]
+            chars = []
+            for b in by.tolist():
+                chars.append(bamio.NIBBLES[b >> 4])
+                chars.append(bamio.NIBBLES[b & 15])
+            recs.append((c, int(batch.ref_start[r]), 0, words, "".join(chars[:lseq])))
+    return contigs, recs

@@ -1,0 +1,54 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/kindel_b200.h declares."""
+import ctypes
+import os
+import re
+
+from helpers import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kindel_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kdl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_bound_and_exported():
+    from kindel_b200 import _ffi
+
+    names = declared_symbols()
+    assert len(names) >= 14
+    assert sorted(_ffi.EXPORTED_SYMBOLS) == names
+    lib = ctypes.CDLL(_ffi.lib_path())
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_abi_version_and_status_strings():
+    from kindel_b200 import _ffi
+
+    lib = _ffi.load()
+    assert lib.kdl_abi_version() == 1
+    assert _ffi.status_string(0) == "ok"
+    assert "IndexError" in _ffi.status_string(_ffi.KDL_ERR_INDEX)
+    assert "KeyError" in _ffi.status_string(_ffi.KDL_ERR_KEY)
+    assert lib.kdl_launch_count() == 0 or lib.kdl_launch_count() > 0
+
+
+def test_struct_layouts_match_the_header():
+    from kindel_b200 import _ffi
+
+    # kdl_batch: 3 x i64, 6 ptr, 2 x i32, 3 ptr, i64, 2 ptr = 17 eight-byte words - 1 (two i32 share one)
+    assert ctypes.sizeof(_ffi.KdlBatch) == 8 * 16
+    assert ctypes.sizeof(_ffi.KdlDiag) == 24
+
+
+def test_engine_refuses_to_run_without_cuda():
+    import pytest
+    import torch
+
+    from kindel_b200 import engine
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        engine.require_cuda()

@@ -1,0 +1,231 @@
+"""Parity of the CUDA engine, through the C ABI, with
+  * the golden vectors produced by the unmodified reference (tests/golden/),
+  * the CPU oracle on seeded synthetic inputs of the BASELINE.json shapes (full size for configs 2, 3
+    and -- marked slow only by its 10^9 bases -- config 4), plus size-independent invariants.
+Bit-exact everywhere: this path is integer / byte work."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+from conftest import golden_input
+from test_host_logic import assert_frame_matches
+
+pytestmark = pytest.mark.gpu
+
+
+def engine_tables(batch):
+    import torch
+
+    from kindel_b200 import engine
+
+    db = engine.upload(batch)
+    counts, events = engine.pileup(db)
+    torch.cuda.synchronize()
+    return db, counts, events
+
+
+def test_native_library_is_the_one_running():
+    from kindel_b200 import _ffi, engine
+
+    lib = _ffi.load()
+    before = lib.kdl_launch_count()
+    from kindel_b200 import synth
+
+    b = synth.simple_reads(0, [2000], 20)
+    engine_tables(b)
+    assert lib.kdl_launch_count() > before
+    assert os.path.basename(_ffi.lib_path()) == "libkindel_b200.so"
+
+
+def test_golden_files_full_api(manifest, golden_npz):
+    from kindel_b200 import kindel as K
+
+    for name, entry in manifest["files"].items():
+        path = golden_input(entry)
+        alns = K.parse_bam(path)
+        g = golden_npz(name)
+        assert list(alns) == [c["name"] for c in entry["contigs"]]
+        for c, (ctg, aln) in enumerate(alns.items()):
+            np.testing.assert_array_equal(aln.table, g["c%d_counts" % c], err_msg=name)
+            np.testing.assert_array_equal(aln.consensus_depth, g["c%d_consensus_depth" % c])
+            np.testing.assert_array_equal(np.array(aln.clip_start_depth), g["c%d_clip_start_depth" % c])
+            np.testing.assert_array_equal(np.array(aln.clip_end_depth), g["c%d_clip_end_depth" % c])
+            np.testing.assert_array_equal(np.array(aln.clip_depth), g["c%d_clip_depth" % c])
+            want = {i: [tuple(kv) for kv in items] for i, items in entry["contigs"][c]["insertions"]}
+            for i in range(len(aln.insertions)):
+                d = aln.insertions[i]
+                assert list(d.items()) == want.get(i, []), (name, i)
+        for tag, realign, md, trim, upper in (("plain", False, 1, False, False), ("realign", True, 1, False, False),
+                                              ("opts", False, 5, True, True)):
+            res = K.bam_to_consensus(path, realign, md, 7, 0.1, 50, trim, upper)
+            want = entry["runs"][tag]
+            assert [[r.name, r.sequence] for r in res.consensuses] == want["fasta"], (name, tag)
+            for ctg, ch in res.refs_changes.items():
+                assert "".join("-" if c is None else c for c in ch) == want["changes"][ctg]
+        assert_frame_matches(K.weights(path), g, "w_")
+        assert_frame_matches(K.weights(path, True, True, 0.05), g, "wrel_")
+        if entry["features_error"]:
+            with pytest.raises(IndexError):
+                K.features(path)
+        else:
+            assert_frame_matches(K.features(path), g, "f_")
+
+
+def test_known_answer_integers(manifest):  # reference tests/test_kindel.py:63-89, through the GPU
+    from kindel_b200 import kindel as K
+
+    a = list(K.parse_bam(golden_input(manifest["files"]["bwa_1_1"])).values())[0]
+    b = list(K.parse_bam(golden_input(manifest["files"]["ext_3_bc75"])).values())[0]
+    assert a.ref_id == "ENA|EU155341|EU155341.2" and len(a.weights) == 9306
+    assert a.weights[0]["A"] == 22 and a.weights[23]["A"] == 57
+    assert b.weights[68]["G"] == 1 and b.weights[2368]["T"] == 13
+    assert [b.deletions[i] for i in (399, 402, 411, 1048, 1049, 1050)] == [14, 14, 15, 14, 14, 14]
+    assert b.clip_ends[1748] == 12 and a.clip_starts[525] == 16 and a.clip_starts[1437] == 84
+    assert sum(b.insertions[453].values()) == 14 and sum(b.insertions[457].values()) == 14
+
+
+def test_edge_cases_and_exceptions(manifest, tmp_path):
+    from kindel_b200 import kindel as K
+
+    for case in manifest["edge_cases"]:
+        p = tmp_path / (case["name"] + ".sam")
+        p.write_text(case["sam"])
+        if case["raises"]:
+            kind, args = case["raises"]
+            with pytest.raises({"IndexError": IndexError, "KeyError": KeyError}[kind]) as exc:
+                K.parse_bam(p)
+            if kind == "KeyError":
+                assert [str(a) for a in exc.value.args] == args, case["name"]
+            continue
+        alns = K.parse_bam(p)
+        assert list(alns) == case["contigs"]
+        aln = alns["ctg"]
+        np.testing.assert_array_equal(aln.table, np.array(case["counts"]), err_msg=case["name"])
+        want = {i: [tuple(kv) for kv in items] for i, items in case["insertions"]}
+        for i in range(len(aln.insertions)):
+            assert list(aln.insertions[i].items()) == want.get(i, []), case["name"]
+        for md in (1, 3):
+            res = K.bam_to_consensus(p, False, md, 7, 0.1, 50, False, False)
+            assert [[r.name, r.sequence] for r in res.consensuses] == case["fasta_min_depth_%d" % md], case["name"]
+            # public consensus_sequence on the views == same answer
+            seq, ch = K.consensus_sequence(aln.weights, aln.insertions, aln.deletions, None, False, md, False)
+            assert seq == case["fasta_min_depth_%d" % md][0][1]
+            assert "".join("-" if c is None else c for c in ch) == case["changes_min_depth_%d" % md]
+
+
+def test_parse_records_and_plain_dict_inputs():
+    """parse_records on record objects; consensus_sequence on plain lists of dicts (a user's own tables)."""
+    from kindel_b200 import kindel as K
+    from oracle import samdecode
+
+    recs = [samdecode.Record("a", 0, "c", 5, "acgTTTTGGAAACCttt", ((3, "S"), (4, "M"), (2, "I"), (3, "M"), (2, "D"), (2, "M"), (3, "S"))),
+            samdecode.Record("b", 4, "c", 5, "ACGT", ((4, "M"),)), samdecode.Record("c", 0, "c", 1, "A", ((1, "M"),))]
+    aln = K.parse_records("c", 20, recs)
+    assert aln.weights[4]["T"] == 1 and aln.weights[8]["A"] == 1 and aln.deletions[11] == 1
+    assert aln.insertions[8] == {"GG": 1} and aln.clip_ends[4] == 1 and aln.clip_starts[14] == 1
+    weights = [{"A": 10, "T": 0, "G": 0, "C": 0, "N": 0}, {"A": 0, "T": 0, "G": 0, "C": 10, "N": 0},
+               {"A": 0, "T": 0, "G": 4, "C": 0, "N": 6}, {"A": 5, "T": 5, "G": 0, "C": 0, "N": 0},
+               {"A": 0, "T": 0, "G": 0, "C": 0, "N": 0}, {"A": 1, "T": 0, "G": 0, "C": 0, "N": 0},
+               {"A": 0, "T": 0, "G": 0, "C": 0, "N": 3}, {"A": 10, "T": 0, "G": 0, "C": 0, "N": 0}]
+    ins = [{}, {"GG": 6}, {}, {"T": 3, "C": 3}, {}, {}, {}, {"AC": 1}, {}]
+    dele = [6, 0, 0, 0, 0, 1, 0, 0, 0]
+    seq, ch = K.consensus_sequence(weights, ins, dele, None, False, 1, False)
+    assert seq == "ggCNNNNNacA" and ch == ["D", "I", None, "I", "N", "D", "N", "I"]
+
+
+def _against_oracle(batch, min_depth=1):
+    import torch
+
+    from kindel_b200 import engine
+    from oracle import coracle
+
+    db, counts, events = engine_tables(batch)
+    calls = engine.vote(counts, min_depth)
+    derived = engine.derive(counts)
+    oc, oe = coracle.pileup(batch)
+    np.testing.assert_array_equal(counts.cpu().numpy(), oc)
+    np.testing.assert_array_equal(events.cpu().numpy(), oe)
+    np.testing.assert_array_equal(calls.cpu().numpy(), coracle.vote(oc, min_depth))
+    np.testing.assert_array_equal(derived.cpu().numpy(), coracle.derive(oc))
+    # invariants that do not need an oracle
+    c = counts.cpu().numpy()
+    assert int(c[0:5].sum()) == batch.aligned_bases
+    assert int(c[6].sum()) == batch.n_events
+    return c
+
+
+def test_synthetic_config2_full_size():
+    from kindel_b200 import synth
+
+    _against_oracle(synth.simple_reads(1, [30000], 2000))
+
+
+def test_synthetic_config3_full_size_with_edge_tail():
+    from kindel_b200 import synth
+
+    b = synth.complex_reads(3, 30000, 5000)
+    assert b.n_reads > 1_000_000 and len(b.complex_idx) > 900_000
+    _against_oracle(b, min_depth=3)
+
+
+def test_synthetic_multi_contig():
+    from kindel_b200 import synth
+
+    _against_oracle(synth.simple_reads(5, [100000] * 8, 100))
+
+
+def test_unsorted_input_is_legal():
+    from kindel_b200 import bamio, synth
+
+    b = synth.simple_reads(7, [20000, 30000], 300)
+    rng = np.random.default_rng(0)
+    parts = []
+    for c in range(2):
+        lo, hi = int(b.contig_read_off[c]), int(b.contig_read_off[c + 1])
+        parts.append(lo + rng.permutation(hi - lo))
+    perm = np.concatenate(parts)
+    n = b.n_reads
+    shuffled = bamio.finalize(b.contig_names, b.contig_len, b.contig_read_off, b.ref_start[perm], b.seq_off[perm],
+                              b.l_seq[perm], np.arange(n + 1), b.cigar[perm], b.seq4)
+    assert not shuffled.reads_sorted
+    _, c0, _ = engine_tables(b)
+    _, c1, _ = engine_tables(shuffled)
+    np.testing.assert_array_equal(c0.cpu().numpy(), c1.cpu().numpy())
+    _against_oracle(shuffled)
+
+
+def test_host_buffer_entry_point():
+    """kdl_ctx_consensus: host pointers in, host buffers out, including the error path."""
+    from kindel_b200 import bamio, engine, synth
+    from oracle import coracle
+
+    ctx = engine.HostContext(0)
+    for b in (synth.complex_reads(21, 20000, 200), synth.simple_reads(22, [50000], 100)):
+        counts = np.empty((19, b.n_slots), dtype=np.int32)
+        events = np.empty((max(b.n_events, 1), 4), dtype=np.int32)
+        calls = ctx.consensus(b, 2, counts_out=counts, events_out=events)
+        oc, oe = coracle.pileup(b)
+        np.testing.assert_array_equal(counts, oc)
+        np.testing.assert_array_equal(events[: b.n_events], oe)
+        np.testing.assert_array_equal(calls, coracle.vote(oc, 2))
+        t = ctx.last_timing()
+        assert t["h2d_ms"] > 0 and t["kernel_ms"] > 0
+    bad = synth.simple_reads(23, [5000], 20)
+    bad.seq4[7] = 0x33  # nibble 3 = 'M' (IUPAC): KeyError('M') in the reference
+    with pytest.raises(KeyError) as exc:
+        ctx.consensus(bad, 1)
+    assert exc.value.args == ("M",)
+    ctx.close()
+
+
+def test_synthetic_config4_full_size():
+    """5 Mb x 200x, 10^9 aligned bases: engine == oracle bit for bit, plus invariants."""
+    from kindel_b200 import synth
+
+    b = synth.simple_reads(4, [5_000_000], 200)
+    assert b.aligned_bases >= 999_000_000
+    c = _against_oracle(b)
+    depth = c[0:5].sum(axis=0)
+    assert abs(float(depth[1000:-1000].mean()) - 200.0) < 1.0

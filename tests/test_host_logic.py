@@ -1,0 +1,169 @@
+"""Host-side halves of the API (string assembly, --realign reassembly, report, weights/features float
+tails, CLI) checked against the reference's golden outputs.  The count tables fed in here come from
+the CPU oracle (test infrastructure), so this runs without a GPU; the `-m gpu` tests feed the same
+host code from the CUDA engine."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import golden_input
+from kindel_b200 import bamio, cli
+from kindel_b200 import kindel as K
+from oracle import coracle
+
+
+def oracle_run(path):
+    batch = bamio.read_alignment(path)
+    counts, events = coracle.pileup(batch)
+    return K.PileupRun.from_host_tables(batch, counts, coracle.derive(counts), events), counts
+
+
+def frame_from_golden(g, prefix):
+    cols = [str(c) for c in g[prefix + "__columns"]]
+    return pd.DataFrame({c: g[prefix + c] for c in cols}, columns=cols)
+
+
+def assert_frame_matches(df, g, prefix):
+    want = frame_from_golden(g, prefix)
+    assert list(df.columns) == list(want.columns)
+    assert len(df) == len(want)
+    for c in want.columns:
+        a, b = df[c].to_numpy(), want[c].to_numpy()
+        if b.dtype.kind in "US":
+            assert a.astype(str).tolist() == b.astype(str).tolist(), c
+        else:
+            assert a.dtype == b.dtype, (c, a.dtype, b.dtype)
+            np.testing.assert_array_equal(a, b, err_msg=prefix + c)  # NaN == NaN here; bit-exact otherwise
+
+
+def test_unit_consensus():  # reference tests/test_kindel.py:25-32
+    w = {"A": 1, "C": 2, "G": 3, "T": 4, "N": 5}
+    assert K.consensus(w) == ("N", 5, 0.33, False)
+    assert K.consensus({"A": 5, "C": 5, "G": 3, "T": 4, "N": 1})[3] is True
+    assert K.consensus({"A": 0, "T": 0, "G": 0, "C": 0, "N": 0}) == ("N", 0, 0, False)
+    assert K.consensus({"A": 2, "T": 2, "G": 0, "C": 0, "N": 0}) == ("A", 2, 0.5, True)
+    assert K.consensus({"A": 0, "T": 0, "G": 3, "C": 3, "N": 0})[0] == "G"
+    assert K.consensus({}) == ("N", 0, 0, False)
+
+
+def test_unit_merge_by_lcs():  # reference tests/test_kindel.py:35-53
+    one = ("AACTGCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGG",
+           "GCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGGCGCTAAGCAGAACA")
+    two = ("AACTGCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGGCGCTAAGCAGAACATC",
+           "GCAGATACCTACACCACCGGGGGAACTGCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGGCGCTAAGCAGAACA")
+    want = "AACTGCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGGCGCTAAGCAGAACA"
+    assert K.merge_by_lcs(*one, min_overlap=7) == want
+    assert K.merge_by_lcs(*two, min_overlap=7) == want
+    assert K.merge_by_lcs("AT", "CG", min_overlap=7) is None
+
+
+def test_cdrp_consensuses_known_strings(manifest):  # reference tests/test_kindel.py:92-111
+    run, _ = oracle_run(golden_input(manifest["files"]["bwa_1_1"]))
+    aln = run.alignment(0)
+    cdrps = K.cdrp_consensuses(aln.weights, aln.deletions, aln.clip_start_weights, aln.clip_end_weights,
+                               aln.clip_start_depth, aln.clip_end_depth, 0.1, 10)
+    assert cdrps[0][0].seq == "AACTGCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGGCGCTAAGCAGAACATCCAGCTGATCAACA"
+    assert cdrps[0][1].seq == ("AGCGTCGATGCAGATACCTACACCACCGGGGGAACTGCCGCTAGGGGCGCGTTCGGGCTCGCCAACATCTTCAGTCCGGG"
+                               "CGCTAAGCAGAACA")
+
+
+def test_known_answer_integers_through_the_views(manifest):  # reference tests/test_kindel.py:63-89
+    a = oracle_run(golden_input(manifest["files"]["bwa_1_1"]))[0].alignment(0)
+    b = oracle_run(golden_input(manifest["files"]["ext_3_bc75"]))[0].alignment(0)
+    assert a.ref_id == "ENA|EU155341|EU155341.2" and len(a.weights) == 9306
+    assert a.weights[0]["A"] == 22 and a.weights[23]["A"] == 57
+    assert b.weights[68]["G"] == 1 and b.weights[2368]["T"] == 13
+    assert [b.deletions[i] for i in (399, 402, 411, 1048, 1049, 1050)] == [14, 14, 15, 14, 14, 14]
+    assert b.clip_ends[1748] == 12 and a.clip_starts[525] == 16 and a.clip_starts[1437] == 84
+    assert sum(b.insertions[452 + 1].values()) == 14 and sum(b.insertions[456 + 1].values()) == 14
+    # namedtuple behaviour of the reference's `alignment`
+    ref_id, weights, insertions, deletions, *rest = a
+    assert ref_id == a.ref_id and len(rest) == 8 and a[1] is a.weights
+    assert list(a.weights[0].keys()) == ["A", "T", "G", "C", "N"]
+    assert len(a.weights[9300:]) == 6 and len(a.insertions) == 9307 and len(a.deletions) == 9307
+
+
+def test_consensus_report_changes_against_golden(manifest):
+    for name, entry in manifest["files"].items():
+        path = golden_input(entry)
+        run, counts = oracle_run(path)
+        for tag, realign, md, trim, upper in (("plain", False, 1, False, False), ("realign", True, 1, False, False),
+                                              ("opts", False, 5, True, True)):
+            res = K.consensus_from_run(run, coracle.vote(counts, md), "X", realign, md, 7, 0.1, 50, trim, upper)
+            want = entry["runs"][tag]
+            assert [[r.name, r.sequence] for r in res.consensuses] == want["fasta"], (name, tag)
+            for ctg, ch in res.refs_changes.items():
+                assert "".join("-" if c is None else c for c in ch) == want["changes"][ctg]
+            for ctg, rep in res.refs_reports.items():
+                # the report echoes the input path; everything else must be identical
+                exp = want["reports"][ctg].splitlines()
+                got = rep.splitlines()
+                assert len(exp) == len(got)
+                assert [l for l in got if not l.startswith("- bam_path")] == [l for l in exp if not l.startswith("- bam_path")]
+
+
+def test_weights_and_features_frames_against_golden(manifest, golden_npz):
+    for name, entry in manifest["files"].items():
+        run, _ = oracle_run(golden_input(entry))
+        g = golden_npz(name)
+        assert_frame_matches(K.weights_from_run(run), g, "w_")
+        assert_frame_matches(K.weights_from_run(run, True, True, 0.05), g, "wrel_")
+        if entry["features_error"]:
+            with pytest.raises(IndexError):
+                K.features_from_run(run)
+        else:
+            assert_frame_matches(K.features_from_run(run), g, "f_")
+
+
+def test_assemble_with_cdr_patches_and_skips():
+    calls = np.array([0, 1, 2, 3, 0x14, 0x24, 0x31, 0, 1, 2], dtype=np.uint8)  # A C G T D N I+C A C G
+    look = lambda p: ("GG", False)
+    seq, ch = K.assemble_consensus(calls, look)
+    assert seq == "ACGTNggCACG" and ch == [None, None, None, None, "D", "N", "I", None, None, None]
+    R = K.Region
+    seq, ch = K.assemble_consensus(calls, look, [R(2, 5, "TTTT", None)])
+    assert seq == "ACttttNggCACG" and ch[2:5] == [None, None, None]
+    seq, _ = K.assemble_consensus(calls, look, [R(2, 5, None, None)])  # falsy seq: ignored
+    assert seq == "ACGTNggCACG"
+    seq, _ = K.assemble_consensus(calls, look, [R(2, 2, "TT", None)])  # zero span: reference never recovers
+    assert seq == "ACtt"
+    seq, _ = K.assemble_consensus(np.array([4, 4, 0, 4], dtype=np.uint8), look, None, True, False)
+    assert seq == "A"
+    seq, _ = K.assemble_consensus(calls, lambda p: ("GG", True), None, False, True)
+    assert seq == "ACGTNNCACG"
+
+
+def test_cli_flag_surface():
+    p = cli.build_parser()
+    a = p.parse_args(["consensus", "x.bam"])
+    assert (a.realign, a.min_depth, a.min_overlap, a.clip_decay_threshold, a.mask_ends, a.trim_ends, a.uppercase) == (
+        False, 1, 7, 0.1, 50, False, False)
+    a = p.parse_args(["consensus", "-r", "--min-depth", "3", "--min-overlap", "9", "-c", "0.2", "--mask-ends", "10",
+                      "-t", "-u", "x.bam"])
+    assert (a.realign, a.min_depth, a.min_overlap, a.clip_decay_threshold, a.mask_ends, a.trim_ends, a.uppercase) == (
+        True, 3, 9, 0.2, 10, True, True)
+    a = p.parse_args(["weights", "-r", "--confidence-alpha", "0.05", "x.bam"])
+    assert a.relative and a.confidence and a.confidence_alpha == 0.05
+    assert cli.version() == "kindel 1.2.1"
+    import kindel
+    assert kindel.__version__ == "1.2.1" and kindel.kindel.bam_to_consensus is K.bam_to_consensus
+
+
+def test_bam_writer_reader_roundtrip(tmp_path):
+    from kindel_b200 import synth
+
+    batch = synth.complex_reads(11, 5000, 30)
+    contigs, recs = synth.to_records(batch)
+    recs.insert(3, (-1, -1, 4, [], "ACGT"))         # unmapped, rname *
+    recs.insert(5, (0, 10, 4, [], "ACGT"))          # unmapped but placed: filtered
+    recs.insert(7, (0, 10, 256, [(4 << 4)], "*"))   # SEQ * : filtered
+    path = tmp_path / "rt.bam"
+    bamio.write_bam(path, contigs, recs)
+    back = bamio.read_alignment(path)
+    assert back.n_records == len(recs) and back.n_reads == batch.n_reads
+    for f in ("ref_start", "cig_off", "cigar", "contig_len", "contig_read_off", "contig_slot", "complex_idx", "evt_off"):
+        np.testing.assert_array_equal(getattr(back, f), getattr(batch, f), err_msg=f)
+    c0, e0 = coracle.pileup(batch)
+    c1, e1 = coracle.pileup(back)
+    np.testing.assert_array_equal(c0, c1)
+    np.testing.assert_array_equal(e0, e1)

@@ -70,7 +70,7 @@ def make_workload(name, rank=0, world=1):
         read_off.append(read_off[-1] + (b - a))
     idx = np.flatnonzero(keep)
     words = (150 + 7) // 8
-    seq4 = full.seq4.reshape(-1, words * 4)[idx].reshape(-1)
+    seq4 = full.seq4.reshape(-1, words)[idx].reshape(-1)
     n = idx.shape[0]
     shard = bamio.finalize(full.contig_names, full.contig_len, np.array(read_off), full.ref_start[idx],
                            np.arange(n, dtype=np.int64) * words, full.l_seq[idx], np.arange(n + 1),

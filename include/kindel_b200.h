@@ -25,12 +25,18 @@
  *     ref_start[n]   int32   0-based reference cursor at walk start (= SAM POS - 1; -1 if POS == 0)
  *     seq_off[n]     uint32  offset of the read's packed bases in `seq4`, in 4-byte words
  *     l_seq[n]       int32   low 31 bits: SEQ length.  bit 31 (KDL_COMPLEX) set = needs the general
- *                            CIGAR walk; clear = "simple" read: exactly one M/=/X op, in bounds,
- *                            and then the low bits hold that op's length (<= SEQ length)
+ *                            CIGAR walk; clear = "simple" read: exactly one M/=/X op whose length
+ *                            equals the SEQ length, fully inside the contig (ref_start >= 0,
+ *                            ref_start + len <= L), every base one of A,C,G,T,N (nibbles
+ *                            1,2,4,8,15).  The flatten step classifies (kindel_b200/bamio.py);
+ *                            the fast pileup kernel relies on it and never looks at the CIGAR
  *     cig_off[n+1]   uint32  prefix offsets into `cigar`
  *     cigar[n_ops]   uint32  BAM encoding  len << 4 | op,  op index into "MIDNSHP=X"
- *     seq4[...]      uint8   BAM nibble encoding "=ACMGRSVTWYHKDBN", high nibble first, every
- *                            read starting on a 4-byte boundary
+ *     seq4[n_words]  uint32  BAM nibble codes "=ACMGRSVTWYHKDBN", 8 bases per 32-bit word, FIRST
+ *                            base in the MOST significant nibble (base k of a read sits at bits
+ *                            [28-4*(k%8), 32-4*(k%8)) of its word k/8); every read starts on a
+ *                            word boundary, unused trailing nibbles of its last word are zero,
+ *                            and reads are laid out in read order (seq_off non-decreasing)
  *   contigs:
  *     contig_read_off[n_contigs+1] int64  reads of contig c are [off[c], off[c+1])
  *     contig_len[n_contigs]        int32  reference length L_c
@@ -58,6 +64,8 @@ extern "C" {
 #define KDL_NCOL 19
 #define KDL_NVOTE_COL 7 /* columns 0..6 are all the vote needs */
 #define KDL_COMPLEX 0x80000000u
+#define KDL_TILE 512          /* slots per tile of the owner-computes pileup; n_slots % KDL_TILE == 0 */
+#define KDL_FAST_MAXLEN 8192  /* longest read the flatten step may mark simple */
 
 enum kdl_col {
     KDL_W_A = 0, KDL_W_C, KDL_W_G, KDL_W_T, KDL_W_N,
@@ -80,15 +88,17 @@ typedef enum kdl_status {
 typedef struct kdl_batch {
     int64_t n_reads;
     int64_t n_ops;       /* entries in cigar */
-    int64_t seq4_bytes;  /* bytes in seq4 (multiple of 4) */
+    int64_t seq4_words;  /* 32-bit words in seq4 */
     const int32_t* ref_start;
     const uint32_t* seq_off;
     const int32_t* l_seq;
     const uint32_t* cig_off;
     const uint32_t* cigar;
-    const uint8_t* seq4;
+    const uint32_t* seq4;
     int32_t n_contigs;
-    int32_t reads_sorted; /* 1 = ref_start is non-decreasing inside every contig */
+    int32_t reads_sorted;   /* 1 = ref_start is non-decreasing inside every contig */
+    int32_t max_simple_len; /* longest simple read (bases); 0 if there is none */
+    int32_t reserved0;
     const int64_t* contig_read_off;
     const int32_t* contig_len;
     const int64_t* contig_slot;
@@ -96,6 +106,10 @@ typedef struct kdl_batch {
     int64_t n_complex;
     const uint32_t* complex_idx; /* [n_complex] */
     const uint32_t* evt_off;     /* [n_complex+1] running count of I ops before each listed read */
+    /* scratch for the tile index kdl_pileup builds (K0): uint32[2 * n_slots / KDL_TILE], device
+     * memory owned by the caller.  NULL, or reads_sorted == 0, selects the order-independent
+     * atomic kernel instead of the tile-owner kernel. */
+    uint32_t* tile_index;
 } kdl_batch;
 
 /* Error report written by the pileup (device memory, 4 x int32, zero it before the call):
@@ -116,7 +130,10 @@ int64_t kdl_launch_count(void);
 /* K1 -- pileup.  Replaces the loop at kindel/kindel.py:40-81.
  * Adds every read's contribution to `counts` (caller zeroes it first, so several batches -- or
  * several read shards -- can accumulate into one table) and writes the insertion event rows.
- * err_flag: device int32[4], caller-zeroed; [0] becomes non-zero if any read raised. */
+ * err_flag: device int32[4], caller-zeroed; [0] becomes non-zero if any read raised.
+ * Coordinate-sorted batches (reads_sorted, tile_index scratch given) take the tile-owner kernel
+ * K1f (no atomics); anything else the order-independent atomic kernel K1s.  Complex reads always
+ * take K1g. */
 int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t* ins_events,
                int32_t* err_flag, void* stream);
 
@@ -172,7 +189,7 @@ int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int
                   int64_t* per_contig, int32_t* first_seen, int64_t* totals);
 int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
                  int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
-                 uint32_t* cig_start, uint32_t* cigar, uint8_t* seq4);
+                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,8 @@ c_u8p = C.POINTER(C.c_uint8)
 KDL_NCOL = 19
 KDL_NVOTE_COL = 7
 KDL_COMPLEX = 0x80000000
+KDL_TILE = 512
+KDL_FAST_MAXLEN = 8192
 KDL_OK = 0
 KDL_ERR_INDEX = 10
 KDL_ERR_KEY = 11
@@ -28,7 +30,7 @@ class KdlBatch(C.Structure):
     _fields_ = [
         ("n_reads", C.c_int64),
         ("n_ops", C.c_int64),
-        ("seq4_bytes", C.c_int64),
+        ("seq4_words", C.c_int64),
         ("ref_start", C.c_void_p),
         ("seq_off", C.c_void_p),
         ("l_seq", C.c_void_p),
@@ -37,12 +39,15 @@ class KdlBatch(C.Structure):
         ("seq4", C.c_void_p),
         ("n_contigs", C.c_int32),
         ("reads_sorted", C.c_int32),
+        ("max_simple_len", C.c_int32),
+        ("reserved0", C.c_int32),
         ("contig_read_off", C.c_void_p),
         ("contig_len", C.c_void_p),
         ("contig_slot", C.c_void_p),
         ("n_complex", C.c_int64),
         ("complex_idx", C.c_void_p),
         ("evt_off", C.c_void_p),
+        ("tile_index", C.c_void_p),
     ]
 
 

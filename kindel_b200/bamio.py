@@ -37,7 +37,7 @@ from . import _ffi
 
 CIGAR_OPS = "MIDNSHP=X"
 NIBBLES = "=ACMGRSVTWYHKDBN"
-SLOT_ALIGN = 256  # table slots are padded to a multiple of this (vector loads, tiles)
+SLOT_ALIGN = _ffi.KDL_TILE  # table slots are padded to whole tiles of the owner-computes pileup
 
 _OP_CODE = {c: i for i, c in enumerate(CIGAR_OPS)}
 _ENC = np.full(256, 255, dtype=np.uint8)
@@ -60,13 +60,14 @@ class ReadBatch:
     l_seq: np.ndarray             # int32 [n]   bit 31 = complex
     cig_off: np.ndarray           # uint32 [n+1]
     cigar: np.ndarray             # uint32 [n_ops]
-    seq4: np.ndarray              # uint8 [4 * words]
+    seq4: np.ndarray              # uint32 [words]: 8 bases per word, first base in the top nibble
     complex_idx: np.ndarray = field(default=None)   # uint32 [n_complex]
     evt_off: np.ndarray = field(default=None)       # uint32 [n_complex+1]
     n_events: int = 0
     reads_sorted: bool = False
     aligned_bases: int = 0        # sum of M/=/X lengths = sum of the weights table (the metric's unit)
     n_records: int = 0            # records in the file, before filtering
+    max_simple_len: int = 0       # longest simple read
 
     @property
     def n_reads(self) -> int:
@@ -81,6 +82,38 @@ class ReadBatch:
         arrs = (self.ref_start, self.seq_off, self.l_seq, self.cig_off, self.cigar, self.seq4,
                 self.complex_idx, self.evt_off, self.contig_len, self.contig_read_off, self.contig_slot)
         return int(sum(a.nbytes for a in arrs if a is not None))
+
+
+def _reads_with_exotic_bases(seq4: np.ndarray, seq_off: np.ndarray, lseq: np.ndarray) -> np.ndarray:
+    """True for reads holding a base outside A,C,G,T,N (nibbles 1,2,4,8,15) inside their SEQ.
+    Such reads take the general kernel, which reproduces the reference's KeyError semantics; the
+    fast kernel relies on simple reads being clean (include/kindel_b200.h).  Vectorised: per word,
+    nibbles with popcount 2 or 3 are exotic; zero nibbles ('=') are exotic unless they are the
+    padding behind the last base of a read."""
+    n = seq_off.shape[0]
+    out = np.zeros(n, dtype=bool)
+    if n == 0 or seq4.size == 0:
+        return out
+    w = seq4.astype(np.uint32)
+    h = w | (w >> 1)
+    pair = w & (w >> 1)
+    two_plus = (pair | (pair >> 2) | (h & (h >> 2))) & 0x11111111
+    all4 = pair & (pair >> 2) & 0x11111111
+    zero = ~(h | (h >> 2)) & 0x11111111
+    starts = seq_off.astype(np.int64)
+    lens = np.maximum(lseq.astype(np.int64), 0)
+    has = lens > 0
+    last = starts + (lens + 7) // 8 - 1
+    pad_nibbles = ((lens + 7) // 8) * 8 - lens                       # 0..7 zero nibbles behind the last base
+    pad_mask = ((np.uint64(1) << (4 * pad_nibbles).astype(np.uint64)) - np.uint64(1)).astype(np.uint32)
+    zero_ok = np.zeros_like(zero)
+    zero_ok[last[has]] = pad_mask[has]
+    flagged = np.flatnonzero(((two_plus & ~all4) | (zero & ~zero_ok)) != 0)
+    if flagged.size:
+        owner = np.searchsorted(starts, flagged, side="right") - 1
+        ok = (owner >= 0) & (flagged <= last[np.maximum(owner, 0)])   # ignore words that belong to no read
+        out[np.unique(owner[ok])] = True
+    return out
 
 
 def layout_slots(contig_len: np.ndarray):
@@ -102,10 +135,10 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
     contig_read_off = np.ascontiguousarray(contig_read_off, dtype=np.int64)
     ref_start = np.ascontiguousarray(ref_start, dtype=np.int32)
     seq_off = np.ascontiguousarray(seq_off, dtype=np.uint32)
-    lseq = np.ascontiguousarray(l_seq, dtype=np.int64)
+    lseq = np.ascontiguousarray(l_seq).astype(np.int64) & 0x7FFFFFFF  # tolerate already-flagged input
     cig_off = np.ascontiguousarray(cig_off, dtype=np.uint32)
     cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
-    seq4 = np.ascontiguousarray(seq4, dtype=np.uint8)
+    seq4 = np.ascontiguousarray(seq4, dtype=np.uint32)
     n = ref_start.shape[0]
     slot, n_slots = layout_slots(contig_len)
     per_contig = np.diff(contig_read_off)
@@ -119,7 +152,9 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
     oplen = (first >> 4).astype(np.int64)
     is_m = (op == 0) | (op == 7) | (op == 8)
     start = ref_start.astype(np.int64)
-    simple = (n_cig == 1) & is_m & (oplen <= lseq) & (start >= 0) & (start + oplen <= read_L)
+    simple = (n_cig == 1) & is_m & (oplen == lseq) & (start >= 0) & (start + oplen <= read_L)
+    simple &= oplen <= _ffi.KDL_FAST_MAXLEN
+    simple &= ~_reads_with_exotic_bases(seq4, seq_off, lseq)
     l_out = np.where(simple, oplen, lseq | _ffi.KDL_COMPLEX).astype(np.uint32).view(np.int32)
 
     complex_idx = np.flatnonzero(~simple).astype(np.uint32)
@@ -133,14 +168,13 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
     is_match = (ops_all == 0) | (ops_all == 7) | (ops_all == 8)
     aligned = int(((cigar >> 4).astype(np.int64) * is_match).sum())
 
-    # coordinate order inside every contig?
+    # coordinate order: the global start slot (contig_slot + ref_start) must be non-decreasing over
+    # ALL reads, and the packed bases must be laid out in read order (the tile-owner kernel stages
+    # the reads of a tile as one contiguous index range and one contiguous byte range)
     sorted_ok = True
     if n > 1:
-        d = np.diff(start) >= 0
-        boundaries = contig_read_off[1:-1]
-        boundaries = boundaries[(boundaries > 0) & (boundaries < n)]
-        d[boundaries - 1] = True
-        sorted_ok = bool(d.all())
+        gstart = np.repeat(slot, per_contig) + start
+        sorted_ok = bool((np.diff(gstart) >= 0).all()) and bool((np.diff(seq_off.astype(np.int64)) >= 0).all())
 
     return ReadBatch(
         contig_names=list(contig_names), contig_len=contig_len, contig_read_off=contig_read_off,
@@ -148,6 +182,7 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
         cig_off=cig_off, cigar=cigar, seq4=seq4, complex_idx=complex_idx,
         evt_off=evt.astype(np.uint32), n_events=n_events, reads_sorted=sorted_ok,
         aligned_bases=aligned, n_records=int(n_records),
+        max_simple_len=int(oplen[simple].max()) if simple.any() else 0,
     )
 
 
@@ -276,7 +311,7 @@ def read_bam(path) -> ReadBatch:
     l_seq = np.empty(n, dtype=np.int32)
     cig_off = np.empty(n + 1, dtype=np.uint32)
     cigar = np.empty(max(n_ops, 1), dtype=np.uint32)[:n_ops]
-    seq4 = np.zeros(max(n_words, 1) * 4, dtype=np.uint8)[: n_words * 4]
+    seq4 = np.zeros(max(n_words, 1), dtype=np.uint32)[:n_words]
     rc = lib.kdl_bam_fill(ptr, buf.size, off, n_ref, cursors.ctypes.data, ref_start.ctypes.data,
                           seq_off.ctypes.data, l_seq.ctypes.data, cig_off.ctypes.data, cigar.ctypes.data,
                           seq4.ctypes.data)
@@ -290,16 +325,37 @@ def read_bam(path) -> ReadBatch:
 
 # ---------------------------------------------------------------------------------------- SAM
 def encode_seq(seq: str) -> np.ndarray:
-    """Text bases -> packed BAM nibbles, padded to a 4-byte multiple.  Case is folded (the
-    reference upper-cases every base it touches: kindel.py:51,56,69,77)."""
+    """Text bases -> uint32 words, 8 nibbles each, first base in the most significant nibble,
+    zero-padded.  Case is folded (the reference upper-cases every base it touches:
+    kindel.py:51,56,69,77)."""
     codes = _ENC[np.frombuffer(seq.encode("ascii"), dtype=np.uint8)]
     if codes.size and codes.max() == 255:
         bad = seq[int(np.argmax(codes == 255))]
         raise ValueError("base %r is outside the BAM alphabet %s and cannot be packed" % (bad, NIBBLES))
     n_words = (len(seq) + 7) // 8
-    padded = np.zeros(n_words * 8, dtype=np.uint8)
+    padded = np.zeros(n_words * 8, dtype=np.uint32)
     padded[: codes.size] = codes
-    return ((padded[0::2] << 4) | padded[1::2]).astype(np.uint8)
+    return pack_nibbles(padded.reshape(-1, 8)).reshape(-1)
+
+
+_SHIFTS = np.arange(28, -4, -4, dtype=np.uint32)
+
+
+def pack_nibbles(nib: np.ndarray) -> np.ndarray:
+    """[..., 8k] nibble codes -> [..., k] uint32 words (first base in the top nibble)."""
+    shape = nib.shape[:-1] + (nib.shape[-1] // 8, 8)
+    return (nib.reshape(shape).astype(np.uint32) << _SHIFTS).sum(axis=-1, dtype=np.uint32)
+
+
+def unpack_nibbles(words: np.ndarray) -> np.ndarray:
+    """uint32 words [..., k] -> nibble codes [..., 8k] uint8."""
+    w = np.asarray(words, dtype=np.uint32)
+    return ((w[..., None] >> _SHIFTS) & 0xF).astype(np.uint8).reshape(w.shape[:-1] + (w.shape[-1] * 8,))
+
+
+def words_to_bam_bytes(words: np.ndarray, l_seq: int) -> bytes:
+    """The BAM on-disk packing of a read (two bases per byte, first in the high nibble)."""
+    return np.asarray(words, dtype=">u4").tobytes()[: (l_seq + 1) // 2]
 
 
 def parse_cigar_text(text: str):
@@ -354,10 +410,10 @@ def read_sam(path) -> ReadBatch:
             cig_off.append(len(cigar))
             enc = encode_seq(seq)
             seq_off.append(words)
-            words += enc.size // 4
+            words += enc.size
             seq_parts.append(enc)
         read_off.append(len(ref_start))
-    seq4 = np.concatenate(seq_parts) if seq_parts else np.zeros(0, dtype=np.uint8)
+    seq4 = np.concatenate(seq_parts) if seq_parts else np.zeros(0, dtype=np.uint32)
     return finalize(contig_names, np.array([sq[nm] for nm in contig_names], dtype=np.int64),
                     np.array(read_off, dtype=np.int64), np.array(ref_start, dtype=np.int64),
                     np.array(seq_off, dtype=np.int64), np.array(l_seq, dtype=np.int64),
@@ -398,7 +454,7 @@ def write_bam(path, contigs, records, header_text=None, level=6):
             l_seq, packed = 0, b""
         else:
             l_seq = len(seq)
-            packed = encode_seq(seq).tobytes()[: (l_seq + 1) // 2]
+            packed = words_to_bam_bytes(encode_seq(seq), l_seq)
         qual = b"\xff" * l_seq
         core = struct.pack("<iiBBHHHiiii", ref_id, pos0, len(qname), 60, 4680, len(cig), flag, l_seq, -1, -1, 0)
         data = core + qname + struct.pack("<%dI" % len(cig), *cig) + packed + qual

@@ -7,6 +7,7 @@
 #include "kdl_common.cuh"
 #include "pileup_general.cu"
 #include "pileup_simple.cu"
+#include "pileup_tiled.cu"
 #include "vote.cu"
 
 namespace {
@@ -74,9 +75,32 @@ int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t
     cudaStream_t st = (cudaStream_t)stream;
     const int cap = sm_count() * 8;
     if (batch->n_reads > batch->n_complex) {
-        const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
-        kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
-        if ((rc = check_launch()) != KDL_OK) return rc;
+        const bool tiled = batch->reads_sorted && batch->tile_index && batch->max_simple_len > 0 &&
+                           batch->max_simple_len <= KDL_FAST_MAXLEN && (n_slots % KDL_TILE) == 0;
+        if (tiled) {
+            // K0: read range per tile (the linear index of a sorted BAM, built on the device)
+            const long long n_tiles = n_slots / KDL_TILE;
+            kdl::tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(*batch, n_tiles,
+                                                                                   batch->tile_index);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+            // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
+            static bool attr_set = false;
+            const int smem = (int)sizeof(kdl::FastSmem);
+            if (!attr_set) {
+                if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem) != cudaSuccess)
+                    return KDL_ERR_CUDA;
+                attr_set = true;
+            }
+            long long grid = n_tiles < (long long)sm_count() * 2 * 4 ? n_tiles : (long long)sm_count() * 2 * 4;
+            kdl::pileup_tiled_kernel<<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(*batch, counts, n_slots,
+                                                                                  batch->tile_index, n_tiles);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        } else {
+            const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
+            kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        }
     }
     if (batch->n_complex > 0) {
         const int grid = grid_for(batch->n_complex, 8, cap);

@@ -99,10 +99,10 @@ int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int
 // cursors[n_ref][3] int64: next read index, next op index, next seq word for each contig
 // (pre-set by the caller from the prefix sums of kdl_bam_count's output; advanced in place).
 // Outputs are sized for all kept records: ref_start/seq_off/l_seq/cig_start [n_kept],
-// cigar [total ops], seq4 [total words * 4] (zero-filled by the caller so padding is defined).
+// cigar [total ops], seq4 [total words] uint32.
 int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
                  int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
-                 uint32_t* cig_start, uint32_t* cigar, uint8_t* seq4) {
+                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4) {
     if (!bam || !cursors) return KDL_ERR_INVALID_ARG;
     int64_t off = first_record;
     RecView r;
@@ -122,7 +122,18 @@ int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int3
         l_seq[i] = r.l_seq;
         cig_start[i] = (uint32_t)o;
         std::memcpy(cigar + o, r.cigar, 4ull * r.n_cigar);
-        std::memcpy(seq4 + 4 * w, r.seq, (size_t)((r.l_seq + 1) / 2));
+        // BAM packs two bases per byte, first base in the high nibble; the engine wants 8 bases
+        // per 32-bit word with the first base in the most significant nibble: a byte-swapped copy.
+        const int64_t n_bytes_seq = ((int64_t)r.l_seq + 1) / 2;
+        const int64_t n_words_seq = ((int64_t)r.l_seq + 7) / 8;
+        for (int64_t k = 0; k < n_words_seq; ++k) {
+            uint8_t b[4] = {0, 0, 0, 0};
+            const int64_t left = n_bytes_seq - 4 * k;
+            std::memcpy(b, r.seq + 4 * k, (size_t)(left < 4 ? left : 4));
+            uint32_t v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+            if (k == n_words_seq - 1 && (r.l_seq & 7)) v &= ~(0xFFFFFFFFu >> (4 * (r.l_seq & 7)));
+            seq4[w + k] = v;
+        }
     }
     return KDL_OK;
 }

@@ -16,7 +16,7 @@ struct kdl_ctx {
         size_t cap = 0;
     };
     enum { B_REF_START, B_SEQ_OFF, B_L_SEQ, B_CIG_OFF, B_CIGAR, B_SEQ4, B_CREAD_OFF, B_CLEN, B_CSLOT,
-           B_CX_IDX, B_EVT_OFF, B_COUNTS, B_EVENTS, B_CALLS, B_FLAG, B_DIAG, B_N };
+           B_CX_IDX, B_EVT_OFF, B_COUNTS, B_EVENTS, B_CALLS, B_FLAG, B_DIAG, B_TILE_IDX, B_N };
     Buf buf[B_N];
 
     int ensure(int which, size_t bytes) {
@@ -91,7 +91,7 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
         {kdl_ctx::B_L_SEQ, hb->l_seq, n * 4},
         {kdl_ctx::B_CIG_OFF, hb->cig_off, (n + 1) * 4},
         {kdl_ctx::B_CIGAR, hb->cigar, (size_t)hb->n_ops * 4},
-        {kdl_ctx::B_SEQ4, hb->seq4, (size_t)hb->seq4_bytes},
+        {kdl_ctx::B_SEQ4, hb->seq4, (size_t)hb->seq4_words * 4},
         {kdl_ctx::B_CREAD_OFF, hb->contig_read_off, (nc + 1) * 8},
         {kdl_ctx::B_CLEN, hb->contig_len, nc * 4},
         {kdl_ctx::B_CSLOT, hb->contig_slot, nc * 8},
@@ -105,6 +105,7 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     if ((rc = c->ensure(kdl_ctx::B_CALLS, (size_t)n_slots)) != KDL_OK) return rc;
     if ((rc = c->ensure(kdl_ctx::B_FLAG, 16)) != KDL_OK) return rc;
     if ((rc = c->ensure(kdl_ctx::B_DIAG, sizeof(kdl_diag))) != KDL_OK) return rc;
+    if ((rc = c->ensure(kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 8)) != KDL_OK) return rc;
 
     cudaStream_t st = c->stream;
     cudaEventRecord(c->ev[0], st);
@@ -120,12 +121,13 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     db.l_seq = (const int32_t*)c->buf[kdl_ctx::B_L_SEQ].p;
     db.cig_off = (const uint32_t*)c->buf[kdl_ctx::B_CIG_OFF].p;
     db.cigar = (const uint32_t*)c->buf[kdl_ctx::B_CIGAR].p;
-    db.seq4 = (const uint8_t*)c->buf[kdl_ctx::B_SEQ4].p;
+    db.seq4 = (const uint32_t*)c->buf[kdl_ctx::B_SEQ4].p;
     db.contig_read_off = (const int64_t*)c->buf[kdl_ctx::B_CREAD_OFF].p;
     db.contig_len = (const int32_t*)c->buf[kdl_ctx::B_CLEN].p;
     db.contig_slot = (const int64_t*)c->buf[kdl_ctx::B_CSLOT].p;
     db.complex_idx = nx ? (const uint32_t*)c->buf[kdl_ctx::B_CX_IDX].p : nullptr;
     db.evt_off = nx ? (const uint32_t*)c->buf[kdl_ctx::B_EVT_OFF].p : nullptr;
+    db.tile_index = (n_slots % KDL_TILE) == 0 ? (uint32_t*)c->buf[kdl_ctx::B_TILE_IDX].p : nullptr;
 
     int32_t* d_counts = (int32_t*)c->buf[kdl_ctx::B_COUNTS].p;
     int32_t* d_events = (int32_t*)c->buf[kdl_ctx::B_EVENTS].p;

@@ -18,9 +18,9 @@ __device__ __forceinline__ int nib2col(int nib) {
     return v == 0xF ? -1 : v;
 }
 
-__device__ __forceinline__ int nibble_at(const uint8_t* __restrict__ seq, long long q) {
-    const unsigned b = seq[q >> 1];
-    return (q & 1) ? (b & 0xF) : (b >> 4);
+// 8 bases per 32-bit word, first base in the most significant nibble
+__device__ __forceinline__ int nibble_at(const uint32_t* __restrict__ seq, long long q) {
+    return (int)((seq[q >> 3] >> (28 - 4 * (int)(q & 7))) & 0xFu);
 }
 
 // Python list indexing (list length n): negative indices wrap once, otherwise IndexError (-1).

@@ -29,7 +29,7 @@ pileup_general_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slo
         const long long L = b.contig_len[c];
         const long long base = b.contig_slot[c];
         const long long lseq = (long long)(b.l_seq[r] & 0x7fffffff);
-        const uint8_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r] * 4;
+        const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
         const uint32_t c0 = b.cig_off[r], c1 = b.cig_off[r + 1];
         long long r_pos = b.ref_start[r];
         long long q_pos = 0;
@@ -127,7 +127,7 @@ __device__ unsigned long long diagnose_read(const kdl_batch& b, long long r) {
     const long long L = b.contig_len[c];
     const int32_t lraw = b.l_seq[r];
     const long long lseq = (long long)(lraw & 0x7fffffff);
-    const uint8_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r] * 4;
+    const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
     const uint32_t c0 = b.cig_off[r], c1 = b.cig_off[r + 1];
     long long r_pos = b.ref_start[r], q_pos = 0;
 #define KDL_FAIL(kind, nib)                                                                     \

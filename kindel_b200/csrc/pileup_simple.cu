@@ -23,7 +23,7 @@ pileup_simple_atomic_kernel(kdl_batch b, int32_t* __restrict__ counts, long long
         if (lraw < 0) continue;  // complex read: K1g walks it
         const int c = find_contig(b.contig_read_off, b.n_contigs, r);
         const long long base = b.contig_slot[c] + b.ref_start[r];
-        const uint8_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r] * 4;
+        const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
         for (int k = lane; k < lraw; k += 32) {
             const int col = nib2col(nibble_at(seq, k));
             if (col < 0) { bad = true; continue; }

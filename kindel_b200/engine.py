@@ -53,7 +53,7 @@ def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     s = _ffi.KdlBatch()
     s.n_reads = host.n_reads
     s.n_ops = int(host.cigar.shape[0])
-    s.seq4_bytes = int(host.seq4.shape[0])
+    s.seq4_words = int(host.seq4.shape[0])
     s.ref_start = ptr["ref_start"]
     s.seq_off = ptr["seq_off"]
     s.l_seq = ptr["l_seq"]
@@ -62,6 +62,7 @@ def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     s.seq4 = ptr["seq4"]
     s.n_contigs = host.n_contigs
     s.reads_sorted = 1 if host.reads_sorted else 0
+    s.max_simple_len = int(host.max_simple_len)
     s.contig_read_off = ptr["contig_read_off"]
     s.contig_len = ptr["contig_len"]
     s.contig_slot = ptr["contig_slot"]
@@ -69,6 +70,7 @@ def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     s.n_complex = n_cx
     s.complex_idx = ptr["complex_idx"] if n_cx else None
     s.evt_off = ptr["evt_off"] if n_cx else None
+    s.tile_index = ptr.get("tile_index")
     return s
 
 
@@ -92,6 +94,8 @@ def upload(host: ReadBatch, device=None, non_blocking: bool = False) -> DeviceBa
             a = a.view(np.int32)
         t = torch.from_numpy(a) if a.size else torch.zeros(4, dtype=torch.from_numpy(a).dtype)
         tensors[f] = t.to(device, non_blocking=non_blocking)
+    # scratch for the tile index kdl_pileup builds on the device (K0)
+    tensors["tile_index"] = torch.empty(2 * (host.n_slots // _ffi.KDL_TILE), dtype=torch.int32, device=device)
     ptr = {f: int(t.data_ptr()) for f, t in tensors.items()}
     return DeviceBatch(host=host, device=device, tensors=tensors, struct=make_struct(host, ptr))
 

@@ -35,8 +35,8 @@ def decode_events(batch: ReadBatch, rows: np.ndarray) -> list:
     starts = ends - ln
     within = np.arange(total, dtype=np.int64) - np.repeat(starts, ln)
     q = np.repeat(q0, ln) + within
-    byte = batch.seq4[np.repeat(batch.seq_off[read].astype(np.int64) * 4, ln) + (q >> 1)]
-    nib = np.where(q & 1, byte & 0xF, byte >> 4)
+    word = batch.seq4[np.repeat(batch.seq_off[read].astype(np.int64), ln) + (q >> 3)]
+    nib = (word >> (28 - 4 * (q & 7)).astype(np.uint32)) & 0xF
     chars = _LUT[nib].tobytes().decode("ascii")
     return [chars[s:e] for s, e in zip(starts.tolist(), ends.tolist())]
 

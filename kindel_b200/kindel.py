@@ -124,9 +124,9 @@ def flatten_records(ref_id, ref_len, records) -> bamio.ReadBatch:
         cig_off.append(len(cigar))
         enc = bamio.encode_seq(rec.seq)
         seq_off.append(words)
-        words += enc.size // 4
+        words += enc.size
         parts.append(enc)
-    seq4 = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+    seq4 = np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint32)
     return bamio.finalize([ref_id], np.array([ref_len], dtype=np.int64), np.array([0, len(ref_start)], dtype=np.int64),
                           np.array(ref_start, dtype=np.int64), np.array(seq_off, dtype=np.int64),
                           np.array(l_seq, dtype=np.int64), np.array(cig_off, dtype=np.int64),

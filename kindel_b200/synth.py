@@ -25,8 +25,8 @@ def random_contig(rng, length: int) -> np.ndarray:
 
 
 def _pack_rows(nib: np.ndarray) -> np.ndarray:
-    """[n, w] nibble codes (w % 8 == 0) -> [n, w/2] packed bytes, high nibble first."""
-    return ((nib[:, 0::2] << 4) | nib[:, 1::2]).astype(np.uint8)
+    """[n, w] nibble codes (w % 8 == 0) -> [n, w/8] uint32 words, first base in the top nibble."""
+    return bamio.pack_nibbles(nib)
 
 
 def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_rate: float = 0.01,
@@ -35,7 +35,6 @@ def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_
     rng = np.random.default_rng(seed)
     contig_lens = [int(x) for x in contig_lens]
     words = (read_len + 7) // 8
-    row_bytes = words * 4
     ref_start_all, seq_rows, read_off = [], [], [0]
     for L in contig_lens:
         n = int(round(depth * L / read_len))
@@ -156,7 +155,7 @@ def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150,
         t_nib[np.arange(t_words * 8)[None, :] >= t_len[:, None]] = 0
         packed = _pack_rows(t_nib)
         if t_words < words:
-            packed = np.concatenate([packed, np.zeros((len(tail), (words - t_words) * 4), dtype=np.uint8)], axis=1)
+            packed = np.concatenate([packed, np.zeros((len(tail), words - t_words), dtype=np.uint32)], axis=1)
         elif t_words > words:
             raise ValueError("edge-tail reads longer than read_len are not laid out here")
         seq_rows.append(packed)
@@ -185,11 +184,7 @@ def to_records(batch: bamio.ReadBatch):
             lraw = int(batch.l_seq[r])
             words = batch.cigar[int(batch.cig_off[r]):int(batch.cig_off[r + 1])].tolist()
             lseq = lraw & 0x7FFFFFFF if lraw < 0 else sum(w >> 4 for w in words if (w & 15) in (0, 1, 4, 7, 8))
-            base = int(batch.seq_off[r]) * 4
-            by = batch.seq4[base:base + (lseq + 1) // 2]
-            chars = []
-            for b in by.tolist():
-                chars.append(bamio.NIBBLES[b >> 4])
-                chars.append(bamio.NIBBLES[b & 15])
-            recs.append((c, int(batch.ref_start[r]), 0, words, "".join(chars[:lseq])))
+            base = int(batch.seq_off[r])
+            nib = bamio.unpack_nibbles(batch.seq4[base:base + (lseq + 7) // 8])[:lseq]
+            recs.append((c, int(batch.ref_start[r]), 0, words, "".join(bamio.NIBBLES[x] for x in nib.tolist())))
     return contigs, recs

@@ -28,10 +28,10 @@ NCOL = 19
 
 class _Batch(C.Structure):
     _fields_ = [
-        ("n_reads", C.c_int64), ("n_ops", C.c_int64), ("seq4_bytes", C.c_int64),
+        ("n_reads", C.c_int64), ("n_ops", C.c_int64), ("seq4_words", C.c_int64),
         ("ref_start", C.c_void_p), ("seq_off", C.c_void_p), ("l_seq", C.c_void_p),
         ("cig_off", C.c_void_p), ("cigar", C.c_void_p), ("seq4", C.c_void_p),
-        ("n_contigs", C.c_int32), ("reads_sorted", C.c_int32),
+        ("n_contigs", C.c_int32), ("reads_sorted", C.c_int32), ("max_simple_len", C.c_int32), ("reserved0", C.c_int32),
         ("contig_read_off", C.c_void_p), ("contig_len", C.c_void_p), ("contig_slot", C.c_void_p),
         ("n_complex", C.c_int64), ("complex_idx", C.c_void_p), ("evt_off", C.c_void_p),
     ]
@@ -76,13 +76,13 @@ def _struct(batch, keep):
     b = _Batch()
     b.n_reads = int(batch.ref_start.shape[0])
     b.n_ops = int(batch.cigar.shape[0])
-    b.seq4_bytes = int(batch.seq4.shape[0])
+    b.seq4_words = int(batch.seq4.shape[0])
     b.ref_start = ptr(batch.ref_start, np.int32)
     b.seq_off = ptr(batch.seq_off, np.uint32)
     b.l_seq = ptr(batch.l_seq, np.int32)
     b.cig_off = ptr(batch.cig_off, np.uint32)
     b.cigar = ptr(batch.cigar, np.uint32)
-    b.seq4 = ptr(batch.seq4, np.uint8)
+    b.seq4 = ptr(batch.seq4, np.uint32)
     b.n_contigs = len(batch.contig_len)
     b.reads_sorted = 0
     b.contig_read_off = ptr(batch.contig_read_off, np.int64)

@@ -30,14 +30,14 @@ enum { W_A = 0, W_N = 4, C_DEL = 5, C_INS = 6, C_CLIP_STARTS = 7, C_CLIP_ENDS = 
 enum { ERR_INDEX = 10, ERR_KEY = 11 };
 
 typedef struct {
-    int64_t n_reads, n_ops, seq4_bytes;
+    int64_t n_reads, n_ops, seq4_words;
     const int32_t* ref_start;
     const uint32_t* seq_off;
     const int32_t* l_seq;
     const uint32_t* cig_off;
     const uint32_t* cigar;
-    const uint8_t* seq4;
-    int32_t n_contigs, reads_sorted;
+    const uint32_t* seq4;
+    int32_t n_contigs, reads_sorted, max_simple_len, reserved0;
     const int64_t* contig_read_off;
     const int32_t* contig_len;
     const int64_t* contig_slot;
@@ -56,9 +56,9 @@ typedef struct {
  * (kindel.py:29) do not hold, which is a KeyError at kindel.py:52/72/79. */
 static const int8_t NIB2COL[16] = {-1, 0, 1, -1, 2, -1, -1, -1, 3, -1, -1, -1, -1, -1, -1, 4};
 
-static inline int nibble_at(const uint8_t* s, int64_t q) {
-    uint8_t b = s[q >> 1];
-    return (q & 1) ? (b & 0xF) : (b >> 4);
+/* 8 bases per 32-bit word, first base in the most significant nibble (include/kindel_b200.h) */
+static inline int nibble_at(const uint32_t* s, int64_t q) {
+    return (int)((s[q >> 3] >> (28 - 4 * (q & 7))) & 0xF);
 }
 
 /* Python list indexing: list of length n, index i.  Returns the wrapped index or -1 (IndexError). */
@@ -89,7 +89,7 @@ int oracle_pileup(const batch_t* b, int32_t* counts, int64_t n_slots, int32_t* i
         for (int k = 0; k < NCOL; ++k) col[k] = counts + (int64_t)k * n_slots + base;
         for (int64_t r = b->contig_read_off[c]; r < b->contig_read_off[c + 1]; ++r) {
             const int64_t lseq = (int64_t)(b->l_seq[r] & 0x7fffffff);
-            const uint8_t* seq = b->seq4 + (size_t)b->seq_off[r] * 4;
+            const uint32_t* seq = b->seq4 + (size_t)b->seq_off[r];
             const uint32_t c0 = b->cig_off[r], c1 = b->cig_off[r + 1];
             int64_t r_pos = b->ref_start[r]; /* kindel.py:42 (already POS-1) */
             int64_t q_pos = 0;               /* kindel.py:41 */

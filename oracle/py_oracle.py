@@ -127,11 +127,9 @@ def records_of(batch, lo=0, hi=None):
         lraw = int(batch.l_seq[r])
         words = batch.cigar[int(batch.cig_off[r]):int(batch.cig_off[r + 1])].tolist()
         lseq = (lraw & 0x7FFFFFFF) if lraw < 0 else (words[0] >> 4)
-        base = int(batch.seq_off[r]) * 4
-        by = batch.seq4[base:base + (lseq + 1) // 2]
-        nib = np.empty(by.shape[0] * 2, dtype=np.uint8)
-        nib[0::2] = by >> 4
-        nib[1::2] = by & 15
+        base = int(batch.seq_off[r])
+        w = batch.seq4[base:base + (lseq + 7) // 8].astype(np.uint32)
+        nib = ((w[:, None] >> np.arange(28, -4, -4, dtype=np.uint32)[None, :]) & 15).reshape(-1)
         seq = lut[nib[:lseq]].tobytes().decode()
         out.append(Rec(int(batch.ref_start[r]) + 1, True, seq, tuple((w >> 4, _OPS[w & 15]) for w in words)))
     return out

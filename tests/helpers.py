@@ -35,11 +35,11 @@ def reference_alignment_to_table(aln):
 def event_string(batch, read, q_off, length):
     """Upper-case inserted string of one event, straight from the packed bases."""
     lseq = int(batch.l_seq[read]) & 0x7FFFFFFF
-    base = int(batch.seq_off[read]) * 4
+    base = int(batch.seq_off[read])
     out = []
     for q in range(q_off, min(q_off + length, lseq)):
-        b = int(batch.seq4[base + (q >> 1)])
-        out.append(NIBBLES[(b & 0xF) if (q & 1) else (b >> 4)])
+        w = int(batch.seq4[base + (q >> 3)])
+        out.append(NIBBLES[(w >> (28 - 4 * (q & 7))) & 0xF])
     return "".join(out)
 
 

@@ -38,7 +38,7 @@ def test_struct_layouts_match_the_header():
     from kindel_b200 import _ffi
 
     # kdl_batch: 3 x i64, 6 ptr, 2 x i32, 3 ptr, i64, 2 ptr = 17 eight-byte words - 1 (two i32 share one)
-    assert ctypes.sizeof(_ffi.KdlBatch) == 8 * 16
+    assert ctypes.sizeof(_ffi.KdlBatch) == 8 * 18
     assert ctypes.sizeof(_ffi.KdlDiag) == 24
 
 

@@ -213,7 +213,9 @@ def test_host_buffer_entry_point():
         t = ctx.last_timing()
         assert t["h2d_ms"] > 0 and t["kernel_ms"] > 0
     bad = synth.simple_reads(23, [5000], 20)
-    bad.seq4[7] = 0x33  # nibble 3 = 'M' (IUPAC): KeyError('M') in the reference
+    bad.seq4[7] = (int(bad.seq4[7]) & 0x0FFFFFFF) | 0x30000000  # nibble 3 = 'M' (IUPAC): KeyError('M')
+    bad = bamio.finalize(bad.contig_names, bad.contig_len, bad.contig_read_off, bad.ref_start, bad.seq_off,
+                         bad.l_seq & 0x7FFFFFFF, bad.cig_off, bad.cigar, bad.seq4)  # re-classify: that read is now complex
     with pytest.raises(KeyError) as exc:
         ctx.consensus(bad, 1)
     assert exc.value.args == ("M",)

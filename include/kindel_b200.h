@@ -106,7 +106,7 @@ typedef struct kdl_batch {
     int64_t n_complex;
     const uint32_t* complex_idx; /* [n_complex] */
     const uint32_t* evt_off;     /* [n_complex+1] running count of I ops before each listed read */
-    /* scratch for the tile index kdl_pileup builds (K0): uint32[2 * n_slots / KDL_TILE], device
+    /* scratch for the tile index kdl_pileup builds (K0): uint32[8 * n_slots / KDL_TILE], device
      * memory owned by the caller.  NULL, or reads_sorted == 0, selects the order-independent
      * atomic kernel instead of the tile-owner kernel. */
     uint32_t* tile_index;

@@ -105,7 +105,7 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     if ((rc = c->ensure(kdl_ctx::B_CALLS, (size_t)n_slots)) != KDL_OK) return rc;
     if ((rc = c->ensure(kdl_ctx::B_FLAG, 16)) != KDL_OK) return rc;
     if ((rc = c->ensure(kdl_ctx::B_DIAG, sizeof(kdl_diag))) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 8)) != KDL_OK) return rc;
+    if ((rc = c->ensure(kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 32)) != KDL_OK) return rc;
 
     cudaStream_t st = c->stream;
     cudaEventRecord(c->ev[0], st);

@@ -37,12 +37,16 @@ constexpr int F_CAPW = 20480;          // seq words per staged sub-chunk (80 KB)
 constexpr int F_P = 8;                 // bit planes per stream: up to 255 reads between flushes
 constexpr int F_FLUSH_BLOCKS = 31;     // 31 blocks x 8 reads = 248 <= 255
 
-// ---- K0: per tile, the index range of reads whose first base lies in (tile_lo - maxlen, tile_hi)
+// ---- K0: per tile, what K1f needs to start without dependent global loads: 8 x int32
+//   [0] lo, [1] hi   index range of reads whose first base lies in (tile_lo - maxlen, tile_hi)
+//   [2] wa, [3] wend word range of their packed bases (wa rounded down to a 16-byte boundary)
+//   [4] c_lo, [5] c_hi contigs of read lo and of read hi - 1
 // global slot of a read's first base = contig_slot[c] + ref_start; reads are sorted by it.
+constexpr int F_IDX = 8;  // int32 per tile in the index
+
 __device__ __forceinline__ long long first_read_at_or_after(const kdl_batch& b, long long g) {
     // first read index whose global start slot is >= g
     if (b.n_contigs == 0) return 0;
-    // contig whose slot range contains g (or the first contig after g)
     int lo = 0, hi = b.n_contigs;  // first contig with slot + len + 1 > g
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
@@ -63,8 +67,48 @@ tile_index_kernel(kdl_batch b, long long n_tiles, uint32_t* __restrict__ index) 
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     const long long g0 = t * KDL_TILE;
-    index[2 * t] = (uint32_t)first_read_at_or_after(b, g0 - b.max_simple_len + 1);
-    index[2 * t + 1] = (uint32_t)first_read_at_or_after(b, g0 + KDL_TILE);
+    const long long lo = first_read_at_or_after(b, g0 - b.max_simple_len + 1);
+    const long long hi = first_read_at_or_after(b, g0 + KDL_TILE);
+    uint32_t* e = index + F_IDX * t;
+    e[0] = (uint32_t)lo;
+    e[1] = (uint32_t)hi;
+    e[2] = lo < b.n_reads ? (b.seq_off[lo] & ~3u) : 0u;
+    e[3] = hi < b.n_reads ? b.seq_off[hi] : (uint32_t)b.seq4_words;
+    e[4] = lo < hi ? (uint32_t)find_contig(b.contig_read_off, b.n_contigs, lo) : 0u;
+    e[5] = lo < hi ? (uint32_t)find_contig(b.contig_read_off, b.n_contigs, hi - 1) : 0u;
+    e[6] = 0u;
+    e[7] = 0u;
+}
+
+// ---- 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP) completing on an mbarrier --------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
 }
 
 // ---- bit-sliced counters ------------------------------------------------------------------------
@@ -146,18 +190,18 @@ __device__ __forceinline__ void extract8(const uint32_t (&pl)[F_P + 2], int bit,
 // no other thread of the grid touches these slots during this kernel.
 __device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t* __restrict__ counts,
                                              long long n_slots, long long slot0, int lane) {
+    const int q = lane >> 3;
+    const long long s = slot0 + 8 * (lane & 7);
+    int4* dst = reinterpret_cast<int4*>(counts + (long long)q * n_slots + s);
+    int4 v0 = dst[0], v1 = dst[1];  // issued first: their latency hides behind the transposition
     uint32_t m[F_P + 2], n[F_P + 2];
     quarter_sum(acc.p, m);
     quarter_sum(accn.p, n);
     acc.clear();
     accn.clear();
-    const int q = lane >> 3;
     int cn[8], cv[8];
     extract8(n, 0, cn);
     extract8(m, q, cv);
-    const long long s = slot0 + 8 * (lane & 7);
-    int4* dst = reinterpret_cast<int4*>(counts + (long long)q * n_slots + s);
-    int4 v0 = dst[0], v1 = dst[1];
     v0.x += cv[0] - cn[0]; v0.y += cv[1] - cn[1]; v0.z += cv[2] - cn[2]; v0.w += cv[3] - cn[3];
     v1.x += cv[4] - cn[4]; v1.y += cv[5] - cn[5]; v1.z += cv[6] - cn[6]; v1.w += cv[7] - cn[7];
     dst[0] = v0;
@@ -174,10 +218,10 @@ __device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t*
 
 struct FastSmem {
     uint32_t seq[F_CAPW];
-    int gs[F_RMAX];        // start slot of the read relative to the tile's first slot
-    uint32_t ww[F_RMAX];   // word offset in seq[] (low 16 bits) | n_words << 16 (0 = not a simple read)
-    int c1;                // end of the current sub-chunk (broadcast)
-    int skip;              // 1 = sub-chunk does not fit: its (necessarily complex) reads are skipped
+    int2 meta[F_RMAX];  // .x = start slot of the read relative to the tile's first slot (all reads,
+                        //      so the array stays sorted); .y = word offset in seq[] | n_words << 16
+                        //      (n_words = 0: not a simple read, adds nothing)
+    uint64_t bar;       // mbarrier the bulk copy of seq[] completes on
 };
 
 __global__ void __launch_bounds__(F_THREADS, 2)
@@ -187,12 +231,21 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = lane >> 3;
+    const int maxlen = b.max_simple_len;
+    uint32_t bar_parity = 0;
+    if (tid == 0) mbar_init(&sm.bar, 1);
+    __syncthreads();
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const long long lo = tile_index[2 * tile], hi = tile_index[2 * tile + 1];
+        const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
+        const uint2 ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
+        const long long lo = ix.x, hi = ix.y;
         if (lo >= hi) continue;  // uniform for the CTA
         const long long tile_slot = tile * KDL_TILE;
-        const int p0 = warp * F_WIN + 8 * (lane & 7);  // lane's first slot, tile-relative
+        const bool one_contig = ic.x == ic.y;
+        const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
+        const int wlo = warp * F_WIN;
+        const int p0 = wlo + 8 * (lane & 7);  // lane's first slot, tile-relative
         Planes acc, accn;
         acc.clear();
         accn.clear();
@@ -200,94 +253,111 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
 
         long long c0 = lo;
         while (c0 < hi) {
-            // ---- sub-chunk [c0, c1): at most F_RMAX reads and F_CAPW words ------------------------
-            __syncthreads();  // previous sub-chunk fully consumed
-            if (tid == 0) {
-                long long c1 = c0 + F_RMAX < hi ? c0 + F_RMAX : hi;
-                const long long wa = (long long)(b.seq_off[c0] & ~3u);
-                int skip = 0;
-                for (;;) {
-                    const long long wend = c1 < b.n_reads ? (long long)b.seq_off[c1] : b.seq4_words;
-                    if (wend - wa <= F_CAPW) break;
-                    if (c1 - c0 == 1) { skip = 1; break; }
-                    c1 = c0 + (c1 - c0) / 2;
-                }
-                sm.c1 = (int)(c1 - c0);
-                sm.skip = skip;
+            // ---- sub-chunk [c0, c1): at most F_RMAX reads and F_CAPW words; every thread derives
+            // the same bounds from the same (broadcast) loads -- no elected thread, no extra barrier
+            long long c1 = c0 + F_RMAX < hi ? c0 + F_RMAX : hi;
+            const long long wa = c0 == lo ? (long long)ix.z : (long long)(b.seq_off[c0] & ~3u);
+            long long wend = c1 == hi ? (long long)ix.w : (long long)b.seq_off[c1];
+            bool skip = false;
+            while (wend - wa > F_CAPW) {
+                if (c1 - c0 == 1) { skip = true; break; }  // one read too long to stage: never simple
+                c1 = c0 + (c1 - c0) / 2;
+                wend = (long long)b.seq_off[c1];
             }
-            __syncthreads();
-            const long long c1 = c0 + sm.c1;
-            const int n_sub = sm.c1;
-            if (sm.skip) { c0 = c1; continue; }  // a read too long to stage is never a simple read
-            const long long wa = (long long)(b.seq_off[c0] & ~3u);
-            const long long wend = c1 < b.n_reads ? (long long)b.seq_off[c1] : b.seq4_words;
-            // metadata
-            for (int i = tid; i < n_sub; i += F_THREADS) {
-                const long long r = c0 + i;
-                const int l = b.l_seq[r];
-                // every read keeps its place in the start-slot order (the flatten step guarantees it is
-                // non-decreasing over ALL reads); complex reads get n_words = 0 and add nothing
-                const int c = find_contig(b.contig_read_off, b.n_contigs, r);
-                long long g = b.contig_slot[c] + b.ref_start[r] - tile_slot;
-                g = g < -0x20000000ll ? -0x20000000ll : (g > 0x20000000ll ? 0x20000000ll : g);
-                uint32_t ww = 0;
-                if (l > 0)  // simple read (bit 31 clear)
-                    ww = (uint32_t)((long long)b.seq_off[r] - wa) | ((uint32_t)((l + 7) >> 3) << 16);
-                sm.gs[i] = (int)g;
-                sm.ww[i] = ww;
-            }
-            // bases: 128-bit copies of [wa, wend)
+            if (skip) { c0 = c1; continue; }
+            const int n_sub = (int)(c1 - c0);
+            __syncthreads();  // previous sub-chunk (or tile) fully consumed
+            // bases: ONE bulk copy of [wa, wend) by the TMA engine, completing on sm.bar; the
+            // threads meanwhile fetch the per-read metadata.  16-byte granules; the (at most one)
+            // partial granule at the very end of the array is copied by hand.
             {
-                const long long n_vec = (wend - wa + 3) >> 2;
-                const uint4* src = reinterpret_cast<const uint4*>(b.seq4 + wa);
-                uint4* dst = reinterpret_cast<uint4*>(sm.seq);
-                for (long long v = tid; v < n_vec; v += F_THREADS) {
-                    if (wa + 4 * v + 4 <= b.seq4_words) {
-                        dst[v] = __ldg(src + v);
-                    } else {  // last, partial vector of the whole array
-                        uint32_t t4[4] = {0u, 0u, 0u, 0u};
-                        for (int k = 0; k < 4; ++k)
-                            if (wa + 4 * v + k < b.seq4_words) t4[k] = b.seq4[wa + 4 * v + k];
-                        dst[v] = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+                const long long n_words = wend - wa;
+                const long long avail = b.seq4_words - wa;
+                const long long want = (n_words + 3) & ~3ll;
+                const long long bulk_words = want <= avail ? want : (avail & ~3ll);
+                if (tid == 0) {
+                    mbar_expect_tx(&sm.bar, (uint32_t)(bulk_words * 4));
+                    if (bulk_words) bulk_g2s(sm.seq, b.seq4 + wa, (uint32_t)(bulk_words * 4), &sm.bar);
+                }
+                if (bulk_words < n_words && tid < 4) {
+                    const long long w = bulk_words + tid;
+                    sm.seq[w] = w < avail ? b.seq4[wa + w] : 0u;
+                }
+            }
+            {   // metadata: all loads of this thread's (up to 4) reads first, then the stores
+                int l[F_RMAX / F_THREADS], rs[F_RMAX / F_THREADS];
+                uint32_t so[F_RMAX / F_THREADS];
+#pragma unroll
+                for (int k = 0; k < F_RMAX / F_THREADS; ++k) {
+                    const int i = tid + k * F_THREADS;
+                    const long long r = c0 + (i < n_sub ? i : 0);
+                    l[k] = b.l_seq[r];
+                    rs[k] = b.ref_start[r];
+                    so[k] = b.seq_off[r];
+                }
+#pragma unroll
+                for (int k = 0; k < F_RMAX / F_THREADS; ++k) {
+                    const int i = tid + k * F_THREADS;
+                    if (i < n_sub) {
+                        long long g;
+                        if (one_contig) {
+                            g = slot_base + rs[k];
+                        } else {
+                            const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
+                            g = b.contig_slot[c] + rs[k] - tile_slot;
+                        }
+                        g = g < -0x20000000ll ? -0x20000000ll : (g > 0x20000000ll ? 0x20000000ll : g);
+                        uint32_t ww = 0;
+                        if (l[k] > 0)  // simple read (bit 31 clear)
+                            ww = (uint32_t)((long long)so[k] - wa) | ((uint32_t)((l[k] + 7) >> 3) << 16);
+                        sm.meta[i] = make_int2((int)g, (int)ww);
                     }
                 }
             }
-            __syncthreads();
+            __syncthreads();                 // metadata visible
+            mbar_wait(&sm.bar, bar_parity);  // bases landed
+            bar_parity ^= 1u;
 
-            // ---- this warp's window against the sub-chunk --------------------------------------
-            const int wlo = warp * F_WIN;
-            int a, e;  // reads of the sub-chunk that can reach [wlo, wlo + 64): gs in (wlo - maxlen, wlo + 64)
+            // ---- this warp's window against the sub-chunk: reads with start in (wlo - maxlen, wlo + 64)
+            int a, e;
             {
                 int l0 = 0, h0 = n_sub;
                 while (l0 < h0) {
                     const int mid = (l0 + h0) >> 1;
-                    if (sm.gs[mid] + b.max_simple_len > wlo) h0 = mid; else l0 = mid + 1;
+                    if (sm.meta[mid].x + maxlen > wlo) h0 = mid; else l0 = mid + 1;
                 }
                 a = l0;
                 int l1 = a, h1 = n_sub;
                 while (l1 < h1) {
                     const int mid = (l1 + h1) >> 1;
-                    if (sm.gs[mid] >= wlo + F_WIN) h1 = mid; else l1 = mid + 1;
+                    if (sm.meta[mid].x >= wlo + F_WIN) h1 = mid; else l1 = mid + 1;
                 }
                 e = l1;
             }
 
             for (int base = a; base < e; base += 32) {
                 uint32_t x[8], xn[8];
+                int2 mt[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {  // all metadata loads first (clamped: branch-free)
+                    const int i = base + 4 * u + quarter;
+                    mt[u] = sm.meta[i < e ? i : e - 1];
+                    if (i >= e) mt[u].y = 0;
+                }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = base + 4 * u + quarter;
-                    uint32_t w = 0;
-                    if (i < e) {
-                        const uint32_t ww = sm.ww[i];
-                        const int o = p0 - sm.gs[i];
-                        const int j = o >> 3;
-                        const int nw = (int)(ww >> 16);
-                        const uint32_t* s = sm.seq + (ww & 0xFFFFu);
-                        const uint32_t hw = ((unsigned)j < (unsigned)nw) ? s[j] : 0u;
-                        const uint32_t lw = ((unsigned)(j + 1) < (unsigned)nw) ? s[j + 1] : 0u;
-                        w = __funnelshift_l(lw, hw, o << 2);
-                    }
+                    const uint32_t ww = (uint32_t)mt[u].y;
+                    const int o = p0 - mt[u].x;
+                    const int j = o >> 3;
+                    const int nw = (int)(ww >> 16);
+                    const int w0 = (int)(ww & 0xFFFFu) + j;
+                    const bool v0 = (unsigned)j < (unsigned)nw;
+                    const bool v1 = (unsigned)(j + 1) < (unsigned)nw;
+                    uint32_t hw = sm.seq[v0 ? w0 : 0];
+                    uint32_t lw = sm.seq[v1 ? w0 + 1 : 0];
+                    hw = v0 ? hw : 0u;
+                    lw = v1 ? lw : 0u;
+                    const uint32_t w = __funnelshift_l(lw, hw, o << 2);
                     x[u] = w;
                     xn[u] = w & (w >> 1) & 0x11111111u;  // nibble 15 (N): bits 0 and 1 both set
                 }
@@ -300,7 +370,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
             }
             c0 = c1;
         }
-        if (blocks_since_flush) flush_window(acc, accn, counts, n_slots, tile_slot + warp * F_WIN, lane);
+        if (blocks_since_flush) flush_window(acc, accn, counts, n_slots, tile_slot + wlo, lane);
     }
 }
 

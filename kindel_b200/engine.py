@@ -95,7 +95,7 @@ def upload(host: ReadBatch, device=None, non_blocking: bool = False) -> DeviceBa
         t = torch.from_numpy(a) if a.size else torch.zeros(4, dtype=torch.from_numpy(a).dtype)
         tensors[f] = t.to(device, non_blocking=non_blocking)
     # scratch for the tile index kdl_pileup builds on the device (K0)
-    tensors["tile_index"] = torch.empty(2 * (host.n_slots // _ffi.KDL_TILE), dtype=torch.int32, device=device)
+    tensors["tile_index"] = torch.empty(8 * (host.n_slots // _ffi.KDL_TILE), dtype=torch.int32, device=device)
     ptr = {f: int(t.data_ptr()) for f, t in tensors.items()}
     return DeviceBatch(host=host, device=device, tensors=tensors, struct=make_struct(host, ptr))
 

@@ -218,9 +218,10 @@ __device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t*
 
 struct FastSmem {
     uint32_t seq[F_CAPW];
-    int2 meta[F_RMAX];  // .x = start slot of the read relative to the tile's first slot (all reads,
-                        //      so the array stays sorted); .y = word offset in seq[] | n_words << 16
-                        //      (n_words = 0: not a simple read, adds nothing)
+    int2 meta[F_RMAX + 32];  // .x = start slot of the read relative to the tile's first slot (all
+                             //      reads, so the array stays sorted); .y = byte offset of its bases
+                             //      in seq[] (17 bits) | byte length of its bases << 17 (0 = not a
+                             //      simple read: adds nothing).  32 sentinels follow the last read.
     uint64_t bar;       // mbarrier the bulk copy of seq[] completes on
 };
 
@@ -309,10 +310,11 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                         g = g < -0x20000000ll ? -0x20000000ll : (g > 0x20000000ll ? 0x20000000ll : g);
                         uint32_t ww = 0;
                         if (l[k] > 0)  // simple read (bit 31 clear)
-                            ww = (uint32_t)((long long)so[k] - wa) | ((uint32_t)((l[k] + 7) >> 3) << 16);
+                            ww = (uint32_t)(((long long)so[k] - wa) << 2) | ((uint32_t)((l[k] + 7) >> 3) << 19);
                         sm.meta[i] = make_int2((int)g, (int)ww);
                     }
                 }
+                if (tid < 32) sm.meta[n_sub + tid] = make_int2(0x20000000, 0);  // sentinels: never overlap
             }
             __syncthreads();                 // metadata visible
             mbar_wait(&sm.bar, bar_parity);  // bases landed
@@ -335,28 +337,35 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                 e = l1;
             }
 
+            const uint32_t seq_base = smem_u32(sm.seq);
             for (int base = a; base < e; base += 32) {
+                // 8 reads per lane and block.  No bounds logic: a read that does not reach the lane's
+                // 8 slots (including the sentinels behind the last read, and reads [e, ...) that start
+                // right of the window) fails both range tests below and contributes zero.
                 uint32_t x[8], xn[8];
                 int2 mt[8];
+                const int2* mp = sm.meta + base + quarter;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {  // all metadata loads first (clamped: branch-free)
-                    const int i = base + 4 * u + quarter;
-                    mt[u] = sm.meta[i < e ? i : e - 1];
-                    if (i >= e) mt[u].y = 0;
-                }
+                for (int u = 0; u < 8; ++u) mt[u] = mp[4 * u];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const uint32_t ww = (uint32_t)mt[u].y;
-                    const int o = p0 - mt[u].x;
-                    const int j = o >> 3;
-                    const int nw = (int)(ww >> 16);
-                    const int w0 = (int)(ww & 0xFFFFu) + j;
-                    const bool v0 = (unsigned)j < (unsigned)nw;
-                    const bool v1 = (unsigned)(j + 1) < (unsigned)nw;
-                    uint32_t hw = sm.seq[v0 ? w0 : 0];
-                    uint32_t lw = sm.seq[v1 ? w0 + 1 : 0];
-                    hw = v0 ? hw : 0u;
-                    lw = v1 ? lw : 0u;
+                    const int o = p0 - mt[u].x;             // first base of the read this lane needs
+                    const uint32_t jb = (uint32_t)((o >> 1) & ~3);  // byte offset of word o / 8
+                    const uint32_t nb = ww >> 17;           // bytes of packed bases
+                    const uint32_t addr = seq_base + (ww & 0x1FFFFu) + jb;
+                    uint32_t hw, lw;
+                    asm("{\n"
+                        ".reg .pred p, q;\n"
+                        "setp.lt.u32 p, %2, %3;\n"
+                        "setp.lt.u32 q, %4, %3;\n"
+                        "mov.u32 %0, 0;\n"
+                        "mov.u32 %1, 0;\n"
+                        "@p ld.shared.u32 %0, [%5];\n"
+                        "@q ld.shared.u32 %1, [%5+4];\n"
+                        "}\n"
+                        : "=&r"(hw), "=&r"(lw)
+                        : "r"(jb), "r"(nb), "r"(jb + 4u), "r"(addr));
                     const uint32_t w = __funnelshift_l(lw, hw, o << 2);
                     x[u] = w;
                     xn[u] = w & (w >> 1) & 0x11111111u;  // nibble 15 (N): bits 0 and 1 both set

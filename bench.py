@@ -53,29 +53,11 @@ WORKLOADS = {
 
 def make_workload(name, rank=0, world=1):
     """The rank's shard of the workload: a contiguous block of the coordinate-sorted reads."""
-    from kindel_b200 import bamio, synth
+    from kindel_b200 import distributed, synth
 
     lens, depth = WORKLOADS[name]
     full = synth.simple_reads(4, lens, depth)
-    if world == 1:
-        return full, full.aligned_bases
-    # contiguous read blocks inside every contig (SURVEY.md 8e)
-    keep = np.zeros(full.n_reads, dtype=bool)
-    read_off = [0]
-    for c in range(full.n_contigs):
-        lo, hi = int(full.contig_read_off[c]), int(full.contig_read_off[c + 1])
-        a = lo + (hi - lo) * rank // world
-        b = lo + (hi - lo) * (rank + 1) // world
-        keep[a:b] = True
-        read_off.append(read_off[-1] + (b - a))
-    idx = np.flatnonzero(keep)
-    words = (150 + 7) // 8
-    seq4 = full.seq4.reshape(-1, words)[idx].reshape(-1)
-    n = idx.shape[0]
-    shard = bamio.finalize(full.contig_names, full.contig_len, np.array(read_off), full.ref_start[idx],
-                           np.arange(n, dtype=np.int64) * words, full.l_seq[idx], np.arange(n + 1),
-                           full.cigar[idx], seq4, n_records=n)
-    return shard, full.aligned_bases
+    return distributed.shard_batch(full, rank, world), full.aligned_bases
 
 
 def algorithmic_bytes(batch):
@@ -226,22 +208,28 @@ def run_native(args):
     lib = _ffi.load()
 
     batch, total_bases = make_workload(args.workload, rank, world)
-    db = engine.upload(batch, dev)
     n_slots = batch.n_slots
-    counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
     k1_bytes, k2_bytes = algorithmic_bytes(batch)
+    if world == 1:
+        db = engine.upload(batch, dev)
+        counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
 
-    def step(timers=None):
-        counts.zero_()
-        if timers:
-            timers[0].record()
-        c, _ = engine.pileup(db, counts, check=False)
-        if timers:
-            timers[1].record()
-        if world > 1:
-            dist.all_reduce(counts[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM)
-        calls = engine.vote(counts, 1)
-        return calls
+        def step(timers=None):
+            counts.zero_()
+            if timers:
+                timers[0].record()
+            engine.pileup(db, counts, check=False)
+            if timers:
+                timers[1].record()
+            return engine.vote(counts, 1)
+    else:
+        from kindel_b200 import distributed
+
+        sc = distributed.ShardedConsensus(batch, dev, mode=args.exchange)
+        db, counts = sc.dbatch, sc.counts
+
+        def step(timers=None):
+            return sc.step(1, timers)
 
     for _ in range(args.warmup):
         step()
@@ -319,7 +307,10 @@ def run_native(args):
             "dtype": "int32", "data": "synthetic",
             "config": {"workload": args.workload, "reads_total": None, "aligned_bases_total": int(total_bases),
                        "sharding": "contiguous blocks of the coordinate-sorted reads" if world > 1 else "none",
-                       "reduction": "NCCL all_reduce(int32 sum) of the 7 vote columns" if world > 1 else "none",
+                       "reduction": ("none" if world == 1 else
+                                     "fused K2p: vote over peer tables mapped with CUDA IPC (NVLink), footprint-clipped, "
+                                     "+ NCCL all_gather of call bytes" if args.exchange == "peer" else
+                                     "NCCL all_reduce(int32 sum) of the 7 vote columns, vote replicated"),
                        "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
             "roofline": {"bound": "hbm", "kernel": "K1 pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -343,6 +334,8 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4_5Mb_200x")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--exchange", choices=["peer", "allreduce"], default="peer",
+                    help="N > 1: fused peer-memory reduce+vote kernel, or NCCL all_reduce then vote")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

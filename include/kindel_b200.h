@@ -160,6 +160,20 @@ int kdl_derive(const int32_t* counts, int64_t n_slots, int32_t* out, void* strea
 int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n_slots,
                    int64_t slot_lo, int64_t slot_hi, int64_t min_depth_ceil, uint8_t* calls,
                    int32_t* reduced, void* stream);
+/* Same, with each table's footprint: peer p only holds non-zero counts in slots
+ * [foot_lo[p], foot_hi[p]) (host int64 arrays, multiples of 4), so a read-sharded, coordinate-sorted
+ * job pulls only the halo of its neighbours over NVLink instead of every table. */
+int kdl_vote_peers_sparse(const int32_t* const* peer_counts, const int64_t* foot_lo, const int64_t* foot_hi,
+                          int32_t n_peers, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
+                          int64_t min_depth_ceil, uint8_t* calls, int32_t* reduced, void* stream);
+
+/* Count tables that peer GPUs (other processes of the same node) can map: plain cudaMalloc
+ * memory exported / opened with CUDA IPC.  kdl_table_alloc zero-fills. */
+int kdl_table_alloc(int64_t bytes, void** dev_ptr);
+int kdl_table_free(void* dev_ptr);
+int kdl_ipc_export(void* dev_ptr, uint8_t handle[64]);
+int kdl_ipc_open(const uint8_t handle[64], void** dev_ptr);
+int kdl_ipc_close(void* dev_ptr);
 
 /* ---- host-buffer path (what a cgo/JNI/ctypes caller without its own CUDA runtime uses) ---- */
 typedef struct kdl_ctx kdl_ctx;

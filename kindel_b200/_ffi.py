@@ -72,6 +72,13 @@ _PROTOTYPES = {
     "kdl_derive": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "kdl_vote_peers": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_vote_peers_sparse": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32,
+                                        C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_table_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "kdl_table_free": (C.c_int, [C.c_void_p]),
+    "kdl_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "kdl_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "kdl_ipc_close": (C.c_int, [C.c_void_p]),
     "kdl_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "kdl_ctx_destroy": (None, [C.c_void_p]),
     "kdl_ctx_consensus": (C.c_int, [C.c_void_p, C.POINTER(KdlBatch), C.c_int64, C.c_int64, C.c_int64,

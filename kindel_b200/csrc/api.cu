@@ -148,6 +148,37 @@ int kdl_derive(const int32_t* counts, int64_t n_slots, int32_t* out, void* strea
 int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n_slots,
                    int64_t slot_lo, int64_t slot_hi, int64_t min_depth_ceil, uint8_t* calls,
                    int32_t* reduced, void* stream) {
+    return kdl_vote_peers_sparse(peer_counts, nullptr, nullptr, n_peers, n_slots, slot_lo, slot_hi,
+                                 min_depth_ceil, calls, reduced, stream);
+}
+
+int kdl_table_alloc(int64_t bytes, void** dev_ptr) {
+    if (!dev_ptr || bytes <= 0) return KDL_ERR_INVALID_ARG;
+    *dev_ptr = nullptr;
+    if (cudaMalloc(dev_ptr, (size_t)bytes) != cudaSuccess) return KDL_ERR_CUDA;
+    if (cudaMemset(*dev_ptr, 0, (size_t)bytes) != cudaSuccess) return KDL_ERR_CUDA;
+    return KDL_OK;
+}
+int kdl_table_free(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? KDL_OK : KDL_ERR_CUDA; }
+int kdl_ipc_export(void* dev_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!dev_ptr || !handle) return KDL_ERR_INVALID_ARG;
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, dev_ptr) != cudaSuccess) return KDL_ERR_CUDA;
+    std::memcpy(handle, &h, 64);
+    return KDL_OK;
+}
+int kdl_ipc_open(const uint8_t handle[64], void** dev_ptr) {
+    if (!dev_ptr || !handle) return KDL_ERR_INVALID_ARG;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    return cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? KDL_OK : KDL_ERR_CUDA;
+}
+int kdl_ipc_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? KDL_OK : KDL_ERR_CUDA; }
+
+int kdl_vote_peers_sparse(const int32_t* const* peer_counts, const int64_t* foot_lo, const int64_t* foot_hi,
+                          int32_t n_peers, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
+                          int64_t min_depth_ceil, uint8_t* calls, int32_t* reduced, void* stream) {
     if (!peer_counts || n_peers < 1 || n_peers > 16 || !calls || n_slots <= 0 || (n_slots & 3) ||
         slot_lo < 0 || slot_hi > n_slots || (slot_lo & 3) || (slot_hi & 3))
         return KDL_ERR_INVALID_ARG;
@@ -157,6 +188,9 @@ int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n
     for (int p = 0; p < n_peers; ++p) {
         if (!peer_counts[p]) return KDL_ERR_INVALID_ARG;
         peers.tab[p] = peer_counts[p];
+        peers.lo[p] = foot_lo ? foot_lo[p] : 0;
+        peers.hi[p] = foot_hi ? foot_hi[p] : n_slots;
+        if ((peers.lo[p] & 3) || (peers.hi[p] & 3)) return KDL_ERR_INVALID_ARG;
     }
     const long long quads = (slot_hi - slot_lo) / 4;
     const long long grid = (quads + 255) / 256;

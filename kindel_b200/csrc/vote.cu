@@ -15,6 +15,7 @@ namespace kdl {
 
 struct Peers {
     const int32_t* tab[16];
+    long long lo[16], hi[16];  // footprint of each table: zero outside [lo, hi)
     int n;
 };
 
@@ -26,6 +27,7 @@ __device__ __forceinline__ int4 load4(const int32_t* __restrict__ counts, const 
     } else {
         int4 acc = make_int4(0, 0, 0, 0);
         for (int p = 0; p < peers.n; ++p) {
+            if (s + 4 <= peers.lo[p] || s >= peers.hi[p]) continue;  // nothing of peer p here
             // peer tables are written by other GPUs: plain (coherent) loads, not the nc path
             const int4 v = *reinterpret_cast<const int4*>(peers.tab[p] + (long long)col * n_slots + s);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -41,7 +43,8 @@ __device__ __forceinline__ int load1(const int32_t* __restrict__ counts, const P
         return __ldg(counts + (long long)col * n_slots + s);
     } else {
         int acc = 0;
-        for (int p = 0; p < peers.n; ++p) acc += peers.tab[p][(long long)col * n_slots + s];
+        for (int p = 0; p < peers.n; ++p)
+            if (s >= peers.lo[p] && s < peers.hi[p]) acc += peers.tab[p][(long long)col * n_slots + s];
         return acc;
     }
 }

@@ -1,0 +1,239 @@
+"""Read-sharded pileup over the GPUs of one node (one process per GPU, `torch.distributed`).
+
+The reference has no parallelism at all; SURVEY.md 8(e) defines the sharding: every record's
+contribution is an independent set of +1s (reference kindel/kindel.py:40-81 has no cross-read
+state) and counts are integer sums, so the coordinate-sorted read array is cut into contiguous
+blocks -- one per rank -- and the only exchange step is an exact int32 sum of the seven vote
+columns in front of the per-position vote (kindel.py:402-424).
+
+Two ways to do that exchange, both bit-identical to one GPU:
+
+  "allreduce"  NCCL all_reduce(SUM) of columns 0..6, then K2 on every rank (what the north star words).
+  "peer"       the fused kernel K2p (`kdl_vote_peers_sparse`): every rank owns a slice of the slots,
+               reads the seven columns of that slice straight out of the peers' tables over NVLink
+               (CUDA IPC mappings), sums, votes, writes its call bytes; the call slices are then
+               all-gathered (1 byte per slot).  Because the shards are blocks of sorted reads, each
+               table is non-zero only on its block's footprint, and the kernel is told the
+               footprints: a rank pulls just the halo (<= one read length) of its neighbours
+               instead of N full tables.
+
+Host-side helpers (`shard_batch`, `footprint`, `owner_slices`) are plain numpy and are exercised
+with a 2-process gloo group on CPU in tests/test_distributed_cpu.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _ffi, bamio
+
+
+def shard_batch(batch: bamio.ReadBatch, rank: int, world: int) -> bamio.ReadBatch:
+    """Rank's contiguous block of the reads of every contig (order and layout preserved)."""
+    if world == 1:
+        return batch
+    keep = np.zeros(batch.n_reads, dtype=bool)
+    read_off = [0]
+    for c in range(batch.n_contigs):
+        lo, hi = int(batch.contig_read_off[c]), int(batch.contig_read_off[c + 1])
+        a = lo + (hi - lo) * rank // world
+        b = lo + (hi - lo) * (rank + 1) // world
+        keep[a:b] = True
+        read_off.append(read_off[-1] + (b - a))
+    idx = np.flatnonzero(keep)
+    n = idx.shape[0]
+    lseq = batch.l_seq[idx].astype(np.int64) & 0x7FFFFFFF
+    n_cig = np.diff(batch.cig_off.astype(np.int64))[idx]
+    # gather the ragged CIGAR and base ranges of the kept reads
+    cig_off = np.concatenate(([0], np.cumsum(n_cig)))
+    cig_src = np.repeat(batch.cig_off[:-1].astype(np.int64)[idx], n_cig) + (
+        np.arange(int(cig_off[-1])) - np.repeat(cig_off[:-1], n_cig))
+    words = (lseq + 7) // 8
+    # a simple read stores its op length in l_seq: its SEQ length is the same (flatten contract)
+    seq_off = np.concatenate(([0], np.cumsum(words)))
+    seq_src = np.repeat(batch.seq_off.astype(np.int64)[idx], words) + (
+        np.arange(int(seq_off[-1])) - np.repeat(seq_off[:-1], words))
+    return bamio.finalize(batch.contig_names, batch.contig_len, np.array(read_off), batch.ref_start[idx],
+                          seq_off[:-1], lseq, cig_off, batch.cigar[cig_src], batch.seq4[seq_src], n_records=n)
+
+
+def footprint(batch: bamio.ReadBatch, align: int = 4):
+    """[lo, hi) slot range outside of which this shard's count table is certainly zero.
+    Conservative: every read may touch from (start - its soft clips) to (start + reference span +
+    clips); bounded here by SEQ length + reference-consuming CIGAR length on both sides."""
+    if batch.n_reads == 0:
+        return 0, 0
+    per_contig = np.diff(batch.contig_read_off)
+    gstart = np.repeat(batch.contig_slot, per_contig) + batch.ref_start.astype(np.int64)
+    lseq = batch.l_seq.astype(np.int64) & 0x7FFFFFFF
+    oplen = (batch.cigar >> 4).astype(np.int64)
+    csum = np.concatenate(([0], np.cumsum(oplen)))
+    span = csum[batch.cig_off[1:].astype(np.int64)] - csum[batch.cig_off[:-1].astype(np.int64)]
+    reach = np.maximum(lseq, span) + 2
+    lo = int((gstart - reach).min())
+    hi = int((gstart + reach).max()) + 1
+    # POS == 0 wraps to the END of the contig: such shards claim everything
+    if (batch.ref_start < 0).any():
+        return 0, int(batch.n_slots)
+    lo = max(0, lo) // align * align
+    hi = min(int(batch.n_slots), (hi + align - 1) // align * align)
+    return lo, hi
+
+
+def owner_slices(n_slots: int, world: int, align: int = 512):
+    """Equal split of the slot space, boundaries on multiples of `align`."""
+    units = n_slots // align
+    cuts = [units * r // world * align for r in range(world)] + [n_slots]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class PeerTables:
+    """This rank's IPC-exportable count table plus mappings of every peer's table."""
+
+    def __init__(self, n_slots: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.lib = _ffi.load()
+        self.n_slots = n_slots
+        self.device = device
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        nbytes = _ffi.KDL_NCOL * n_slots * 4
+        ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            _ffi.check(self.lib.kdl_table_alloc(nbytes, C.byref(ptr)), "kdl_table_alloc")
+            handle = C.create_string_buffer(64)
+            _ffi.check(self.lib.kdl_ipc_export(ptr, handle), "kdl_ipc_export")
+        self.ptr = ptr.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer_ptrs = []
+        self._opened = []
+        with torch.cuda.device(device):
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.peer_ptrs.append(self.ptr)
+                    continue
+                p = C.c_void_p()
+                _ffi.check(self.lib.kdl_ipc_open(h, C.byref(p)), "kdl_ipc_open")
+                self.peer_ptrs.append(p.value)
+                self._opened.append(p.value)
+        self.counts = _wrap_device_memory(self.ptr, (_ffi.KDL_NCOL, n_slots), device)
+
+    def close(self):
+        import torch
+
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self.lib.kdl_ipc_close(p)
+            self._opened = []
+            if self.ptr:
+                self.lib.kdl_table_free(self.ptr)
+                self.ptr = None
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def _wrap_device_memory(ptr: int, shape, device):
+    """torch view (int32) over memory this library allocated (no copy)."""
+    import torch
+
+    with torch.cuda.device(device):
+        return torch.as_tensor(_CudaArray(ptr, tuple(shape)), device=device)
+
+
+class ShardedConsensus:
+    """One rank's part of a read-sharded pileup + vote.  `step()` is the whole exchange + vote."""
+
+    def __init__(self, shard: bamio.ReadBatch, device, mode: str = "peer", group=None):
+        import torch
+        import torch.distributed as dist
+
+        from . import engine
+
+        self.torch, self.dist, self.engine = torch, dist, engine
+        self.shard, self.device, self.mode, self.group = shard, device, mode, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.n_slots = shard.n_slots
+        self.dbatch = engine.upload(shard, device)
+        self.lib = _ffi.load()
+        if mode == "peer":
+            self.tables = PeerTables(self.n_slots, device, group)
+            self.counts = self.tables.counts
+            feet = [None] * self.world
+            dist.all_gather_object(feet, footprint(shard), group=group)
+            self.foot_lo = (C.c_int64 * self.world)(*[f[0] for f in feet])
+            self.foot_hi = (C.c_int64 * self.world)(*[f[1] for f in feet])
+            self.ptr_arr = (C.c_void_p * self.world)(*self.tables.peer_ptrs)
+            self.slices = owner_slices(self.n_slots, self.world)
+            self.calls = torch.empty(self.n_slots, dtype=torch.uint8, device=device)
+            self.sizes = [hi - lo for lo, hi in self.slices]
+        elif mode == "allreduce":
+            self.tables = None
+            self.counts = torch.zeros((_ffi.KDL_NCOL, self.n_slots), dtype=torch.int32, device=device)
+        else:
+            raise ValueError("mode must be 'peer' or 'allreduce'")
+
+    def step(self, min_depth=1, timers=None):
+        """zero, K1 on the shard, exchange, vote.  Returns the complete call bytes on every rank.
+        `timers`: optional pair of CUDA events recorded around K1 (bench.py's roofline leg)."""
+        torch, dist, engine = self.torch, self.dist, self.engine
+        self.counts.zero_()
+        if timers:
+            timers[0].record()
+        engine.pileup(self.dbatch, self.counts, check=False)
+        if timers:
+            timers[1].record()
+        if self.mode == "allreduce":
+            dist.all_reduce(self.counts[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM, group=self.group)
+            return engine.vote(self.counts, min_depth)
+        # every table complete before anybody reads it over NVLink
+        dist.barrier(group=self.group)
+        lo, hi = self.slices[self.rank]
+        with torch.cuda.device(self.device):
+            rc = self.lib.kdl_vote_peers_sparse(
+                self.ptr_arr, self.foot_lo, self.foot_hi, self.world, self.n_slots, lo, hi,
+                int(math.ceil(min_depth)), self.calls.data_ptr(), None,
+                int(torch.cuda.current_stream(self.device).cuda_stream))
+        _ffi.check(rc, "kdl_vote_peers_sparse")
+        # 1 byte per slot; also the fence after which peers may overwrite their tables again
+        self._gather_calls(lo, hi)
+        return self.calls
+
+    def _gather_calls(self, lo, hi):
+        torch, dist = self.torch, self.dist
+        chunk = max(self.sizes)
+        if all(sz == chunk for sz in self.sizes):
+            dist.all_gather_into_tensor(self._recv(chunk), self.calls[lo:hi].clone(), group=self.group)
+            self.calls.copy_(self._recv(chunk))
+            return
+        send = torch.zeros(chunk, dtype=torch.uint8, device=self.device)
+        send[: hi - lo] = self.calls[lo:hi]
+        recv = self._recv(chunk)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        for r, (a, b) in enumerate(self.slices):
+            self.calls[a:b] = recv[r * chunk: r * chunk + (b - a)]
+
+    def _recv(self, chunk):
+        if getattr(self, "_recv_buf", None) is None or self._recv_buf.numel() != chunk * self.world:
+            self._recv_buf = self.torch.empty(chunk * self.world, dtype=self.torch.uint8, device=self.device)
+        return self._recv_buf
+
+    def check_errors(self):
+        """Raise the reference's exception if any rank's shard hit a data error (first rank wins)."""
+        # engine.pileup(check=False) leaves the flag unread in the hot loop; a checked pass is
+        # `engine.pileup(self.dbatch)` on a scratch table, which raises exactly like one GPU.
+        counts = self.torch.zeros_like(self.counts)
+        self.engine.pileup(self.dbatch, counts, check=True)
+
+    def close(self):
+        if self.tables is not None:
+            self.tables.close()

@@ -231,3 +231,22 @@ def test_synthetic_config4_full_size():
     c = _against_oracle(b)
     depth = c[0:5].sum(axis=0)
     assert abs(float(depth[1000:-1000].mean()) - 200.0) < 1.0
+
+
+def test_multi_gpu_exchange_modes_match_one_gpu():
+    """N = 2 (or more) ranks over NCCL: fused peer-memory vote and all_reduce+vote == oracle."""
+    import subprocess
+    import sys
+
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    n = 2 if n < 4 else 4
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", "29533",
+           os.path.join(os.path.dirname(os.path.abspath(__file__)), "dist_gpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "dist parity ok" in res.stdout

@@ -212,13 +212,14 @@ def run_native(args):
     k1_bytes, k2_bytes = algorithmic_bytes(batch)
     if world == 1:
         db = engine.upload(batch, dev)
-        counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
+        table = engine.CountTable(n_slots, dev)
+        counts = table.t
 
         def step(timers=None):
-            counts.zero_()
+            # a fresh pileup into a reused table: nothing is memset, K1f overwrites the weight columns
             if timers:
                 timers[0].record()
-            engine.pileup(db, counts, check=False)
+            engine.pileup(db, check=False, table=table)
             if timers:
                 timers[1].record()
             return engine.vote(counts, 1)
@@ -308,8 +309,10 @@ def run_native(args):
             "config": {"workload": args.workload, "reads_total": None, "aligned_bases_total": int(total_bases),
                        "sharding": "contiguous blocks of the coordinate-sorted reads" if world > 1 else "none",
                        "reduction": ("none" if world == 1 else
-                                     "fused K2p: vote over peer tables mapped with CUDA IPC (NVLink), footprint-clipped, "
-                                     "+ NCCL all_gather of call bytes" if args.exchange == "peer" else
+                                     "K2x: flags + reduce + vote + call scatter in one kernel over CUDA-IPC peer memory "
+                                     "(NVLink), footprint-clipped; no NCCL on the data path" if args.exchange == "fused" else
+                                     "K2p: vote over peer tables (NVLink), NCCL barrier + all_gather of call bytes"
+                                     if args.exchange == "peer" else
                                      "NCCL all_reduce(int32 sum) of the 7 vote columns, vote replicated"),
                        "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
             "roofline": {"bound": "hbm", "kernel": "K1 pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -334,8 +337,10 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4_5Mb_200x")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--exchange", choices=["peer", "allreduce"], default="peer",
-                    help="N > 1: fused peer-memory reduce+vote kernel, or NCCL all_reduce then vote")
+    ap.add_argument("--exchange", choices=["fused", "peer", "allreduce"], default="fused",
+                    help="N > 1: fused = flags + reduce + vote + call scatter over NVLink peer memory (no NCCL on "
+                         "the data path); peer = same kernel with NCCL barrier/all_gather; allreduce = NCCL "
+                         "all_reduce of the vote columns, vote replicated")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -137,6 +137,17 @@ int64_t kdl_launch_count(void);
 int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t* ins_events,
                int32_t* err_flag, void* stream);
 
+/* Same as kdl_pileup, restricted to the slot range [slot_lo, slot_hi) (multiples of KDL_TILE) that
+ * contains everything the batch can touch (a shard's footprint), with control over zeroing:
+ *   KDL_PILEUP_FRESH_WEIGHTS  columns 0..4 of the range hold stale data: the tile-owner kernel
+ *                             OVERWRITES them (plain stores, no prior memset, no read-modify-write)
+ *   KDL_PILEUP_ZERO_REST      columns 5..18 of the range are zeroed first (needed only when an
+ *                             earlier pileup with complex reads dirtied them) */
+#define KDL_PILEUP_FRESH_WEIGHTS 1
+#define KDL_PILEUP_ZERO_REST 2
+int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int64_t slot_lo,
+                     int64_t slot_hi, int32_t flags, int32_t* ins_events, int32_t* err_flag, void* stream);
+
 /* Exact first error in reference iteration order (only needed when err_flag[0] != 0).
  * `diag_dev`: device kdl_diag, written asynchronously. */
 int kdl_diagnose(const kdl_batch* batch, kdl_diag* diag_dev, void* stream);
@@ -166,6 +177,34 @@ int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n
 int kdl_vote_peers_sparse(const int32_t* const* peer_counts, const int64_t* foot_lo, const int64_t* foot_hi,
                           int32_t n_peers, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
                           int64_t min_depth_ceil, uint8_t* calls, int32_t* reduced, void* stream);
+
+/* ---- fully fused exchange (no NCCL on the data path) ------------------------------------------
+ * Every rank owns one IPC block: [count table 19 x n_slots int32][calls n_slots bytes][flags].
+ * Per step (epoch e = 1, 2, ...), on every rank, in stream order:
+ *   kdl_pileup(...)                       its shard into its own table
+ *   kdl_exchange_signal(x, e)             "my table is complete" -> ready[p][rank] = e in every peer p
+ *   kdl_exchange_vote(x, ..., e)          K2x: waits for ready[rank][*] >= e, sums the 7 vote columns
+ *                                         of its slot slice over the (footprint-clipped) peer tables
+ *                                         through NVLink, votes, stores the call bytes into EVERY
+ *                                         rank's call buffer, then done[p][rank] = e
+ *   kdl_exchange_wait(x, e)               waits for done[rank][*] >= e: all slices have landed here
+ *                                         and nobody still reads this rank's table
+ * All pointers of rank p (tables[p], calls[p], ready[p], done[p]) are this process's mappings of
+ * rank p's block (own block: the local pointer). */
+typedef struct kdl_exchange {
+    int32_t n_ranks, rank;
+    const int32_t* tables[16];
+    uint8_t* calls[16];
+    int32_t* ready[16]; /* int32[16] per rank */
+    int32_t* done[16];  /* int32[16] per rank */
+    int64_t foot_lo[16], foot_hi[16];
+    int32_t* counter;   /* local device int32, zero-initialised */
+} kdl_exchange;
+
+int kdl_exchange_signal(const kdl_exchange* x, int32_t epoch, void* stream);
+int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
+                      int64_t min_depth_ceil, int32_t epoch, void* stream);
+int kdl_exchange_wait(const kdl_exchange* x, int32_t epoch, void* stream);
 
 /* Count tables that peer GPUs (other processes of the same node) can map: plain cudaMalloc
  * memory exported / opened with CUDA IPC.  kdl_table_alloc zero-fills. */

@@ -20,6 +20,8 @@ KDL_NCOL = 19
 KDL_NVOTE_COL = 7
 KDL_COMPLEX = 0x80000000
 KDL_TILE = 512
+KDL_PILEUP_FRESH_WEIGHTS = 1
+KDL_PILEUP_ZERO_REST = 2
 KDL_FAST_MAXLEN = 8192
 KDL_OK = 0
 KDL_ERR_INDEX = 10
@@ -51,6 +53,20 @@ class KdlBatch(C.Structure):
     ]
 
 
+class KdlExchange(C.Structure):
+    _fields_ = [
+        ("n_ranks", C.c_int32),
+        ("rank", C.c_int32),
+        ("tables", C.c_void_p * 16),
+        ("calls", C.c_void_p * 16),
+        ("ready", C.c_void_p * 16),
+        ("done", C.c_void_p * 16),
+        ("foot_lo", C.c_int64 * 16),
+        ("foot_hi", C.c_int64 * 16),
+        ("counter", C.c_void_p),
+    ]
+
+
 class KdlDiag(C.Structure):
     _fields_ = [
         ("status", C.c_int32),
@@ -67,6 +83,8 @@ _PROTOTYPES = {
     "kdl_status_string": (C.c_char_p, [C.c_int]),
     "kdl_launch_count": (C.c_int64, []),
     "kdl_pileup": (C.c_int, [C.POINTER(KdlBatch), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_pileup_range": (C.c_int, [C.POINTER(KdlBatch), C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdl_diagnose": (C.c_int, [C.POINTER(KdlBatch), C.c_void_p, C.c_void_p]),
     "kdl_vote": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "kdl_derive": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
@@ -74,6 +92,10 @@ _PROTOTYPES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdl_vote_peers_sparse": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32,
                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_exchange_signal": (C.c_int, [C.POINTER(KdlExchange), C.c_int32, C.c_void_p]),
+    "kdl_exchange_vote": (C.c_int, [C.POINTER(KdlExchange), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
+                                    C.c_void_p]),
+    "kdl_exchange_wait": (C.c_int, [C.POINTER(KdlExchange), C.c_int32, C.c_void_p]),
     "kdl_table_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "kdl_table_free": (C.c_int, [C.c_void_p]),
     "kdl_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p]),

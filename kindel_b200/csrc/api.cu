@@ -68,39 +68,63 @@ int64_t kdl_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 
 int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t* ins_events,
                int32_t* err_flag, void* stream) {
+    return kdl_pileup_range(batch, counts, n_slots, 0, n_slots, 0, ins_events, err_flag, stream);
+}
+
+int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int64_t slot_lo,
+                     int64_t slot_hi, int32_t flags, int32_t* ins_events, int32_t* err_flag, void* stream) {
     int rc = validate_batch(batch);
     if (rc != KDL_OK) return rc;
-    if (!counts || !err_flag || n_slots <= 0) return KDL_ERR_INVALID_ARG;
-    if (batch->n_reads == 0) return KDL_OK;
+    if (!counts || !err_flag || n_slots <= 0 || slot_lo < 0 || slot_hi > n_slots || slot_lo > slot_hi)
+        return KDL_ERR_INVALID_ARG;
+    const bool tileable = (n_slots % KDL_TILE) == 0 && (slot_lo % KDL_TILE) == 0 && (slot_hi % KDL_TILE) == 0;
+    if ((slot_lo & 3) || (slot_hi & 3)) return KDL_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int cap = sm_count() * 8;
-    if (batch->n_reads > batch->n_complex) {
-        const bool tiled = batch->reads_sorted && batch->tile_index && batch->max_simple_len > 0 &&
-                           batch->max_simple_len <= KDL_FAST_MAXLEN && (n_slots % KDL_TILE) == 0;
-        if (tiled) {
-            // K0: read range per tile (the linear index of a sorted BAM, built on the device)
-            const long long n_tiles = n_slots / KDL_TILE;
-            kdl::tile_index_kernel<<<(unsigned)((n_tiles + 255) / 256), 256, 0, st>>>(*batch, n_tiles,
+    const bool has_simple = batch->n_reads > batch->n_complex;
+    const bool tiled = has_simple && tileable && batch->reads_sorted && batch->tile_index &&
+                       batch->max_simple_len > 0 && batch->max_simple_len <= KDL_FAST_MAXLEN;
+    const bool fresh = (flags & KDL_PILEUP_FRESH_WEIGHTS) != 0;
+    // zeroing that the chosen kernels will not do themselves
+    const int zero_from = (fresh && !tiled) ? 0 : 5;
+    const int zero_to = (flags & KDL_PILEUP_ZERO_REST) ? KDL_NCOL : 5;
+    if (zero_to > zero_from && slot_hi > slot_lo) {
+        kdl::zero_cols_kernel<<<sm_count() * 4, 256, 0, st>>>(counts, n_slots, zero_from, zero_to, slot_lo, slot_hi);
+        if ((rc = check_launch()) != KDL_OK) return rc;
+    }
+    if (batch->n_reads == 0) return KDL_OK;
+    if (tiled) {
+        // K0: read range per tile (the linear index of a sorted BAM, built on the device)
+        const long long n_tiles_all = n_slots / KDL_TILE;
+        kdl::tile_index_kernel<<<(unsigned)((n_tiles_all + 255) / 256), 256, 0, st>>>(*batch, n_tiles_all,
                                                                                    batch->tile_index);
-            if ((rc = check_launch()) != KDL_OK) return rc;
-            // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
-            static bool attr_set = false;
-            const int smem = (int)sizeof(kdl::FastSmem);
-            if (!attr_set) {
-                if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem) != cudaSuccess)
-                    return KDL_ERR_CUDA;
-                attr_set = true;
-            }
+        if ((rc = check_launch()) != KDL_OK) return rc;
+        // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
+        static bool attr_set = false;
+        const int smem = (int)sizeof(kdl::FastSmem);
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem) != cudaSuccess ||
+                cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smem) != cudaSuccess)
+                return KDL_ERR_CUDA;
+            attr_set = true;
+        }
+        const long long tile_lo = slot_lo / KDL_TILE, n_tiles = (slot_hi - slot_lo) / KDL_TILE;
+        if (n_tiles > 0) {
             long long grid = n_tiles < (long long)sm_count() * 2 * 4 ? n_tiles : (long long)sm_count() * 2 * 4;
-            kdl::pileup_tiled_kernel<<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(*batch, counts, n_slots,
-                                                                                  batch->tile_index, n_tiles);
-            if ((rc = check_launch()) != KDL_OK) return rc;
-        } else {
-            const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
-            kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
+            if (fresh)
+                kdl::pileup_tiled_kernel<true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            else
+                kdl::pileup_tiled_kernel<false><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
+    } else if (has_simple) {
+        const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
+        kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
+        if ((rc = check_launch()) != KDL_OK) return rc;
     }
     if (batch->n_complex > 0) {
         const int grid = grid_for(batch->n_complex, 8, cap);
@@ -150,6 +174,59 @@ int kdl_vote_peers(const int32_t* const* peer_counts, int32_t n_peers, int64_t n
                    int32_t* reduced, void* stream) {
     return kdl_vote_peers_sparse(peer_counts, nullptr, nullptr, n_peers, n_slots, slot_lo, slot_hi,
                                  min_depth_ceil, calls, reduced, stream);
+}
+
+static int make_exchange(const kdl_exchange* x, kdl::Exchange* e, int64_t n_slots) {
+    if (!x || x->n_ranks < 1 || x->n_ranks > 16 || x->rank < 0 || x->rank >= x->n_ranks || !x->counter)
+        return KDL_ERR_INVALID_ARG;
+    e->peers.n = x->n_ranks;
+    e->rank = x->rank;
+    e->counter = x->counter;
+    for (int p = 0; p < x->n_ranks; ++p) {
+        if (!x->tables[p] || !x->calls[p] || !x->ready[p] || !x->done[p]) return KDL_ERR_INVALID_ARG;
+        e->peers.tab[p] = x->tables[p];
+        e->peers.lo[p] = x->foot_lo[p];
+        e->peers.hi[p] = n_slots > 0 && x->foot_hi[p] > n_slots ? n_slots : x->foot_hi[p];
+        if ((e->peers.lo[p] & 3) || (e->peers.hi[p] & 3)) return KDL_ERR_INVALID_ARG;
+        e->calls[p] = x->calls[p];
+        e->ready[p] = x->ready[p];
+        e->done[p] = x->done[p];
+    }
+    e->ready_local = x->ready[x->rank];
+    e->done_local = x->done[x->rank];
+    return KDL_OK;
+}
+
+int kdl_exchange_signal(const kdl_exchange* x, int32_t epoch, void* stream) {
+    kdl::Exchange e;
+    int rc = make_exchange(x, &e, 0);
+    if (rc != KDL_OK) return rc;
+    kdl::exchange_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e, epoch);
+    return check_launch();
+}
+
+int kdl_exchange_wait(const kdl_exchange* x, int32_t epoch, void* stream) {
+    kdl::Exchange e;
+    int rc = make_exchange(x, &e, 0);
+    if (rc != KDL_OK) return rc;
+    kdl::exchange_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e, epoch);
+    return check_launch();
+}
+
+int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
+                      int64_t min_depth_ceil, int32_t epoch, void* stream) {
+    if (n_slots <= 0 || (n_slots & 3) || slot_lo < 0 || slot_hi > n_slots || (slot_lo & 3) || (slot_hi & 3) ||
+        slot_hi < slot_lo)
+        return KDL_ERR_INVALID_ARG;
+    kdl::Exchange e;
+    int rc = make_exchange(x, &e, n_slots);
+    if (rc != KDL_OK) return rc;
+    const long long quads = (slot_hi - slot_lo) / 4;
+    long long grid = (quads + 255) / 256;
+    if (grid < 1) grid = 1;  // an empty slice still has to take part in the flag protocol
+    kdl::vote_exchange_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(e, n_slots, slot_lo, slot_hi,
+                                                                              min_depth_ceil, epoch);
+    return check_launch();
 }
 
 int kdl_table_alloc(int64_t bytes, void** dev_ptr) {

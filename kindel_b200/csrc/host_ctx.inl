@@ -11,6 +11,8 @@ struct kdl_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float ms[3] = {0.f, 0.f, 0.f};
+    int64_t table_slots = -1;  // layout of the count table left by the previous call (-1: none)
+    bool table_dirty_rest = false;
     struct Buf {
         void* p = nullptr;
         size_t cap = 0;
@@ -26,6 +28,7 @@ struct kdl_ctx {
         if (b.p) cudaFree(b.p);
         b.p = nullptr;
         b.cap = 0;
+        if (which == B_COUNTS) table_slots = -1;  // a new buffer holds garbage
         size_t want = bytes + bytes / 8;  // slack so slowly growing batches do not reallocate
         if (cudaMalloc(&b.p, want) != cudaSuccess) {
             if (cudaMalloc(&b.p, bytes) != cudaSuccess) return KDL_ERR_CUDA;
@@ -133,9 +136,21 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     int32_t* d_events = (int32_t*)c->buf[kdl_ctx::B_EVENTS].p;
     uint8_t* d_calls = (uint8_t*)c->buf[kdl_ctx::B_CALLS].p;
     int32_t* d_flag = (int32_t*)c->buf[kdl_ctx::B_FLAG].p;
-    if (cudaMemsetAsync(d_counts, 0, (size_t)n_slots * KDL_NCOL * 4, st) != cudaSuccess) return KDL_ERR_CUDA;
     if (cudaMemsetAsync(d_flag, 0, 16, st) != cudaSuccess) return KDL_ERR_CUDA;
-    if ((rc = kdl_pileup(&db, d_counts, n_slots, n_events ? d_events : nullptr, d_flag, st)) != KDL_OK) return rc;
+    // the table is reused from call to call: memset only when its layout changed (or the buffer is
+    // new); otherwise the kernels overwrite the weight columns and zero the rest only if dirty
+    int32_t pflags = 0;
+    if (c->table_slots != n_slots) {
+        if (cudaMemsetAsync(d_counts, 0, (size_t)n_slots * KDL_NCOL * 4, st) != cudaSuccess) return KDL_ERR_CUDA;
+    } else {
+        pflags = KDL_PILEUP_FRESH_WEIGHTS | (c->table_dirty_rest ? KDL_PILEUP_ZERO_REST : 0);
+    }
+    c->table_slots = -1;  // until this call has gone through
+    if ((rc = kdl_pileup_range(&db, d_counts, n_slots, 0, n_slots, pflags, n_events ? d_events : nullptr, d_flag,
+                               st)) != KDL_OK)
+        return rc;
+    c->table_slots = n_slots;
+    c->table_dirty_rest = hb->n_complex > 0;
     if ((rc = kdl_vote(d_counts, n_slots, min_depth_ceil, d_calls, st)) != KDL_OK) return rc;
     cudaEventRecord(c->ev[2], st);
 

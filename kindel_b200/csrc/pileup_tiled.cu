@@ -188,12 +188,14 @@ __device__ __forceinline__ void extract8(const uint32_t (&pl)[F_P + 2], int bit,
 // Add the window's counters to the table.  Quarter q owns column q (A,C,G,T); quarter 0 also adds
 // column 4 (N).  Each lane holds 8 consecutive slots -> two 128-bit read-modify-writes per column;
 // no other thread of the grid touches these slots during this kernel.
+template <bool kStore>
 __device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t* __restrict__ counts,
                                              long long n_slots, long long slot0, int lane) {
     const int q = lane >> 3;
     const long long s = slot0 + 8 * (lane & 7);
     int4* dst = reinterpret_cast<int4*>(counts + (long long)q * n_slots + s);
-    int4 v0 = dst[0], v1 = dst[1];  // issued first: their latency hides behind the transposition
+    int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
+    if (!kStore) { v0 = dst[0]; v1 = dst[1]; }  // issued first: latency hides behind the transposition
     uint32_t m[F_P + 2], n[F_P + 2];
     quarter_sum(acc.p, m);
     quarter_sum(accn.p, n);
@@ -208,7 +210,8 @@ __device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t*
     dst[1] = v1;
     if (q == 0) {
         int4* dn = reinterpret_cast<int4*>(counts + (long long)KDL_W_N * n_slots + s);
-        int4 n0 = dn[0], n1 = dn[1];
+        int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
+        if (!kStore) { n0 = dn[0]; n1 = dn[1]; }
         n0.x += cn[0]; n0.y += cn[1]; n0.z += cn[2]; n0.w += cn[3];
         n1.x += cn[4]; n1.y += cn[5]; n1.z += cn[6]; n1.w += cn[7];
         dn[0] = n0;
@@ -225,9 +228,12 @@ struct FastSmem {
     uint64_t bar;       // mbarrier the bulk copy of seq[] completes on
 };
 
+// kFresh: columns 0..4 hold stale data; the first flush of every window stores instead of adding,
+// and windows / tiles without reads are stored as zeros.
+template <bool kFresh>
 __global__ void __launch_bounds__(F_THREADS, 2)
 pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
-                    const uint32_t* __restrict__ tile_index, long long n_tiles) {
+                    const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -237,12 +243,20 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
     if (tid == 0) mbar_init(&sm.bar, 1);
     __syncthreads();
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
         const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
         const uint2 ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
         const long long lo = ix.x, hi = ix.y;
-        if (lo >= hi) continue;  // uniform for the CTA
         const long long tile_slot = tile * KDL_TILE;
+        if (lo >= hi) {  // uniform for the CTA: no read reaches this tile
+            if (kFresh) {  // 5 columns x 512 slots of zeros, 128-bit stores
+                for (int v = tid; v < 5 * (KDL_TILE / 4); v += F_THREADS) {
+                    const int col = v / (KDL_TILE / 4), off = v % (KDL_TILE / 4);
+                    reinterpret_cast<int4*>(counts + (long long)col * n_slots + tile_slot)[off] = make_int4(0, 0, 0, 0);
+                }
+            }
+            continue;
+        }
         const bool one_contig = ic.x == ic.y;
         const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
         const int wlo = warp * F_WIN;
@@ -251,6 +265,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
         acc.clear();
         accn.clear();
         int blocks_since_flush = 0;
+        bool stored = false;  // kFresh: has this window been written yet?
 
         long long c0 = lo;
         while (c0 < hi) {
@@ -373,13 +388,29 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                 acc.add8(x);
                 accn.add8(xn);
                 if (++blocks_since_flush == F_FLUSH_BLOCKS) {
-                    flush_window(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+                    if (kFresh && !stored) flush_window<true>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+                    else flush_window<false>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+                    stored = true;
                     blocks_since_flush = 0;
                 }
             }
             c0 = c1;
         }
-        if (blocks_since_flush) flush_window(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+        if (kFresh && !stored) flush_window<true>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+        else if (blocks_since_flush) flush_window<false>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+    }
+}
+
+// zero columns [col_lo, col_hi) of slots [slot_lo, slot_hi) (multiples of 4), 128-bit stores
+__global__ void __launch_bounds__(256)
+zero_cols_kernel(int32_t* __restrict__ counts, long long n_slots, int col_lo, int col_hi, long long slot_lo,
+                 long long slot_hi) {
+    const long long per_col = (slot_hi - slot_lo) >> 2;
+    const long long total = per_col * (col_hi - col_lo);
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < total;
+         v += (long long)gridDim.x * blockDim.x) {
+        const long long col = col_lo + v / per_col, off = v % per_col;
+        reinterpret_cast<int4*>(counts + col * n_slots + slot_lo)[off] = make_int4(0, 0, 0, 0);
     }
 }
 

@@ -92,6 +92,91 @@ vote_kernel(const int32_t* __restrict__ counts, Peers peers, long long n_slots, 
     *reinterpret_cast<uint32_t*>(calls + s) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
 }
 
+// ---- K2x: the exchange fused end to end (flags + reduce + vote + scatter of the call bytes) -------
+struct Exchange {
+    Peers peers;
+    uint8_t* calls[16];
+    int32_t* ready_local;   // ready[rank]: written by the peers
+    int32_t* done[16];      // done[p] for every p (peer memory)
+    int32_t* done_local;    // done[rank]
+    int32_t* ready[16];
+    int32_t* counter;
+    int rank;
+};
+
+__device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__global__ void exchange_signal_kernel(Exchange x, int epoch) {
+    const int p = threadIdx.x;
+    __threadfence_system();
+    if (p < x.peers.n) st_release_sys(x.ready[p] + x.rank, epoch);
+}
+
+__global__ void exchange_wait_kernel(Exchange x, int epoch) {
+    const int p = threadIdx.x;
+    if (p < x.peers.n)
+        while (ld_acquire_sys(x.done_local + p) < epoch) __nanosleep(64);
+}
+
+__global__ void __launch_bounds__(256)
+vote_exchange_kernel(Exchange x, long long n_slots, long long slot_lo, long long slot_hi,
+                     long long min_depth_ceil, int epoch) {
+    // every table this CTA may read must be complete: ready[rank][p] >= epoch for all p
+    if (threadIdx.x < x.peers.n)
+        while (ld_acquire_sys(x.ready_local + threadIdx.x) < epoch) __nanosleep(32);
+    __syncthreads();
+    const Peers& peers = x.peers;
+    const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long s = slot_lo + quad * 4;
+    const bool active = s < slot_hi;
+    int4 v[KDL_NVOTE_COL];
+    long long d0 = 0;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < KDL_NVOTE_COL; ++k) v[k] = load4<true>(nullptr, peers, k, n_slots, s);
+        d0 = (long long)v[0].x + v[1].x + v[2].x + v[3].x;
+    }
+    long long dn = __shfl_down_sync(0xffffffffu, d0, 1);
+    if ((threadIdx.x & 31) == 31 || !active || s + 4 >= slot_hi) {
+        dn = 0;
+        if (active && s + 4 < n_slots) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dn += load1<true>(nullptr, peers, k, n_slots, s + 4);
+        }
+    }
+    if (active) {
+        const long long d1 = (long long)v[0].y + v[1].y + v[2].y + v[3].y;
+        const long long d2 = (long long)v[0].z + v[1].z + v[2].z + v[3].z;
+        const long long d3 = (long long)v[0].w + v[1].w + v[2].w + v[3].w;
+        const unsigned c0 = vote_slot(v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, d1, min_depth_ceil);
+        const unsigned c1 = vote_slot(v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, d2, min_depth_ceil);
+        const unsigned c2 = vote_slot(v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, d3, min_depth_ceil);
+        const unsigned c3 = vote_slot(v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, dn, min_depth_ceil);
+        const uint32_t packed = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
+        for (int p = 0; p < peers.n; ++p) *reinterpret_cast<uint32_t*>(x.calls[p] + s) = packed;
+    }
+    // last CTA out publishes "my slice has landed everywhere"
+    __syncthreads();
+    __shared__ int last;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = (atomicAdd(x.counter, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *x.counter = 0;
+        __threadfence_system();
+        if (threadIdx.x < peers.n) st_release_sys(x.done[threadIdx.x] + x.rank, epoch);
+    }
+}
+
 // Derived columns (kindel/kindel.py:83-96, :450): out[5][n_slots].
 __global__ void __launch_bounds__(256)
 derive_kernel(const int32_t* __restrict__ counts, long long n_slots, int32_t* __restrict__ out) {

@@ -102,7 +102,11 @@ class PeerTables:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        nbytes = _ffi.KDL_NCOL * n_slots * 4
+        # one IPC block per rank: [count table][call bytes][flags: ready[16], done[16], counter]
+        self.table_bytes = _ffi.KDL_NCOL * n_slots * 4
+        self.calls_off = self.table_bytes
+        self.flags_off = self.table_bytes + n_slots
+        nbytes = self.flags_off + 256
         ptr = C.c_void_p()
         with torch.cuda.device(device):
             _ffi.check(self.lib.kdl_table_alloc(nbytes, C.byref(ptr)), "kdl_table_alloc")
@@ -123,6 +127,19 @@ class PeerTables:
                 self.peer_ptrs.append(p.value)
                 self._opened.append(p.value)
         self.counts = _wrap_device_memory(self.ptr, (_ffi.KDL_NCOL, n_slots), device)
+        self.calls = _wrap_device_memory(self.ptr + self.calls_off, (n_slots,), device, "|u1")
+
+    def exchange_struct(self, feet) -> _ffi.KdlExchange:
+        x = _ffi.KdlExchange()
+        x.n_ranks, x.rank = self.world, self.rank
+        for r, base in enumerate(self.peer_ptrs):
+            x.tables[r] = base
+            x.calls[r] = base + self.calls_off
+            x.ready[r] = base + self.flags_off
+            x.done[r] = base + self.flags_off + 64
+            x.foot_lo[r], x.foot_hi[r] = feet[r]
+        x.counter = self.ptr + self.flags_off + 128
+        return x
 
     def close(self):
         import torch
@@ -137,16 +154,16 @@ class PeerTables:
 
 
 class _CudaArray:
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<i4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def _wrap_device_memory(ptr: int, shape, device):
-    """torch view (int32) over memory this library allocated (no copy)."""
+def _wrap_device_memory(ptr: int, shape, device, typestr="<i4"):
+    """torch view over memory this library allocated (no copy)."""
     import torch
 
     with torch.cuda.device(device):
-        return torch.as_tensor(_CudaArray(ptr, tuple(shape)), device=device)
+        return torch.as_tensor(_CudaArray(ptr, tuple(shape), typestr), device=device)
 
 
 class ShardedConsensus:
@@ -165,11 +182,14 @@ class ShardedConsensus:
         self.n_slots = shard.n_slots
         self.dbatch = engine.upload(shard, device)
         self.lib = _ffi.load()
-        if mode == "peer":
+        self.epoch = 0
+        if mode in ("peer", "fused"):
             self.tables = PeerTables(self.n_slots, device, group)
             self.counts = self.tables.counts
             feet = [None] * self.world
             dist.all_gather_object(feet, footprint(shard), group=group)
+            self.foot = feet[self.rank]
+            self.xstruct = self.tables.exchange_struct(feet)
             self.foot_lo = (C.c_int64 * self.world)(*[f[0] for f in feet])
             self.foot_hi = (C.c_int64 * self.world)(*[f[1] for f in feet])
             self.ptr_arr = (C.c_void_p * self.world)(*self.tables.peer_ptrs)
@@ -180,18 +200,38 @@ class ShardedConsensus:
             self.tables = None
             self.counts = torch.zeros((_ffi.KDL_NCOL, self.n_slots), dtype=torch.int32, device=device)
         else:
-            raise ValueError("mode must be 'peer' or 'allreduce'")
+            raise ValueError("mode must be 'fused', 'peer' or 'allreduce'")
+        if mode == "allreduce":
+            self.foot = (0, self.n_slots)
+        self.table = engine.CountTable(self.n_slots, device, tensor=self.counts)
 
     def step(self, min_depth=1, timers=None):
         """zero, K1 on the shard, exchange, vote.  Returns the complete call bytes on every rank.
         `timers`: optional pair of CUDA events recorded around K1 (bench.py's roofline leg)."""
         torch, dist, engine = self.torch, self.dist, self.engine
-        self.counts.zero_()
         if timers:
             timers[0].record()
-        engine.pileup(self.dbatch, self.counts, check=False)
+        if self.mode == "allreduce":
+            # the all_reduce writes sums everywhere: the whole table is dirty every step
+            self.table.dirty = (0, self.n_slots)
+            self.table.dirty_rest = True  # columns 5, 6 hold sums over ALL ranks after the all_reduce
+            engine.pileup(self.dbatch, check=False, table=self.table)
+        else:  # only this shard's footprint is ever touched (kdl_table_alloc zero-filled the rest)
+            engine.pileup(self.dbatch, check=False, table=self.table, slot_range=self.foot)
         if timers:
             timers[1].record()
+        if self.mode == "fused":
+            # no NCCL on the data path: flags, reduction, vote and the scatter of the call bytes are
+            # three launches of this library over NVLink peer memory
+            self.epoch += 1
+            lo, hi = self.slices[self.rank]
+            st = int(torch.cuda.current_stream(self.device).cuda_stream)
+            with torch.cuda.device(self.device):
+                _ffi.check(self.lib.kdl_exchange_signal(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_signal")
+                _ffi.check(self.lib.kdl_exchange_vote(C.byref(self.xstruct), self.n_slots, lo, hi,
+                                                      int(math.ceil(min_depth)), self.epoch, st), "kdl_exchange_vote")
+                _ffi.check(self.lib.kdl_exchange_wait(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_wait")
+            return self.tables.calls
         if self.mode == "allreduce":
             dist.all_reduce(self.counts[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM, group=self.group)
             return engine.vote(self.counts, min_depth)

@@ -111,22 +111,60 @@ def raise_like_reference(status: int, read: int, nibble: int, op_index: int):
                      % (read, op_index))
 
 
-def pileup(dbatch: DeviceBatch, counts: torch.Tensor = None, check: bool = True):
+class CountTable:
+    """A count table [19, n_slots] that is REUSED across pileups without being memset.
+
+    It remembers which slot range earlier pileups may have dirtied and whether the non-weight
+    columns (5..18: indels, clips -- only complex reads write them) are dirty, and asks the kernels
+    to overwrite / zero exactly that (KDL_PILEUP_FRESH_WEIGHTS / KDL_PILEUP_ZERO_REST) instead of
+    clearing 76 bytes per slot every time."""
+
+    def __init__(self, n_slots: int, device, tensor: torch.Tensor = None):
+        self.n_slots = n_slots
+        self.device = device
+        self.t = tensor if tensor is not None else torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32,
+                                                                device=device)
+        self.dirty = None        # (lo, hi) slot range holding counts of an earlier pileup
+        self.dirty_rest = False  # columns 5..18 non-zero somewhere inside `dirty`
+
+
+def _tile_align(lo: int, hi: int, n_slots: int):
+    t = _ffi.KDL_TILE
+    return max(0, lo // t * t), min(n_slots, (hi + t - 1) // t * t)
+
+
+def pileup(dbatch: DeviceBatch, counts: torch.Tensor = None, check: bool = True, table: CountTable = None,
+           slot_range=None):
     """K1.  Returns (counts int32[19, n_slots], events int32[n_events, 4]) on the device.
 
-    `counts` may be passed to accumulate several batches / shards into one table.
+    counts=<tensor>  accumulate into a table the caller zeroed (several batches / shards may add up).
+    table=<CountTable>  fresh result in a reused table: nothing is memset, the kernels overwrite the
+                     weight columns and zero the others only if an earlier pileup dirtied them.
+                     slot_range = (lo, hi) bounds what the batch can touch (default: everything).
     With check=True the error flag is read back (one 16-byte D2H) and, if set, the exact first
     offending read is located on the device and the reference's exception is raised."""
     lib = _ffi.load()
     dev = dbatch.device
     n_slots = dbatch.n_slots
     with torch.cuda.device(dev):
-        if counts is None:
-            counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
         events = torch.empty((max(dbatch.host.n_events, 1), 4), dtype=torch.int32, device=dev)
         flag = torch.zeros(4, dtype=torch.int32, device=dev)
-        rc = lib.kdl_pileup(C.byref(dbatch.struct), counts.data_ptr(), n_slots, events.data_ptr(),
-                            flag.data_ptr(), _stream_ptr(dev))
+        if table is not None:
+            counts = table.t
+            lo, hi = slot_range if slot_range is not None else (0, n_slots)
+            if table.dirty is not None:
+                lo, hi = min(lo, table.dirty[0]), max(hi, table.dirty[1])
+            lo, hi = _tile_align(lo, hi, n_slots)
+            flags = _ffi.KDL_PILEUP_FRESH_WEIGHTS | (_ffi.KDL_PILEUP_ZERO_REST if table.dirty_rest else 0)
+            rc = lib.kdl_pileup_range(C.byref(dbatch.struct), counts.data_ptr(), n_slots, lo, hi, flags,
+                                      events.data_ptr(), flag.data_ptr(), _stream_ptr(dev))
+            table.dirty = (lo, hi)
+            table.dirty_rest = len(dbatch.host.complex_idx) > 0
+        else:
+            if counts is None:
+                counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
+            rc = lib.kdl_pileup(C.byref(dbatch.struct), counts.data_ptr(), n_slots, events.data_ptr(),
+                                flag.data_ptr(), _stream_ptr(dev))
         _ffi.check(rc, "kdl_pileup")
         if check and int(flag[0].item()) != 0:
             diagnose_and_raise(dbatch)

@@ -1,0 +1,59 @@
+"""Diagnostic (not a test): per-stage CUDA-event breakdown of the fused multi-GPU step."""
+import ctypes as C
+import math
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from kindel_b200 import _ffi, distributed as D, engine, synth  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+full = synth.simple_reads(4, [5_000_000], 200)
+shard = D.shard_batch(full, rank, world)
+sc = D.ShardedConsensus(shard, dev, mode="fused")
+lib = _ffi.load()
+names = ["zero", "pileup", "signal", "vote", "wait"]
+acc = {n: 0.0 for n in names}
+wall = 0.0
+for it in range(13):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ev[0].record()
+    sc.counts[:, sc.foot[0]:sc.foot[1]].zero_()
+    ev[1].record()
+    engine.pileup(sc.dbatch, sc.counts, check=False)
+    ev[2].record()
+    sc.epoch += 1
+    lo, hi = sc.slices[sc.rank]
+    st = int(torch.cuda.current_stream(dev).cuda_stream)
+    lib.kdl_exchange_signal(C.byref(sc.xstruct), sc.epoch, st)
+    ev[3].record()
+    lib.kdl_exchange_vote(C.byref(sc.xstruct), sc.n_slots, lo, hi, 1, sc.epoch, st)
+    ev[4].record()
+    lib.kdl_exchange_wait(C.byref(sc.xstruct), sc.epoch, st)
+    ev[5].record()
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    if it >= 3:
+        for k, n in enumerate(names):
+            acc[n] += ev[k].elapsed_time(ev[k + 1])
+        wall += (t2 - t0) * 1e3
+        if it == 12 and rank == 0:
+            print("cpu enqueue ms", (t1 - t0) * 1e3)
+if rank == 0:
+    print({n: round(v / 10, 4) for n, v in acc.items()}, "sum", round(sum(acc.values()) / 10, 4), "wall", round(wall / 10, 4),
+          "foot", sc.foot, "slots", sc.n_slots)
+dist.barrier()
+sc.close()
+dist.destroy_process_group()

@@ -29,7 +29,7 @@ def main():
         oc, _ = coracle.pileup(full)
         want = coracle.vote(oc, 2)
         shard = D.shard_batch(full, rank, world)
-        for mode in ("peer", "allreduce"):
+        for mode in ("fused", "peer", "allreduce"):
             sc = D.ShardedConsensus(shard, dev, mode=mode)
             for _ in range(3):  # repeated steps: the tables are re-zeroed and re-read safely
                 calls = sc.step(2)

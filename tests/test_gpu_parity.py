@@ -250,3 +250,47 @@ def test_multi_gpu_exchange_modes_match_one_gpu():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert "dist parity ok" in res.stdout
+
+
+def test_count_table_reuse_without_memset():
+    """CountTable: a reused table is never memset; kernels overwrite the weights and zero the other
+    columns only when an earlier pileup dirtied them.  Every result must equal a fresh oracle run."""
+    import torch
+
+    from kindel_b200 import distributed as D
+    from kindel_b200 import engine, synth
+    from oracle import coracle
+
+    seq = [synth.complex_reads(41, 30000, 80), synth.simple_reads(42, [30000], 60), synth.simple_reads(43, [30000], 5),
+           synth.complex_reads(44, 30000, 20, edge_tail=False), synth.simple_reads(45, [30000], 700)]
+    table = None
+    for b in seq:
+        db = engine.upload(b)
+        if table is None:
+            table = engine.CountTable(b.n_slots, db.device)
+        assert b.n_slots == table.n_slots
+        counts, events = engine.pileup(db, table=table)
+        torch.cuda.synchronize()
+        oc, oe = coracle.pileup(b)
+        np.testing.assert_array_equal(counts.cpu().numpy(), oc)
+        np.testing.assert_array_equal(events.cpu().numpy(), oe)
+    # range-restricted: a shard only touches (and only cleans) its footprint
+    full = synth.simple_reads(46, [200000], 50)
+    table = engine.CountTable(full.n_slots, torch.device("cuda", torch.cuda.current_device()))
+    want = coracle.pileup(full)[0]
+    for rank in (0, 1, 2, 1):
+        shard = D.shard_batch(full, rank, 3)
+        counts, _ = engine.pileup(engine.upload(shard), table=table, slot_range=D.footprint(shard))
+        np.testing.assert_array_equal(counts.cpu().numpy(), coracle.pileup(shard)[0])
+    assert int(want[0:5].sum()) == full.aligned_bases
+
+
+def test_sparse_and_unaligned_layouts():
+    """Low depth (most tiles empty), tiny contigs sharing a tile, deep pile-ups (multi-flush, sub-chunks)."""
+    from kindel_b200 import synth
+
+    _against_oracle(synth.simple_reads(51, [700_000], 0.4))
+    _against_oracle(synth.simple_reads(52, [151, 200, 333, 152, 1000, 77777], 25, read_len=150))
+    _against_oracle(synth.simple_reads(53, [5000], 9000))
+    _against_oracle(synth.simple_reads(54, [40000], 300, read_len=37))
+    _against_oracle(synth.simple_reads(55, [60000], 50, read_len=1203))

@@ -184,11 +184,14 @@ int kdl_vote_peers_sparse(const int32_t* const* peer_counts, const int64_t* foot
  *   kdl_pileup(...)                       its shard into its own table
  *   kdl_exchange_signal(x, e)             "my table is complete" -> ready[p][rank] = e in every peer p
  *   kdl_exchange_vote(x, ..., e)          K2x: waits for ready[rank][*] >= e, sums the 7 vote columns
- *                                         of its slot slice over the (footprint-clipped) peer tables
- *                                         through NVLink, votes, stores the call bytes into EVERY
- *                                         rank's call buffer, then done[p][rank] = e
- *   kdl_exchange_wait(x, e)               waits for done[rank][*] >= e: all slices have landed here
- *                                         and nobody still reads this rank's table
+ *                                         of its slot slice [slice_lo[rank], slice_hi[rank]) over the
+ *                                         (footprint-clipped) peer tables through NVLink, votes,
+ *                                         stores the call bytes of the slice locally; the last CTA
+ *                                         out publishes done[p][rank] = e to every peer p
+ *   kdl_exchange_wait(x, e)               K2g: per peer p, waits for done[rank][p] >= e and pulls p's
+ *                                         call slice over NVLink into the local call buffer; when it
+ *                                         ends every slice is here and nobody still reads this
+ *                                         rank's table
  * All pointers of rank p (tables[p], calls[p], ready[p], done[p]) are this process's mappings of
  * rank p's block (own block: the local pointer). */
 typedef struct kdl_exchange {
@@ -197,13 +200,14 @@ typedef struct kdl_exchange {
     uint8_t* calls[16];
     int32_t* ready[16]; /* int32[16] per rank */
     int32_t* done[16];  /* int32[16] per rank */
-    int64_t foot_lo[16], foot_hi[16];
+    int64_t foot_lo[16], foot_hi[16];   /* table p is zero outside [foot_lo[p], foot_hi[p]) */
+    int64_t slice_lo[16], slice_hi[16]; /* slots rank p votes on (multiples of 4, a partition) */
     int32_t* counter;   /* local device int32, zero-initialised */
 } kdl_exchange;
 
 int kdl_exchange_signal(const kdl_exchange* x, int32_t epoch, void* stream);
-int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
-                      int64_t min_depth_ceil, int32_t epoch, void* stream);
+int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t min_depth_ceil, int32_t epoch,
+                      void* stream);
 int kdl_exchange_wait(const kdl_exchange* x, int32_t epoch, void* stream);
 
 /* Count tables that peer GPUs (other processes of the same node) can map: plain cudaMalloc

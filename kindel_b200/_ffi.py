@@ -63,6 +63,8 @@ class KdlExchange(C.Structure):
         ("done", C.c_void_p * 16),
         ("foot_lo", C.c_int64 * 16),
         ("foot_hi", C.c_int64 * 16),
+        ("slice_lo", C.c_int64 * 16),
+        ("slice_hi", C.c_int64 * 16),
         ("counter", C.c_void_p),
     ]
 
@@ -93,8 +95,7 @@ _PROTOTYPES = {
     "kdl_vote_peers_sparse": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32,
                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdl_exchange_signal": (C.c_int, [C.POINTER(KdlExchange), C.c_int32, C.c_void_p]),
-    "kdl_exchange_vote": (C.c_int, [C.POINTER(KdlExchange), C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32,
-                                    C.c_void_p]),
+    "kdl_exchange_vote": (C.c_int, [C.POINTER(KdlExchange), C.c_int64, C.c_int64, C.c_int32, C.c_void_p]),
     "kdl_exchange_wait": (C.c_int, [C.POINTER(KdlExchange), C.c_int32, C.c_void_p]),
     "kdl_table_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
     "kdl_table_free": (C.c_int, [C.c_void_p]),

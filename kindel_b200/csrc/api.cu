@@ -191,6 +191,9 @@ static int make_exchange(const kdl_exchange* x, kdl::Exchange* e, int64_t n_slot
         e->calls[p] = x->calls[p];
         e->ready[p] = x->ready[p];
         e->done[p] = x->done[p];
+        e->slice_lo[p] = x->slice_lo[p];
+        e->slice_hi[p] = x->slice_hi[p];
+        if ((x->slice_lo[p] & 3) || (x->slice_hi[p] & 3) || x->slice_hi[p] < x->slice_lo[p]) return KDL_ERR_INVALID_ARG;
     }
     e->ready_local = x->ready[x->rank];
     e->done_local = x->done[x->rank];
@@ -209,23 +212,24 @@ int kdl_exchange_wait(const kdl_exchange* x, int32_t epoch, void* stream) {
     kdl::Exchange e;
     int rc = make_exchange(x, &e, 0);
     if (rc != KDL_OK) return rc;
-    kdl::exchange_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e, epoch);
+    dim3 grid((unsigned)(sm_count() * 2 / x->n_ranks + 1), (unsigned)x->n_ranks);
+    kdl::exchange_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(e, epoch);
     return check_launch();
 }
 
-int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
-                      int64_t min_depth_ceil, int32_t epoch, void* stream) {
-    if (n_slots <= 0 || (n_slots & 3) || slot_lo < 0 || slot_hi > n_slots || (slot_lo & 3) || (slot_hi & 3) ||
-        slot_hi < slot_lo)
-        return KDL_ERR_INVALID_ARG;
+int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t min_depth_ceil, int32_t epoch,
+                      void* stream) {
+    if (n_slots <= 0 || (n_slots & 3)) return KDL_ERR_INVALID_ARG;
     kdl::Exchange e;
     int rc = make_exchange(x, &e, n_slots);
     if (rc != KDL_OK) return rc;
-    const long long quads = (slot_hi - slot_lo) / 4;
+    if (x->slice_hi[x->rank] > n_slots) return KDL_ERR_INVALID_ARG;
+    const long long quads = (x->slice_hi[x->rank] - x->slice_lo[x->rank]) / 4;
     long long grid = (quads + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;  // an empty slice still has to take part in the flag protocol
-    kdl::vote_exchange_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(e, n_slots, slot_lo, slot_hi,
-                                                                              min_depth_ceil, epoch);
+    kdl::vote_exchange_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(e, n_slots, min_depth_ceil, epoch);
     return check_launch();
 }
 

@@ -92,14 +92,15 @@ vote_kernel(const int32_t* __restrict__ counts, Peers peers, long long n_slots, 
     *reinterpret_cast<uint32_t*>(calls + s) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
 }
 
-// ---- K2x: the exchange fused end to end (flags + reduce + vote + scatter of the call bytes) -------
+// ---- K2x / K2g: the exchange without NCCL (flags + reduce + vote, then a pull of the call bytes) --
 struct Exchange {
     Peers peers;
     uint8_t* calls[16];
-    int32_t* ready_local;   // ready[rank]: written by the peers
-    int32_t* done[16];      // done[p] for every p (peer memory)
-    int32_t* done_local;    // done[rank]
-    int32_t* ready[16];
+    long long slice_lo[16], slice_hi[16];
+    int32_t* ready[16];     // ready[p]: flag array living in rank p's block
+    int32_t* done[16];
+    int32_t* ready_local;   // = ready[rank]: written by the peers
+    int32_t* done_local;
     int32_t* counter;
     int rank;
 };
@@ -113,60 +114,90 @@ __device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// "my table is complete": runs after the pileup kernels in stream order
 __global__ void exchange_signal_kernel(Exchange x, int epoch) {
     const int p = threadIdx.x;
     __threadfence_system();
     if (p < x.peers.n) st_release_sys(x.ready[p] + x.rank, epoch);
 }
 
-__global__ void exchange_wait_kernel(Exchange x, int epoch) {
-    const int p = threadIdx.x;
-    if (p < x.peers.n)
-        while (ld_acquire_sys(x.done_local + p) < epoch) __nanosleep(64);
+// K2g: one CTA group per peer pulls that peer's call slice once the peer has published it
+__global__ void __launch_bounds__(256) exchange_gather_kernel(Exchange x, int epoch) {
+    const int p = blockIdx.y;
+    if (p == x.rank) return;
+    if (threadIdx.x == 0)
+        while (ld_acquire_sys(x.done_local + p) < epoch) __nanosleep(32);
+    __syncthreads();
+    const long long lo = x.slice_lo[p], n16 = (x.slice_hi[p] - lo) >> 4;  // slices are multiples of 16 here
+    const uint4* src = reinterpret_cast<const uint4*>(x.calls[p] + lo);
+    uint4* dst = reinterpret_cast<uint4*>(x.calls[x.rank] + lo);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; v + 3 * stride < n16; v += 4 * stride) {  // four NVLink reads in flight per thread
+        const uint4 a0 = src[v], a1 = src[v + stride], a2 = src[v + 2 * stride], a3 = src[v + 3 * stride];
+        dst[v] = a0; dst[v + stride] = a1; dst[v + 2 * stride] = a2; dst[v + 3 * stride] = a3;
+    }
+    for (; v < n16; v += stride) dst[v] = src[v];
+    const long long tail0 = lo + (n16 << 4);
+    if (blockIdx.x == 0)
+        for (long long s = tail0 + threadIdx.x; s < x.slice_hi[p]; s += blockDim.x) x.calls[x.rank][s] = x.calls[p][s];
 }
 
 __global__ void __launch_bounds__(256)
-vote_exchange_kernel(Exchange x, long long n_slots, long long slot_lo, long long slot_hi,
-                     long long min_depth_ceil, int epoch) {
+vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, int epoch) {
     // every table this CTA may read must be complete: ready[rank][p] >= epoch for all p
     if (threadIdx.x < x.peers.n)
         while (ld_acquire_sys(x.ready_local + threadIdx.x) < epoch) __nanosleep(32);
     __syncthreads();
     const Peers& peers = x.peers;
-    const long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long s = slot_lo + quad * 4;
-    const bool active = s < slot_hi;
-    int4 v[KDL_NVOTE_COL];
-    long long d0 = 0;
-    if (active) {
+    const long long slot_lo = x.slice_lo[x.rank], slot_hi = x.slice_hi[x.rank];
+    uint8_t* __restrict__ calls = x.calls[x.rank];
+    for (long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x; quad * 4 < ((slot_hi - slot_lo + 127) & ~127ll);
+         quad += (long long)gridDim.x * blockDim.x) {  // whole warps iterate together (shuffle below)
+        const long long s = slot_lo + quad * 4;
+        const bool active = s < slot_hi;
+        int4 v[KDL_NVOTE_COL];
+        long long d0 = 0;
+        if (active) {
 #pragma unroll
-        for (int k = 0; k < KDL_NVOTE_COL; ++k) v[k] = load4<true>(nullptr, peers, k, n_slots, s);
-        d0 = (long long)v[0].x + v[1].x + v[2].x + v[3].x;
-    }
-    long long dn = __shfl_down_sync(0xffffffffu, d0, 1);
-    if ((threadIdx.x & 31) == 31 || !active || s + 4 >= slot_hi) {
-        dn = 0;
-        if (active && s + 4 < n_slots) {
+            for (int k = 0; k < KDL_NVOTE_COL; ++k) v[k] = make_int4(0, 0, 0, 0);
+            for (int p = 0; p < peers.n; ++p) {
+                if (s + 4 <= peers.lo[p] || s >= peers.hi[p]) continue;  // nothing of table p here
+                int4 t[KDL_NVOTE_COL];  // seven independent 128-bit loads in flight per table
 #pragma unroll
-            for (int k = 0; k < 4; ++k) dn += load1<true>(nullptr, peers, k, n_slots, s + 4);
+                for (int k = 0; k < KDL_NVOTE_COL; ++k)
+                    t[k] = *reinterpret_cast<const int4*>(peers.tab[p] + (long long)k * n_slots + s);
+#pragma unroll
+                for (int k = 0; k < KDL_NVOTE_COL; ++k) {
+                    v[k].x += t[k].x; v[k].y += t[k].y; v[k].z += t[k].z; v[k].w += t[k].w;
+                }
+            }
+            d0 = (long long)v[0].x + v[1].x + v[2].x + v[3].x;
+        }
+        long long dn = __shfl_down_sync(0xffffffffu, d0, 1);
+        if ((threadIdx.x & 31) == 31 || !active || s + 4 >= slot_hi) {
+            dn = 0;
+            if (active && s + 4 < n_slots) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dn += load1<true>(nullptr, peers, k, n_slots, s + 4);
+            }
+        }
+        if (active) {
+            const long long d1 = (long long)v[0].y + v[1].y + v[2].y + v[3].y;
+            const long long d2 = (long long)v[0].z + v[1].z + v[2].z + v[3].z;
+            const long long d3 = (long long)v[0].w + v[1].w + v[2].w + v[3].w;
+            const unsigned c0 = vote_slot(v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, d1, min_depth_ceil);
+            const unsigned c1 = vote_slot(v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, d2, min_depth_ceil);
+            const unsigned c2 = vote_slot(v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, d3, min_depth_ceil);
+            const unsigned c3 = vote_slot(v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, dn, min_depth_ceil);
+            *reinterpret_cast<uint32_t*>(calls + s) = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
         }
     }
-    if (active) {
-        const long long d1 = (long long)v[0].y + v[1].y + v[2].y + v[3].y;
-        const long long d2 = (long long)v[0].z + v[1].z + v[2].z + v[3].z;
-        const long long d3 = (long long)v[0].w + v[1].w + v[2].w + v[3].w;
-        const unsigned c0 = vote_slot(v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, d1, min_depth_ceil);
-        const unsigned c1 = vote_slot(v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, d2, min_depth_ceil);
-        const unsigned c2 = vote_slot(v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, d3, min_depth_ceil);
-        const unsigned c3 = vote_slot(v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, dn, min_depth_ceil);
-        const uint32_t packed = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-        for (int p = 0; p < peers.n; ++p) *reinterpret_cast<uint32_t*>(x.calls[p] + s) = packed;
-    }
-    // last CTA out publishes "my slice has landed everywhere"
+    // last CTA out publishes "my slice is voted (and I no longer read your tables)" to every peer
     __syncthreads();
     __shared__ int last;
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         last = (atomicAdd(x.counter, 1) == (int)gridDim.x - 1);
     }
     __syncthreads();

@@ -129,7 +129,7 @@ class PeerTables:
         self.counts = _wrap_device_memory(self.ptr, (_ffi.KDL_NCOL, n_slots), device)
         self.calls = _wrap_device_memory(self.ptr + self.calls_off, (n_slots,), device, "|u1")
 
-    def exchange_struct(self, feet) -> _ffi.KdlExchange:
+    def exchange_struct(self, feet, slices) -> _ffi.KdlExchange:
         x = _ffi.KdlExchange()
         x.n_ranks, x.rank = self.world, self.rank
         for r, base in enumerate(self.peer_ptrs):
@@ -138,6 +138,7 @@ class PeerTables:
             x.ready[r] = base + self.flags_off
             x.done[r] = base + self.flags_off + 64
             x.foot_lo[r], x.foot_hi[r] = feet[r]
+            x.slice_lo[r], x.slice_hi[r] = slices[r]
         x.counter = self.ptr + self.flags_off + 128
         return x
 
@@ -189,7 +190,8 @@ class ShardedConsensus:
             feet = [None] * self.world
             dist.all_gather_object(feet, footprint(shard), group=group)
             self.foot = feet[self.rank]
-            self.xstruct = self.tables.exchange_struct(feet)
+            self.slices = owner_slices(self.n_slots, self.world)
+            self.xstruct = self.tables.exchange_struct(feet, self.slices)
             self.foot_lo = (C.c_int64 * self.world)(*[f[0] for f in feet])
             self.foot_hi = (C.c_int64 * self.world)(*[f[1] for f in feet])
             self.ptr_arr = (C.c_void_p * self.world)(*self.tables.peer_ptrs)
@@ -228,8 +230,8 @@ class ShardedConsensus:
             st = int(torch.cuda.current_stream(self.device).cuda_stream)
             with torch.cuda.device(self.device):
                 _ffi.check(self.lib.kdl_exchange_signal(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_signal")
-                _ffi.check(self.lib.kdl_exchange_vote(C.byref(self.xstruct), self.n_slots, lo, hi,
-                                                      int(math.ceil(min_depth)), self.epoch, st), "kdl_exchange_vote")
+                _ffi.check(self.lib.kdl_exchange_vote(C.byref(self.xstruct), self.n_slots, int(math.ceil(min_depth)),
+                                                      self.epoch, st), "kdl_exchange_vote")
                 _ffi.check(self.lib.kdl_exchange_wait(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_wait")
             return self.tables.calls
         if self.mode == "allreduce":

@@ -29,16 +29,15 @@ for it in range(13):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     ev[0].record()
-    sc.counts[:, sc.foot[0]:sc.foot[1]].zero_()
     ev[1].record()
-    engine.pileup(sc.dbatch, sc.counts, check=False)
+    engine.pileup(sc.dbatch, check=False, table=sc.table, slot_range=sc.foot)
     ev[2].record()
     sc.epoch += 1
     lo, hi = sc.slices[sc.rank]
     st = int(torch.cuda.current_stream(dev).cuda_stream)
     lib.kdl_exchange_signal(C.byref(sc.xstruct), sc.epoch, st)
     ev[3].record()
-    lib.kdl_exchange_vote(C.byref(sc.xstruct), sc.n_slots, lo, hi, 1, sc.epoch, st)
+    lib.kdl_exchange_vote(C.byref(sc.xstruct), sc.n_slots, 1, sc.epoch, st)
     ev[4].record()
     lib.kdl_exchange_wait(C.byref(sc.xstruct), sc.epoch, st)
     ev[5].record()
@@ -51,9 +50,11 @@ for it in range(13):
         wall += (t2 - t0) * 1e3
         if it == 12 and rank == 0:
             print("cpu enqueue ms", (t1 - t0) * 1e3)
-if rank == 0:
-    print({n: round(v / 10, 4) for n, v in acc.items()}, "sum", round(sum(acc.values()) / 10, 4), "wall", round(wall / 10, 4),
-          "foot", sc.foot, "slots", sc.n_slots)
+for r in range(world):
+  dist.barrier()
+  if rank == r:
+    print("rank", rank, {n: round(v / 10, 4) for n, v in acc.items()}, "sum", round(sum(acc.values()) / 10, 4), "wall", round(wall / 10, 4),
+          "foot", sc.foot, "slots", sc.n_slots, flush=True)
 dist.barrier()
 sc.close()
 dist.destroy_process_group()

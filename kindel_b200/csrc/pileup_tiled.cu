@@ -13,8 +13,8 @@
 //     two staged words; out-of-range words read as zero and add nothing.
 //   * Counting is bit-sliced: the 32 bits of that word are 32 independent 1-bit inputs (8 slots x
 //     A,C,G,T) added into vertical counters with a Harley-Seal carry-save tree -- 7 full adders
-//     (14 LOP3) per 8 reads, instead of 8 x 150 read-modify-writes.  N (all four bits set) is
-//     counted in a second set of planes and subtracted from A,C,G,T at the end.
+//     (14 LOP3) per 8 reads, instead of 8 x 150 read-modify-writes.  N (all four bits set) is not
+//     counted at all: it is recovered per slot from A+C+G+T = coverage + 3N (see flush_window).
 //   * The 4 quarter-warps walk 4 different reads at once (a 150-base read covers ~6 of 8 lanes of a
 //     64-slot window, so quarter-warps keep ~80 % of lanes busy where a full warp would keep 40 %);
 //     their planes are summed bit-sliced by two shuffle butterflies, transposed to integers once
@@ -33,7 +33,7 @@ namespace kdl {
 constexpr int F_THREADS = 256;
 constexpr int F_WIN = 64;              // slots per warp window
 constexpr int F_RMAX = 1024;           // reads per staged sub-chunk
-constexpr int F_CAPW = 20480;          // seq words per staged sub-chunk (80 KB)
+constexpr int F_CAPW = 18432;          // seq words per staged sub-chunk (72 KB)
 constexpr int F_P = 8;                 // bit planes per stream: up to 255 reads between flushes
 constexpr int F_FLUSH_BLOCKS = 31;     // 31 blocks x 8 reads = 248 <= 255
 
@@ -188,32 +188,58 @@ __device__ __forceinline__ void extract8(const uint32_t (&pl)[F_P + 2], int bit,
 // Add the window's counters to the table.  Quarter q owns column q (A,C,G,T); quarter 0 also adds
 // column 4 (N).  Each lane holds 8 consecutive slots -> two 128-bit read-modify-writes per column;
 // no other thread of the grid touches these slots during this kernel.
-template <bool kStore>
-__device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t* __restrict__ counts,
-                                             long long n_slots, long long slot0, int lane) {
+// ---- flush: planes -> integers -> table ----------------------------------------------------------
+// N is not counted: an N nibble (15) adds 1 to all four of A,C,G,T, so for every slot
+//     A_raw + C_raw + G_raw + T_raw = cov + 3 N        (cov = simple reads covering the slot)
+// and cov comes from a +1/-1 difference array over read starts/ends (two shared-memory atomics per
+// staged read, one prefix sum per window).  The correction is applied by the FINAL flush of a window
+// (kFinal); earlier flushes -- only needed when more than 248 reads per stream pile up on one
+// window -- add raw counts and remember the raw total in `rawacc`.
+// Quarter q owns column q (A,C,G,T); quarter 0 also writes column 4 (N).  Each lane holds 8
+// consecutive slots: two 128-bit stores (kStore) or read-modify-writes per column; no other thread
+// of the grid touches these slots during this kernel.
+template <bool kStore, bool kFinal>
+__device__ __forceinline__ void flush_window(Planes& acc, int (&rawacc)[8], const int (&covacc)[8],
+                                             int32_t* __restrict__ counts, long long n_slots, long long slot0,
+                                             int lane) {
     const int q = lane >> 3;
     const long long s = slot0 + 8 * (lane & 7);
     int4* dst = reinterpret_cast<int4*>(counts + (long long)q * n_slots + s);
     int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
     if (!kStore) { v0 = dst[0]; v1 = dst[1]; }  // issued first: latency hides behind the transposition
-    uint32_t m[F_P + 2], n[F_P + 2];
+    uint32_t m[F_P + 2];
     quarter_sum(acc.p, m);
-    quarter_sum(accn.p, n);
     acc.clear();
-    accn.clear();
-    int cn[8], cv[8];
-    extract8(n, 0, cn);
+    int cv[8], tot[8];
     extract8(m, q, cv);
-    v0.x += cv[0] - cn[0]; v0.y += cv[1] - cn[1]; v0.z += cv[2] - cn[2]; v0.w += cv[3] - cn[3];
-    v1.x += cv[4] - cn[4]; v1.y += cv[5] - cn[5]; v1.z += cv[6] - cn[6]; v1.w += cv[7] - cn[7];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {  // A+C+G+T raw of each slot: sum of the four quarters' columns
+        int t = cv[k];
+        t += __shfl_xor_sync(0xffffffffu, t, 8);
+        t += __shfl_xor_sync(0xffffffffu, t, 16);
+        tot[k] = t + rawacc[k];
+    }
+    int nn[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (kFinal) {
+            nn[k] = (tot[k] - covacc[k]) / 3;  // exact by construction
+            rawacc[k] = 0;
+        } else {
+            nn[k] = 0;
+            rawacc[k] = tot[k];
+        }
+    }
+    v0.x += cv[0] - nn[0]; v0.y += cv[1] - nn[1]; v0.z += cv[2] - nn[2]; v0.w += cv[3] - nn[3];
+    v1.x += cv[4] - nn[4]; v1.y += cv[5] - nn[5]; v1.z += cv[6] - nn[6]; v1.w += cv[7] - nn[7];
     dst[0] = v0;
     dst[1] = v1;
-    if (q == 0) {
+    if (q == 0 && (kFinal || kStore)) {
         int4* dn = reinterpret_cast<int4*>(counts + (long long)KDL_W_N * n_slots + s);
         int4 n0 = make_int4(0, 0, 0, 0), n1 = n0;
         if (!kStore) { n0 = dn[0]; n1 = dn[1]; }
-        n0.x += cn[0]; n0.y += cn[1]; n0.z += cn[2]; n0.w += cn[3];
-        n1.x += cn[4]; n1.y += cn[5]; n1.z += cn[6]; n1.w += cn[7];
+        n0.x += nn[0]; n0.y += nn[1]; n0.z += nn[2]; n0.w += nn[3];
+        n1.x += nn[4]; n1.y += nn[5]; n1.z += nn[6]; n1.w += nn[7];
         dn[0] = n0;
         dn[1] = n1;
     }
@@ -221,11 +247,17 @@ __device__ __forceinline__ void flush_window(Planes& acc, Planes& accn, int32_t*
 
 struct FastSmem {
     uint32_t seq[F_CAPW];
-    int2 meta[F_RMAX + 32];  // .x = start slot of the read relative to the tile's first slot (all
-                             //      reads, so the array stays sorted); .y = byte offset of its bases
-                             //      in seq[] (17 bits) | byte length of its bases << 17 (0 = not a
-                             //      simple read: adds nothing).  32 sentinels follow the last read.
-    uint64_t bar;       // mbarrier the bulk copy of seq[] completes on
+    // per staged read (32 sentinels follow the last one):
+    //   .x  byte offset, relative to the tile, of the first 8-slot group the read can serve:
+    //       4 * ceil(start / 8)            (lane byte offset - this = word of the read, in bytes)
+    //   .y  shared-memory address (u32) of the read's first word
+    //   .z  bytes of packed bases (0 = not a simple read: adds nothing)
+    //   .w  funnel-shift amount 4 * ((-start) & 7)
+    int4 meta[F_RMAX + 32];
+    int gs[F_RMAX + 32];          // start slot relative to the tile (all reads: the array stays sorted)
+    int diff[2][KDL_TILE + 32];   // +1 at read start, -1 at read end (double-buffered per sub-chunk)
+    int cov[KDL_TILE];            // prefix sums of diff: simple reads covering each slot
+    uint64_t bar;                 // mbarrier the bulk copy of seq[] completes on
 };
 
 // kFresh: columns 0..4 hold stale data; the first flush of every window stores instead of adding,
@@ -239,8 +271,11 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = lane >> 3;
     const int maxlen = b.max_simple_len;
+    const uint32_t seq_base = smem_u32(sm.seq);
     uint32_t bar_parity = 0;
+    int dbuf = 0;
     if (tid == 0) mbar_init(&sm.bar, 1);
+    for (int k = tid; k < 2 * (KDL_TILE + 32); k += F_THREADS) (&sm.diff[0][0])[k] = 0;
     __syncthreads();
 
     for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
@@ -260,10 +295,12 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
         const bool one_contig = ic.x == ic.y;
         const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
         const int wlo = warp * F_WIN;
-        const int p0 = wlo + 8 * (lane & 7);  // lane's first slot, tile-relative
-        Planes acc, accn;
+        const int p8b = (wlo >> 1) + 4 * (lane & 7);  // 4 * (lane's first slot / 8): byte offset of its word
+        Planes acc;
         acc.clear();
-        accn.clear();
+        int rawacc[8], covacc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { rawacc[k] = 0; covacc[k] = 0; }
         int blocks_since_flush = 0;
         bool stored = false;  // kFresh: has this window been written yet?
 
@@ -300,6 +337,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                     sm.seq[w] = w < avail ? b.seq4[wa + w] : 0u;
                 }
             }
+            int* diff = sm.diff[dbuf];
             {   // metadata: all loads of this thread's (up to 4) reads first, then the stores
                 int l[F_RMAX / F_THREADS], rs[F_RMAX / F_THREADS];
                 uint32_t so[F_RMAX / F_THREADS];
@@ -322,18 +360,57 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                             const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
                             g = b.contig_slot[c] + rs[k] - tile_slot;
                         }
-                        g = g < -0x20000000ll ? -0x20000000ll : (g > 0x20000000ll ? 0x20000000ll : g);
-                        uint32_t ww = 0;
-                        if (l[k] > 0)  // simple read (bit 31 clear)
-                            ww = (uint32_t)(((long long)so[k] - wa) << 2) | ((uint32_t)((l[k] + 7) >> 3) << 19);
-                        sm.meta[i] = make_int2((int)g, (int)ww);
+                        g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
+                        const int gs = (int)g;
+                        int nb = 0;
+                        if (l[k] > 0) {  // simple read (bit 31 clear)
+                            nb = ((l[k] + 7) >> 3) << 2;
+                            const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
+                            if (cs < ce) {
+                                atomicAdd(diff + cs, 1);
+                                atomicAdd(diff + ce, -1);
+                            }
+                        }
+                        sm.gs[i] = gs;
+                        sm.meta[i] = make_int4(((gs + 7) >> 3) << 2,
+                                               (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
+                                               ((-gs) & 7) << 2);
                     }
                 }
-                if (tid < 32) sm.meta[n_sub + tid] = make_int2(0x20000000, 0);  // sentinels: never overlap
+                if (tid < 32) {  // sentinels: never overlap anything
+                    sm.gs[n_sub + tid] = 0x10000000;
+                    sm.meta[n_sub + tid] = make_int4(0x10000000, (int)seq_base, 0, 0);
+                }
+                int* other = sm.diff[dbuf ^ 1];  // clean the buffer the NEXT sub-chunk will use
+                for (int k = tid; k < KDL_TILE + 32; k += F_THREADS) other[k] = 0;
             }
-            __syncthreads();                 // metadata visible
+            __syncthreads();                 // metadata + difference array complete
             mbar_wait(&sm.bar, bar_parity);  // bases landed
             bar_parity ^= 1u;
+            dbuf ^= 1;
+
+            // ---- coverage of this warp's 64 slots: prefix sum of the difference array ------------
+            {
+                int pre = 0;
+                for (int k = lane; k < wlo; k += 32) pre += diff[k];
+#pragma unroll
+                for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
+                const int d0 = diff[wlo + 2 * lane], d1 = diff[wlo + 2 * lane + 1];
+                int run = d0 + d1;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, run, d);
+                    if (lane >= d) run += o;
+                }
+                const int before = pre + run - d0 - d1;
+                sm.cov[wlo + 2 * lane] = before + d0;
+                sm.cov[wlo + 2 * lane + 1] = before + d0 + d1;
+                __syncwarp();
+                const int4 ca = *reinterpret_cast<const int4*>(sm.cov + wlo + 8 * (lane & 7));
+                const int4 cb = *reinterpret_cast<const int4*>(sm.cov + wlo + 8 * (lane & 7) + 4);
+                covacc[0] += ca.x; covacc[1] += ca.y; covacc[2] += ca.z; covacc[3] += ca.w;
+                covacc[4] += cb.x; covacc[5] += cb.y; covacc[6] += cb.z; covacc[7] += cb.w;
+            }
 
             // ---- this warp's window against the sub-chunk: reads with start in (wlo - maxlen, wlo + 64)
             int a, e;
@@ -341,34 +418,30 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                 int l0 = 0, h0 = n_sub;
                 while (l0 < h0) {
                     const int mid = (l0 + h0) >> 1;
-                    if (sm.meta[mid].x + maxlen > wlo) h0 = mid; else l0 = mid + 1;
+                    if (sm.gs[mid] + maxlen > wlo) h0 = mid; else l0 = mid + 1;
                 }
                 a = l0;
                 int l1 = a, h1 = n_sub;
                 while (l1 < h1) {
                     const int mid = (l1 + h1) >> 1;
-                    if (sm.meta[mid].x >= wlo + F_WIN) h1 = mid; else l1 = mid + 1;
+                    if (sm.gs[mid] >= wlo + F_WIN) h1 = mid; else l1 = mid + 1;
                 }
                 e = l1;
             }
 
-            const uint32_t seq_base = smem_u32(sm.seq);
             for (int base = a; base < e; base += 32) {
                 // 8 reads per lane and block.  No bounds logic: a read that does not reach the lane's
                 // 8 slots (including the sentinels behind the last read, and reads [e, ...) that start
                 // right of the window) fails both range tests below and contributes zero.
-                uint32_t x[8], xn[8];
-                int2 mt[8];
-                const int2* mp = sm.meta + base + quarter;
+                uint32_t x[8];
+                int4 mt[8];
+                const int4* mp = sm.meta + base + quarter;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) mt[u] = mp[4 * u];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t ww = (uint32_t)mt[u].y;
-                    const int o = p0 - mt[u].x;             // first base of the read this lane needs
-                    const uint32_t jb = (uint32_t)((o >> 1) & ~3);  // byte offset of word o / 8
-                    const uint32_t nb = ww >> 17;           // bytes of packed bases
-                    const uint32_t addr = seq_base + (ww & 0x1FFFFu) + jb;
+                    const uint32_t jb = (uint32_t)(p8b - mt[u].x);  // byte offset of the read's word
+                    const uint32_t addr = (uint32_t)mt[u].y + jb;
                     uint32_t hw, lw;
                     asm("{\n"
                         ".reg .pred p, q;\n"
@@ -380,24 +453,23 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                         "@q ld.shared.u32 %1, [%5+4];\n"
                         "}\n"
                         : "=&r"(hw), "=&r"(lw)
-                        : "r"(jb), "r"(nb), "r"(jb + 4u), "r"(addr));
-                    const uint32_t w = __funnelshift_l(lw, hw, o << 2);
-                    x[u] = w;
-                    xn[u] = w & (w >> 1) & 0x11111111u;  // nibble 15 (N): bits 0 and 1 both set
+                        : "r"(jb), "r"((uint32_t)mt[u].z), "r"(jb + 4u), "r"(addr));
+                    x[u] = __funnelshift_l(lw, hw, (uint32_t)mt[u].w);
                 }
                 acc.add8(x);
-                accn.add8(xn);
                 if (++blocks_since_flush == F_FLUSH_BLOCKS) {
-                    if (kFresh && !stored) flush_window<true>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
-                    else flush_window<false>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+                    if (kFresh && !stored)
+                        flush_window<true, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+                    else
+                        flush_window<false, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
                     stored = true;
                     blocks_since_flush = 0;
                 }
             }
             c0 = c1;
         }
-        if (kFresh && !stored) flush_window<true>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
-        else if (blocks_since_flush) flush_window<false>(acc, accn, counts, n_slots, tile_slot + wlo, lane);
+        if (kFresh && !stored) flush_window<true, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+        else flush_window<false, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
     }
 }
 

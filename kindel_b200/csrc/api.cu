@@ -96,7 +96,7 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
     if (tiled) {
         // K0: read range per tile (the linear index of a sorted BAM, built on the device)
         const long long n_tiles_all = n_slots / KDL_TILE;
-        kdl::tile_index_kernel<<<(unsigned)((n_tiles_all + 255) / 256), 256, 0, st>>>(*batch, n_tiles_all,
+        kdl::tile_index_kernel<<<(unsigned)((n_tiles_all * 32 + 255) / 256), 256, 0, st>>>(*batch, n_tiles_all,
                                                                                    batch->tile_index);
         if ((rc = check_launch()) != KDL_OK) return rc;
         // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)

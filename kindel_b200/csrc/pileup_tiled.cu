@@ -44,8 +44,10 @@ constexpr int F_FLUSH_BLOCKS = 31;     // 31 blocks x 8 reads = 248 <= 255
 // global slot of a read's first base = contig_slot[c] + ref_start; reads are sorted by it.
 constexpr int F_IDX = 8;  // int32 per tile in the index
 
-__device__ __forceinline__ long long first_read_at_or_after(const kdl_batch& b, long long g) {
-    // first read index whose global start slot is >= g
+// first read index whose global start slot is >= g.  Warp-cooperative: the contig is found by every
+// lane (few contigs), the read by a 32-ary search -- each round the 32 lanes probe 32 evenly spaced
+// elements of the remaining range in ONE memory round trip (5 rounds for 10^7 reads, not 24).
+__device__ __forceinline__ long long first_read_at_or_after(const kdl_batch& b, long long g, int lane) {
     if (b.n_contigs == 0) return 0;
     int lo = 0, hi = b.n_contigs;  // first contig with slot + len + 1 > g
     while (lo < hi) {
@@ -55,20 +57,33 @@ __device__ __forceinline__ long long first_read_at_or_after(const kdl_batch& b, 
     if (lo >= b.n_contigs) return b.n_reads;
     const long long p = g - b.contig_slot[lo];  // position inside contig `lo` (may be < 0)
     long long a = b.contig_read_off[lo], e = b.contig_read_off[lo + 1];
-    while (a < e) {
-        const long long mid = (a + e) >> 1;
-        if ((long long)b.ref_start[mid] >= p) e = mid; else a = mid + 1;
+    while (a < e) {  // invariant: every read before a is < p, every read from e on is >= p
+        const long long n = e - a;
+        const long long step = (n + 31) >> 5;
+        const long long idx = a + (long long)(lane + 1) * step - 1;  // last element of the lane's bucket
+        const bool ge = idx < e ? ((long long)b.ref_start[idx] >= p) : true;
+        const unsigned m = __ballot_sync(0xffffffffu, ge);
+        if (m == 0u) { a = e; break; }  // 32 full buckets and even the very last element is < p
+        const int k = __ffs(m) - 1;     // first bucket whose last element is >= p
+        const long long na = a + (long long)k * step;
+        long long ne = a + (long long)(k + 1) * step - 1;  // that last element is >= p: answer <= ne
+        if (ne > e) ne = e;
+        a = na;
+        e = ne < a ? a : ne;
+        if (step == 1) { a = e; }  // buckets were single elements: e is the answer
     }
     return a;
 }
 
 __global__ void __launch_bounds__(256)
 tile_index_kernel(kdl_batch b, long long n_tiles, uint32_t* __restrict__ index) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tile
     if (t >= n_tiles) return;
     const long long g0 = t * KDL_TILE;
-    const long long lo = first_read_at_or_after(b, g0 - b.max_simple_len + 1);
-    const long long hi = first_read_at_or_after(b, g0 + KDL_TILE);
+    const long long lo = first_read_at_or_after(b, g0 - b.max_simple_len + 1, lane);
+    const long long hi = first_read_at_or_after(b, g0 + KDL_TILE, lane);
+    if (lane) return;
     uint32_t* e = index + F_IDX * t;
     e[0] = (uint32_t)lo;
     e[1] = (uint32_t)hi;
@@ -96,6 +111,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// 4-byte asynchronous global -> shared copy (LDGSTS): no register staging, completes in background
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
@@ -109,6 +130,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
     }
+}
+
+// first index i in [0, n) with g[i] >= key (n if none); g sorted, n <= 1024, whole warp calls
+__device__ __forceinline__ int lower_bound_warp(const int* g, int n, int key, int lane) {
+    const int step = (n + 31) >> 5;  // <= 32
+    if (step == 0) return 0;
+    const int i1 = (lane + 1) * step - 1;
+    const unsigned m1 = __ballot_sync(0xffffffffu, i1 < n ? g[i1] >= key : true);
+    if (m1 == 0u) return n;       // every probed element (incl. the last one) is < key
+    const int k = __ffs(m1) - 1;  // first bucket whose last element is >= key
+    const int i2 = k * step + lane;
+    const unsigned m2 = __ballot_sync(0xffffffffu, (lane < step && i2 < n) ? g[i2] >= key : true);
+    const int r = k * step + __ffs(m2) - 1;
+    return r < n ? r : n;
 }
 
 // ---- bit-sliced counters ------------------------------------------------------------------------
@@ -257,6 +292,7 @@ struct FastSmem {
     int gs[F_RMAX + 32];          // start slot relative to the tile (all reads: the array stays sorted)
     int diff[2][KDL_TILE + 32];   // +1 at read start, -1 at read end (double-buffered per sub-chunk)
     int cov[KDL_TILE];            // prefix sums of diff: simple reads covering each slot
+    int raw[3][F_RMAX];           // l_seq / ref_start / seq_off of the NEXT tile's first reads (cp.async)
     uint64_t bar;                 // mbarrier the bulk copy of seq[] completes on
 };
 
@@ -278,11 +314,28 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
     for (int k = tid; k < 2 * (KDL_TILE + 32); k += F_THREADS) (&sm.diff[0][0])[k] = 0;
     __syncthreads();
 
+    // Software pipeline across this CTA's tiles: while tile t is being counted, the per-read
+    // metadata of tile t + gridDim.x's first sub-chunk streams into sm.raw (cp.async, each thread
+    // fetches exactly the elements it will later consume, so no barrier is needed for them).
+    auto prefetch_raw = [&](long long t) {
+        if (t >= tile_lo + n_tiles) return;
+        const uint2 nx = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * t));
+        const long long plo = nx.x, phi = nx.y;
+        const int cnt = (int)(phi - plo < F_RMAX ? phi - plo : F_RMAX);
+        for (int i = tid; i < cnt; i += F_THREADS) {
+            cp_async4(&sm.raw[0][i], b.l_seq + plo + i);
+            cp_async4(&sm.raw[1][i], b.ref_start + plo + i);
+            cp_async4(&sm.raw[2][i], b.seq_off + plo + i);
+        }
+    };
+    prefetch_raw(tile_lo + blockIdx.x);
+
     for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
         const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
         const uint2 ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
         const long long lo = ix.x, hi = ix.y;
         const long long tile_slot = tile * KDL_TILE;
+        bool raw_pending = true;  // sm.raw holds this tile's first reads; the next prefetch is still to issue
         if (lo >= hi) {  // uniform for the CTA: no read reaches this tile
             if (kFresh) {  // 5 columns x 512 slots of zeros, 128-bit stores
                 for (int v = tid; v < 5 * (KDL_TILE / 4); v += F_THREADS) {
@@ -290,6 +343,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                     reinterpret_cast<int4*>(counts + (long long)col * n_slots + tile_slot)[off] = make_int4(0, 0, 0, 0);
                 }
             }
+            prefetch_raw(tile + gridDim.x);  // nothing was prefetched for an empty tile: raw is free
             continue;
         }
         const bool one_contig = ic.x == ic.y;
@@ -341,13 +395,25 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
             {   // metadata: all loads of this thread's (up to 4) reads first, then the stores
                 int l[F_RMAX / F_THREADS], rs[F_RMAX / F_THREADS];
                 uint32_t so[F_RMAX / F_THREADS];
+                if (c0 == lo) {  // first sub-chunk: already in shared memory (prefetched during the last tile)
+                    cp_async_wait_all();
 #pragma unroll
-                for (int k = 0; k < F_RMAX / F_THREADS; ++k) {
-                    const int i = tid + k * F_THREADS;
-                    const long long r = c0 + (i < n_sub ? i : 0);
-                    l[k] = b.l_seq[r];
-                    rs[k] = b.ref_start[r];
-                    so[k] = b.seq_off[r];
+                    for (int k = 0; k < F_RMAX / F_THREADS; ++k) {
+                        const int i = tid + k * F_THREADS;
+                        const int ii = i < n_sub ? i : tid;
+                        l[k] = sm.raw[0][ii];
+                        rs[k] = sm.raw[1][ii];
+                        so[k] = (uint32_t)sm.raw[2][ii];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < F_RMAX / F_THREADS; ++k) {
+                        const int i = tid + k * F_THREADS;
+                        const long long r = c0 + (i < n_sub ? i : 0);
+                        l[k] = b.l_seq[r];
+                        rs[k] = b.ref_start[r];
+                        so[k] = b.seq_off[r];
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < F_RMAX / F_THREADS; ++k) {
@@ -381,6 +447,10 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                     sm.gs[n_sub + tid] = 0x10000000;
                     sm.meta[n_sub + tid] = make_int4(0x10000000, (int)seq_base, 0, 0);
                 }
+                if (raw_pending) {  // this thread's raw elements are consumed: refill them for the next tile
+                    prefetch_raw(tile + gridDim.x);
+                    raw_pending = false;
+                }
                 int* other = sm.diff[dbuf ^ 1];  // clean the buffer the NEXT sub-chunk will use
                 for (int k = tid; k < KDL_TILE + 32; k += F_THREADS) other[k] = 0;
             }
@@ -413,21 +483,9 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
             }
 
             // ---- this warp's window against the sub-chunk: reads with start in (wlo - maxlen, wlo + 64)
-            int a, e;
-            {
-                int l0 = 0, h0 = n_sub;
-                while (l0 < h0) {
-                    const int mid = (l0 + h0) >> 1;
-                    if (sm.gs[mid] + maxlen > wlo) h0 = mid; else l0 = mid + 1;
-                }
-                a = l0;
-                int l1 = a, h1 = n_sub;
-                while (l1 < h1) {
-                    const int mid = (l1 + h1) >> 1;
-                    if (sm.gs[mid] >= wlo + F_WIN) h1 = mid; else l1 = mid + 1;
-                }
-                e = l1;
-            }
+            // two lower bounds over the sorted starts, each in two 32-wide probe rounds (n_sub <= 1024)
+            const int a = lower_bound_warp(sm.gs, n_sub, wlo - maxlen + 1, lane);
+            const int e = lower_bound_warp(sm.gs, n_sub, wlo + F_WIN, lane);
 
             for (int base = a; base < e; base += 32) {
                 // 8 reads per lane and block.  No bounds logic: a read that does not reach the lane's

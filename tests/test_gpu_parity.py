@@ -294,3 +294,16 @@ def test_sparse_and_unaligned_layouts():
     _against_oracle(synth.simple_reads(53, [5000], 9000))
     _against_oracle(synth.simple_reads(54, [40000], 300, read_len=37))
     _against_oracle(synth.simple_reads(55, [60000], 50, read_len=1203))
+
+
+def test_tile_index_power_of_32_read_counts():
+    """K0's 32-ary search with read counts that fill all 32 buckets exactly (regression: the last
+    element of the last bucket being smaller than the key must yield 'end', not bucket -1)."""
+    from kindel_b200 import synth
+
+    for L, depth in ((15360, 10), (4800, 32), (153600, 32)):  # 1024, 1024, 32768 reads of 150 bp
+        b = synth.simple_reads(61, [L], depth)
+        assert b.n_reads in (1024, 32768)
+        _against_oracle(b)
+    b = synth.simple_reads(62, [2000, 90000], 8)  # reads only at the very start of a long slot space
+    _against_oracle(b)

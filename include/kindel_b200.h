@@ -30,8 +30,9 @@
  *                            ref_start + len <= L), every base one of A,C,G,T,N (nibbles
  *                            1,2,4,8,15).  The flatten step classifies (kindel_b200/bamio.py);
  *                            the fast pileup kernel relies on it and never looks at the CIGAR
- *     cig_off[n+1]   uint32  prefix offsets into `cigar`
- *     cigar[n_ops]   uint32  BAM encoding  len << 4 | op,  op index into "MIDNSHP=X"
+ *     cig_off[n_complex+1] uint32  prefix offsets into `cigar`, one entry per COMPLEX read (list order)
+ *     cigar[n_ops]   uint32  BAM encoding  len << 4 | op,  op index into "MIDNSHP=X", of the complex
+ *                            reads only: a simple read's CIGAR is implied by l_seq and never travels
  *     seq4[n_words]  uint32  BAM nibble codes "=ACMGRSVTWYHKDBN", 8 bases per 32-bit word, FIRST
  *                            base in the MOST significant nibble (base k of a read sits at bits
  *                            [28-4*(k%8), 32-4*(k%8)) of its word k/8); every read starts on a
@@ -87,7 +88,7 @@ typedef enum kdl_status {
  * pointers for the kdl_ctx_* entry points. */
 typedef struct kdl_batch {
     int64_t n_reads;
-    int64_t n_ops;       /* entries in cigar */
+    int64_t n_ops;       /* entries in cigar (complex reads only) */
     int64_t seq4_words;  /* 32-bit words in seq4 */
     const int32_t* ref_start;
     const uint32_t* seq_off;
@@ -106,6 +107,8 @@ typedef struct kdl_batch {
     int64_t n_complex;
     const uint32_t* complex_idx; /* [n_complex] */
     const uint32_t* evt_off;     /* [n_complex+1] running count of I ops before each listed read */
+    /* cig_off above is indexed like complex_idx / evt_off: cigar[cig_off[j] .. cig_off[j+1]) is the
+     * CIGAR of read complex_idx[j] */
     /* scratch for the tile index kdl_pileup builds (K0): uint32[8 * n_slots / KDL_TILE], device
      * memory owned by the caller.  NULL, or reads_sorted == 0, selects the order-independent
      * atomic kernel instead of the tile-owner kernel. */

@@ -63,6 +63,8 @@ class ReadBatch:
     seq4: np.ndarray              # uint32 [words]: 8 bases per word, first base in the top nibble
     complex_idx: np.ndarray = field(default=None)   # uint32 [n_complex]
     evt_off: np.ndarray = field(default=None)       # uint32 [n_complex+1]
+    cx_cig_off: np.ndarray = field(default=None)    # uint32 [n_complex+1]  device view: CIGARs of the
+    cx_cigar: np.ndarray = field(default=None)      # uint32 [ops]          complex reads only
     n_events: int = 0
     reads_sorted: bool = False
     aligned_bases: int = 0        # sum of M/=/X lengths = sum of the weights table (the metric's unit)
@@ -79,7 +81,7 @@ class ReadBatch:
 
     def input_bytes(self) -> int:
         """Bytes of read data the device consumes (what the e2e path copies host->device)."""
-        arrs = (self.ref_start, self.seq_off, self.l_seq, self.cig_off, self.cigar, self.seq4,
+        arrs = (self.ref_start, self.seq_off, self.l_seq, self.cx_cig_off, self.cx_cigar, self.seq4,
                 self.complex_idx, self.evt_off, self.contig_len, self.contig_read_off, self.contig_slot)
         return int(sum(a.nbytes for a in arrs if a is not None))
 
@@ -165,6 +167,12 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
     evt = np.zeros(complex_idx.shape[0] + 1, dtype=np.int64)
     np.cumsum(ins_per_read[complex_idx], out=evt[1:])
     n_events = int(evt[-1])
+    # only complex reads need their CIGAR on the device (a simple read's is implied by l_seq)
+    cx_n = n_cig[complex_idx]
+    cx_cig_off = np.concatenate(([0], np.cumsum(cx_n))).astype(np.int64)
+    cx_src = np.repeat(cig_off[:-1].astype(np.int64)[complex_idx], cx_n) + (
+        np.arange(int(cx_cig_off[-1]), dtype=np.int64) - np.repeat(cx_cig_off[:-1], cx_n))
+    cx_cigar = cigar[cx_src]
     is_match = (ops_all == 0) | (ops_all == 7) | (ops_all == 8)
     aligned = int(((cigar >> 4).astype(np.int64) * is_match).sum())
 
@@ -181,6 +189,7 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
         contig_slot=slot, n_slots=n_slots, ref_start=ref_start, seq_off=seq_off, l_seq=l_out,
         cig_off=cig_off, cigar=cigar, seq4=seq4, complex_idx=complex_idx,
         evt_off=evt.astype(np.uint32), n_events=n_events, reads_sorted=sorted_ok,
+        cx_cig_off=cx_cig_off.astype(np.uint32), cx_cigar=np.ascontiguousarray(cx_cigar, dtype=np.uint32),
         aligned_bases=aligned, n_records=int(n_records),
         max_simple_len=int(oplen[simple].max()) if simple.any() else 0,
     )

@@ -39,10 +39,11 @@ inline int check_launch() {
 
 int validate_batch(const kdl_batch* b) {
     if (!b || b->n_reads < 0 || b->n_contigs < 0) return KDL_ERR_INVALID_ARG;
-    if (b->n_reads > 0 && (!b->ref_start || !b->seq_off || !b->l_seq || !b->cig_off || !b->seq4 ||
+    if (b->n_reads > 0 && (!b->ref_start || !b->seq_off || !b->l_seq || !b->seq4 ||
                            !b->contig_read_off || !b->contig_len || !b->contig_slot))
         return KDL_ERR_INVALID_ARG;
-    if (b->n_complex > 0 && (!b->complex_idx || !b->evt_off || !b->cigar)) return KDL_ERR_INVALID_ARG;
+    if (b->n_complex > 0 && (!b->complex_idx || !b->evt_off || !b->cig_off || (b->n_ops > 0 && !b->cigar)))
+        return KDL_ERR_INVALID_ARG;
     return KDL_OK;
 }
 
@@ -141,8 +142,8 @@ int kdl_diagnose(const kdl_batch* batch, kdl_diag* diag_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     kdl::diagnose_init_kernel<<<1, 1, 0, st>>>(diag_dev);
     if ((rc = check_launch()) != KDL_OK) return rc;
-    if (batch->n_reads > 0) {
-        const long long grid = (batch->n_reads + 255) / 256;
+    if (batch->n_complex > 0) {
+        const long long grid = (batch->n_complex + 255) / 256;
         kdl::diagnose_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, diag_dev);
         if ((rc = check_launch()) != KDL_OK) return rc;
     }

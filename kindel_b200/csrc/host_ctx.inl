@@ -92,7 +92,7 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
         {kdl_ctx::B_REF_START, hb->ref_start, n * 4},
         {kdl_ctx::B_SEQ_OFF, hb->seq_off, n * 4},
         {kdl_ctx::B_L_SEQ, hb->l_seq, n * 4},
-        {kdl_ctx::B_CIG_OFF, hb->cig_off, (n + 1) * 4},
+        {kdl_ctx::B_CIG_OFF, hb->cig_off, nx ? (nx + 1) * 4 : 0},
         {kdl_ctx::B_CIGAR, hb->cigar, (size_t)hb->n_ops * 4},
         {kdl_ctx::B_SEQ4, hb->seq4, (size_t)hb->seq4_words * 4},
         {kdl_ctx::B_CREAD_OFF, hb->contig_read_off, (nc + 1) * 8},

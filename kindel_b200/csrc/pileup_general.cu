@@ -20,20 +20,20 @@ pileup_general_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slo
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long n_list = b.complex_idx ? b.n_complex : b.n_reads;
+    const long long n_list = b.n_complex;
     bool bad = false;
 
     for (long long j = warp0; j < n_list; j += n_warps) {
-        const long long r = b.complex_idx ? (long long)b.complex_idx[j] : j;
+        const long long r = (long long)b.complex_idx[j];
         const int c = find_contig(b.contig_read_off, b.n_contigs, r);
         const long long L = b.contig_len[c];
         const long long base = b.contig_slot[c];
         const long long lseq = (long long)(b.l_seq[r] & 0x7fffffff);
         const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
-        const uint32_t c0 = b.cig_off[r], c1 = b.cig_off[r + 1];
+        const uint32_t c0 = b.cig_off[j], c1 = b.cig_off[j + 1];  // CIGARs travel for complex reads only
         long long r_pos = b.ref_start[r];
         long long q_pos = 0;
-        uint32_t evt = b.evt_off ? b.evt_off[j] : 0;
+        uint32_t evt = b.evt_off[j];
 
         for (uint32_t i = c0; i < c1; ++i) {
             const uint32_t cg = b.cigar[i];
@@ -122,13 +122,14 @@ pileup_general_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slo
 // One thread per read walks sequentially and stops at the first exception the reference would
 // raise; the minimum over reads of (read << 24 | kind << 20 | nibble << 16 | op) is the error of
 // the first offending record.
-__device__ unsigned long long diagnose_read(const kdl_batch& b, long long r) {
+__device__ unsigned long long diagnose_read(const kdl_batch& b, long long j) {
+    const long long r = (long long)b.complex_idx[j];  // only complex reads can raise (flatten contract)
     const int c = find_contig(b.contig_read_off, b.n_contigs, r);
     const long long L = b.contig_len[c];
     const int32_t lraw = b.l_seq[r];
     const long long lseq = (long long)(lraw & 0x7fffffff);
     const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
-    const uint32_t c0 = b.cig_off[r], c1 = b.cig_off[r + 1];
+    const uint32_t c0 = b.cig_off[j], c1 = b.cig_off[j + 1];
     long long r_pos = b.ref_start[r], q_pos = 0;
 #define KDL_FAIL(kind, nib)                                                                     \
     return ((unsigned long long)r << 24) | ((unsigned long long)(kind) << 20) |                 \
@@ -189,9 +190,9 @@ __global__ void diagnose_init_kernel(kdl_diag* d) {
 }
 
 __global__ void __launch_bounds__(256) diagnose_kernel(kdl_batch b, kdl_diag* d) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= b.n_reads) return;
-    const unsigned long long key = diagnose_read(b, r);
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= b.n_complex) return;
+    const unsigned long long key = diagnose_read(b, j);
     if (key != ~0ull) atomicMin(reinterpret_cast<unsigned long long*>(&d->read), key);
 }
 

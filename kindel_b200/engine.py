@@ -52,13 +52,13 @@ class DeviceBatch:
 def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     s = _ffi.KdlBatch()
     s.n_reads = host.n_reads
-    s.n_ops = int(host.cigar.shape[0])
+    s.n_ops = int(host.cx_cigar.shape[0])
     s.seq4_words = int(host.seq4.shape[0])
     s.ref_start = ptr["ref_start"]
     s.seq_off = ptr["seq_off"]
     s.l_seq = ptr["l_seq"]
-    s.cig_off = ptr["cig_off"]
-    s.cigar = ptr["cigar"]
+    s.cig_off = ptr["cx_cig_off"]
+    s.cigar = ptr["cx_cigar"]
     s.seq4 = ptr["seq4"]
     s.n_contigs = host.n_contigs
     s.reads_sorted = 1 if host.reads_sorted else 0
@@ -74,7 +74,7 @@ def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     return s
 
 
-_FIELDS = ("ref_start", "seq_off", "l_seq", "cig_off", "cigar", "seq4", "contig_read_off", "contig_len",
+_FIELDS = ("ref_start", "seq_off", "l_seq", "cx_cig_off", "cx_cigar", "seq4", "contig_read_off", "contig_len",
            "contig_slot", "complex_idx", "evt_off")
 
 

@@ -95,11 +95,13 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
     }
     if (batch->n_reads == 0) return KDL_OK;
     if (tiled) {
-        // K0: read range per tile (the linear index of a sorted BAM, built on the device)
-        const long long n_tiles_all = n_slots / KDL_TILE;
-        kdl::tile_index_kernel<<<(unsigned)((n_tiles_all * 32 + 255) / 256), 256, 0, st>>>(*batch, n_tiles_all,
-                                                                                   batch->tile_index);
-        if ((rc = check_launch()) != KDL_OK) return rc;
+        // K0: read range per tile of the slot range (the linear index of a sorted BAM, built on device)
+        const long long tile_lo = slot_lo / KDL_TILE, n_tiles = (slot_hi - slot_lo) / KDL_TILE;
+        if (n_tiles > 0) {
+            kdl::tile_index_kernel<<<(unsigned)((n_tiles * 32 + 255) / 256), 256, 0, st>>>(*batch, tile_lo, n_tiles,
+                                                                                          batch->tile_index);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        }
         // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
         static bool attr_set = false;
         const int smem = (int)sizeof(kdl::FastSmem);
@@ -111,7 +113,6 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
                 return KDL_ERR_CUDA;
             attr_set = true;
         }
-        const long long tile_lo = slot_lo / KDL_TILE, n_tiles = (slot_hi - slot_lo) / KDL_TILE;
         if (n_tiles > 0) {
             long long grid = n_tiles < (long long)sm_count() * 2 * 4 ? n_tiles : (long long)sm_count() * 2 * 4;
             if (fresh)

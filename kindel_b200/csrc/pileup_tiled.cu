@@ -76,10 +76,11 @@ __device__ __forceinline__ long long first_read_at_or_after(const kdl_batch& b, 
 }
 
 __global__ void __launch_bounds__(256)
-tile_index_kernel(kdl_batch b, long long n_tiles, uint32_t* __restrict__ index) {
+tile_index_kernel(kdl_batch b, long long tile_lo, long long n_tiles, uint32_t* __restrict__ index) {
     const int lane = threadIdx.x & 31;
-    const long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tile
-    if (t >= n_tiles) return;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tile
+    if (w >= n_tiles) return;
+    const long long t = tile_lo + w;
     const long long g0 = t * KDL_TILE;
     const long long lo = first_read_at_or_after(b, g0 - b.max_simple_len + 1, lane);
     const long long hi = first_read_at_or_after(b, g0 + KDL_TILE, lane);

@@ -131,6 +131,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this same command (profiles/); None for configurations not captured."""
+    if workload != "cfg4_5Mb_200x" or world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_k1f_traffic.json")) as fh:
+            d = json.load(fh)
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------ CPU baselines
 def cpu_port_sample(batch, seconds_target=12.0):
     """Reference-shaped Python port (oracle/py_oracle.py) on a bounded window of the workload:
@@ -315,8 +328,9 @@ def run_native(args):
                                      if args.exchange == "peer" else
                                      "NCCL all_reduce(int32 sum) of the 7 vote columns, vote replicated"),
                        "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": "K1 pileup", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "K0 tile index + K1f tiled pileup", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, world),
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms_max},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI declared in include/kindel_b200.h (unity build of the kernel files).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -114,7 +115,12 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             attr_set = true;
         }
         if (n_tiles > 0) {
-            long long grid = n_tiles < (long long)sm_count() * 2 * 4 ? n_tiles : (long long)sm_count() * 2 * 4;
+            // CTAs per SM-slot: 2 are resident per SM; each CTA walks its tiles with a software pipeline
+            // (metadata of its next tile streams in while it counts), so a persistent grid is best
+            long long mult = 1;
+            if (const char* ev = getenv("KDL_K1F_GRID_MULT")) { mult = atoll(ev); if (mult < 1) mult = 1; }
+            const long long max_grid = (long long)sm_count() * 2 * mult;
+            long long grid = n_tiles < max_grid ? n_tiles : max_grid;
             if (fresh)
                 kdl::pileup_tiled_kernel<true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);

@@ -44,35 +44,53 @@ constexpr int F_FLUSH_BLOCKS = 31;     // 31 blocks x 8 reads = 248 <= 255
 // global slot of a read's first base = contig_slot[c] + ref_start; reads are sorted by it.
 constexpr int F_IDX = 8;  // int32 per tile in the index
 
-// first read index whose global start slot is >= g.  Warp-cooperative: the contig is found by every
-// lane (few contigs), the read by a 32-ary search -- each round the 32 lanes probe 32 evenly spaced
-// elements of the remaining range in ONE memory round trip (5 rounds for 10^7 reads, not 24).
-__device__ __forceinline__ long long first_read_at_or_after(const kdl_batch& b, long long g, int lane) {
-    if (b.n_contigs == 0) return 0;
+// First read index whose global start slot is >= g, for TWO keys at once (a tile's lower and upper
+// bound).  Warp-cooperative: the contig is found by every lane (few contigs), the read by a 32-ary
+// search -- each round the 32 lanes probe 32 evenly spaced elements of the remaining range in ONE
+// memory round trip (5 rounds for 10^7 reads, not 24); the two searches advance in lockstep so
+// their round trips overlap.
+struct Search {
+    long long a, e, p;  // invariant: reads before a are < p, reads from e on are >= p (or e = end)
+    bool live;
+};
+
+__device__ __forceinline__ Search search_begin(const kdl_batch& b, long long g) {
+    Search s;
+    s.live = false;
+    s.a = s.e = 0;
+    s.p = 0;
+    if (b.n_contigs == 0) return s;
     int lo = 0, hi = b.n_contigs;  // first contig with slot + len + 1 > g
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (b.contig_slot[mid] + b.contig_len[mid] + 1 > g) hi = mid; else lo = mid + 1;
     }
-    if (lo >= b.n_contigs) return b.n_reads;
-    const long long p = g - b.contig_slot[lo];  // position inside contig `lo` (may be < 0)
-    long long a = b.contig_read_off[lo], e = b.contig_read_off[lo + 1];
-    while (a < e) {  // invariant: every read before a is < p, every read from e on is >= p
-        const long long n = e - a;
-        const long long step = (n + 31) >> 5;
-        const long long idx = a + (long long)(lane + 1) * step - 1;  // last element of the lane's bucket
-        const bool ge = idx < e ? ((long long)b.ref_start[idx] >= p) : true;
-        const unsigned m = __ballot_sync(0xffffffffu, ge);
-        if (m == 0u) { a = e; break; }  // 32 full buckets and even the very last element is < p
-        const int k = __ffs(m) - 1;     // first bucket whose last element is >= p
-        const long long na = a + (long long)k * step;
-        long long ne = a + (long long)(k + 1) * step - 1;  // that last element is >= p: answer <= ne
-        if (ne > e) ne = e;
-        a = na;
-        e = ne < a ? a : ne;
-        if (step == 1) { a = e; }  // buckets were single elements: e is the answer
-    }
-    return a;
+    if (lo >= b.n_contigs) { s.a = s.e = b.n_reads; return s; }
+    s.p = g - b.contig_slot[lo];  // position inside contig `lo` (may be < 0)
+    s.a = b.contig_read_off[lo];
+    s.e = b.contig_read_off[lo + 1];
+    s.live = s.a < s.e;
+    return s;
+}
+
+__device__ __forceinline__ void search_probe(const kdl_batch& b, const Search& s, int lane, long long& step, bool& ge) {
+    step = (s.e - s.a + 31) >> 5;
+    const long long idx = s.a + (long long)(lane + 1) * step - 1;  // last element of the lane's bucket
+    ge = (s.live && idx < s.e) ? ((long long)b.ref_start[idx] >= s.p) : true;
+}
+
+__device__ __forceinline__ void search_narrow(Search& s, long long step, bool ge) {
+    const unsigned m = __ballot_sync(0xffffffffu, ge);
+    if (!s.live) return;
+    if (m == 0u) { s.a = s.e; s.live = false; return; }  // even the very last element is < p
+    const int k = __ffs(m) - 1;                          // first bucket whose last element is >= p
+    const long long na = s.a + (long long)k * step;
+    long long ne = s.a + (long long)(k + 1) * step - 1;  // that element is >= p: the answer is <= ne
+    if (ne > s.e) ne = s.e;
+    s.a = na;
+    s.e = ne < na ? na : ne;
+    if (step == 1) s.a = s.e;
+    s.live = s.a < s.e;
 }
 
 __global__ void __launch_bounds__(256)
@@ -82,8 +100,16 @@ tile_index_kernel(kdl_batch b, long long tile_lo, long long n_tiles, uint32_t* _
     if (w >= n_tiles) return;
     const long long t = tile_lo + w;
     const long long g0 = t * KDL_TILE;
-    const long long lo = first_read_at_or_after(b, g0 - b.max_simple_len + 1, lane);
-    const long long hi = first_read_at_or_after(b, g0 + KDL_TILE, lane);
+    Search s1 = search_begin(b, g0 - b.max_simple_len + 1), s2 = search_begin(b, g0 + KDL_TILE);
+    while (s1.live || s2.live) {  // warp-uniform
+        long long st1, st2;
+        bool ge1, ge2;
+        search_probe(b, s1, lane, st1, ge1);  // both probes are issued before either is consumed
+        search_probe(b, s2, lane, st2, ge2);
+        search_narrow(s1, st1, ge1);
+        search_narrow(s2, st2, ge2);
+    }
+    const long long lo = s1.a, hi = s2.a;
     if (lane) return;
     uint32_t* e = index + F_IDX * t;
     e[0] = (uint32_t)lo;

@@ -307,3 +307,33 @@ def test_tile_index_power_of_32_read_counts():
         _against_oracle(b)
     b = synth.simple_reads(62, [2000, 90000], 8)  # reads only at the very start of a long slot space
     _against_oracle(b)
+
+
+def test_cli_end_to_end(manifest, tmp_path):
+    """`python -m kindel consensus|weights|features|version` == the reference CLI's output
+    (reference tests/test_kindel.py:114-238 shell out to `kindel consensus <path>`)."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, PYTHONPATH=H.ROOT)
+    for name in ("mm2_multi", "ext_3_bc75", "mm2_gp120"):
+        entry = manifest["files"][name]
+        path = golden_input(entry)
+        for tag, extra in (("plain", []), ("realign", ["-r"]), ("opts", ["--min-depth", "5", "-t", "-u"])):
+            res = subprocess.run([sys.executable, "-m", "kindel", "consensus", *extra, path], capture_output=True,
+                                 text=True, env=env, timeout=300)
+            assert res.returncode == 0, res.stderr[-2000:]
+            lines = res.stdout.strip().split("\n")
+            got = [[lines[i][1:], lines[i + 1] if i + 1 < len(lines) else ""] for i in range(0, len(lines), 2)]
+            assert got == entry["runs"][tag]["fasta"], (name, tag)
+            assert "========================= REPORT ===========================" in res.stderr
+    res = subprocess.run([sys.executable, "-m", "kindel", "version"], capture_output=True, text=True, env=env)
+    assert res.stdout.strip() == "kindel 1.2.1"
+    entry = manifest["files"]["ext_3_bc75"]
+    res = subprocess.run([sys.executable, "-m", "kindel", "weights", golden_input(entry)], capture_output=True,
+                         text=True, env=env, timeout=300)
+    assert res.returncode == 0
+    header = res.stdout.split("\n", 1)[0].split("\t")
+    assert header == ["chrom", "pos", "A", "C", "G", "T", "N", "insertions", "deletions", "clip_starts", "clip_ends",
+                      "depth", "consensus", "shannon", "lower_ci", "upper_ci"]
+    assert len(res.stdout.strip().split("\n")) == 1 + entry["contigs"][0]["ref_len"]

@@ -227,6 +227,7 @@ def run_native(args):
         db = engine.upload(batch, dev)
         table = engine.CountTable(n_slots, dev)
         counts = table.t
+        calls_buf = torch.empty(n_slots, dtype=torch.uint8, device=dev)
 
         def step(timers=None):
             # a fresh pileup into a reused table: nothing is memset, K1f overwrites the weight columns
@@ -235,7 +236,7 @@ def run_native(args):
             engine.pileup(db, check=False, table=table)
             if timers:
                 timers[1].record()
-            return engine.vote(counts, 1)
+            return engine.vote(counts, 1, out=calls_buf)
     else:
         from kindel_b200 import distributed
 
@@ -319,7 +320,8 @@ def run_native(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "reads_total": None, "aligned_bases_total": int(total_bases),
+            "config": {"workload": args.workload, "reads_per_rank": int(batch.n_reads),
+                       "aligned_bases_total": int(total_bases),
                        "sharding": "contiguous blocks of the coordinate-sorted reads" if world > 1 else "none",
                        "reduction": ("none" if world == 1 else
                                      "K2x: flags + reduce + vote + call scatter in one kernel over CUDA-IPC peer memory "

@@ -236,7 +236,9 @@ class ShardedConsensus:
             return self.tables.calls
         if self.mode == "allreduce":
             dist.all_reduce(self.counts[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM, group=self.group)
-            return engine.vote(self.counts, min_depth)
+            if getattr(self, "_calls_ar", None) is None:
+                self._calls_ar = torch.empty(self.n_slots, dtype=torch.uint8, device=self.device)
+            return engine.vote(self.counts, min_depth, out=self._calls_ar)
         # every table complete before anybody reads it over NVLink
         dist.barrier(group=self.group)
         lo, hi = self.slices[self.rank]

@@ -147,8 +147,15 @@ def pileup(dbatch: DeviceBatch, counts: torch.Tensor = None, check: bool = True,
     dev = dbatch.device
     n_slots = dbatch.n_slots
     with torch.cuda.device(dev):
-        events = torch.empty((max(dbatch.host.n_events, 1), 4), dtype=torch.int32, device=dev)
-        flag = torch.zeros(4, dtype=torch.int32, device=dev)
+        # scratch that lives with the batch: the insertion-event rows and the 16-byte error flag
+        events = dbatch.tensors.get("_events")
+        if events is None:
+            events = dbatch.tensors["_events"] = torch.empty((max(dbatch.host.n_events, 1), 4), dtype=torch.int32,
+                                                             device=dev)
+            dbatch.tensors["_flag"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        flag = dbatch.tensors["_flag"]
+        if check:
+            flag.zero_()  # unchecked calls (hot loops) never read it
         if table is not None:
             counts = table.t
             lo, hi = slot_range if slot_range is not None else (0, n_slots)
@@ -184,13 +191,13 @@ def diagnose_and_raise(dbatch: DeviceBatch):
     raise RuntimeError("pileup raised its error flag but no offending read was found")
 
 
-def vote(counts: torch.Tensor, min_depth=1) -> torch.Tensor:
-    """K2.  counts int32[>=7, n_slots] (contiguous) -> calls uint8[n_slots]."""
+def vote(counts: torch.Tensor, min_depth=1, out: torch.Tensor = None) -> torch.Tensor:
+    """K2.  counts int32[>=7, n_slots] (contiguous) -> calls uint8[n_slots] (`out` reuses a buffer)."""
     lib = _ffi.load()
     dev = counts.device
     n_slots = counts.shape[1]
     with torch.cuda.device(dev):
-        calls = torch.empty(n_slots, dtype=torch.uint8, device=dev)
+        calls = out if out is not None else torch.empty(n_slots, dtype=torch.uint8, device=dev)
         rc = lib.kdl_vote(counts.data_ptr(), n_slots, int(math.ceil(min_depth)), calls.data_ptr(),
                           _stream_ptr(dev))
         _ffi.check(rc, "kdl_vote")

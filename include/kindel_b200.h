@@ -185,7 +185,8 @@ int kdl_vote_peers_sparse(const int32_t* const* peer_counts, const int64_t* foot
  * Every rank owns one IPC block: [count table 19 x n_slots int32][calls n_slots bytes][flags].
  * Per step (epoch e = 1, 2, ...), on every rank, in stream order:
  *   kdl_pileup(...)                       its shard into its own table
- *   kdl_exchange_signal(x, e)             "my table is complete" -> ready[p][rank] = e in every peer p
+ *   kdl_exchange_signal(x, e)             optional early "my table is complete" -> ready[p][rank] = e in
+ *                                         every peer p (kdl_exchange_vote publishes it too, first thing)
  *   kdl_exchange_vote(x, ..., e)          K2x: waits for ready[rank][*] >= e, sums the 7 vote columns
  *                                         of its slot slice [slice_lo[rank], slice_hi[rank]) over the
  *                                         (footprint-clipped) peer tables through NVLink, votes,

@@ -145,7 +145,13 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(Exchange x, int ep
 
 __global__ void __launch_bounds__(256)
 vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, int epoch) {
-    // every table this CTA may read must be complete: ready[rank][p] >= epoch for all p
+    // this kernel runs after the rank's pileup kernels in stream order, so its own table is complete:
+    // CTA 0 publishes that to every peer (kdl_exchange_signal is then optional) ...
+    if (blockIdx.x == 0 && threadIdx.x < x.peers.n) {
+        __threadfence_system();
+        st_release_sys(x.ready[threadIdx.x] + x.rank, epoch);
+    }
+    // ... and every table this CTA may read must be complete: ready[rank][p] >= epoch for all p
     if (threadIdx.x < x.peers.n)
         while (ld_acquire_sys(x.ready_local + threadIdx.x) < epoch) __nanosleep(32);
     __syncthreads();

@@ -223,13 +223,12 @@ class ShardedConsensus:
         if timers:
             timers[1].record()
         if self.mode == "fused":
-            # no NCCL on the data path: flags, reduction, vote and the scatter of the call bytes are
-            # three launches of this library over NVLink peer memory
+            # no NCCL on the data path: flags + reduction + vote (K2x) and the pull of the call slices
+            # (K2g) are two launches of this library over NVLink peer memory
             self.epoch += 1
             lo, hi = self.slices[self.rank]
             st = int(torch.cuda.current_stream(self.device).cuda_stream)
             with torch.cuda.device(self.device):
-                _ffi.check(self.lib.kdl_exchange_signal(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_signal")
                 _ffi.check(self.lib.kdl_exchange_vote(C.byref(self.xstruct), self.n_slots, int(math.ceil(min_depth)),
                                                       self.epoch, st), "kdl_exchange_vote")
                 _ffi.check(self.lib.kdl_exchange_wait(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_wait")

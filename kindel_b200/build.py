@@ -26,7 +26,7 @@ ORACLE_LIB = os.path.join(ORACLE_DIR, "libkindel_oracle.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
+    "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-fvisibility=default",
     "-Xptxas", "-v",
     "-shared", "-cudart", "static",

@@ -22,15 +22,38 @@ inline int grid_for(long long items, int per_block, int cap) {
     return (int)g;
 }
 
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+
+// SM count of the CURRENT device (a process may drive several GPUs)
 inline int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
     }
     return n;
+}
+
+// opt-in to > 48 KB dynamic shared memory for K1f, once per device
+inline int ensure_k1f_smem(int smem) {
+    static std::atomic<int> done[kMaxDevices];
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
+    if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+        return KDL_ERR_CUDA;
+    done[dev].store(1, std::memory_order_release);
+    return KDL_OK;
 }
 
 inline int check_launch() {
@@ -104,16 +127,8 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
         // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
-        static bool attr_set = false;
         const int smem = (int)sizeof(kdl::FastSmem);
-        if (!attr_set) {
-            if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     smem) != cudaSuccess ||
-                cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     smem) != cudaSuccess)
-                return KDL_ERR_CUDA;
-            attr_set = true;
-        }
+        if ((rc = ensure_k1f_smem(smem)) != KDL_OK) return rc;
         if (n_tiles > 0) {
             // CTAs per SM-slot: 2 are resident per SM; each CTA walks its tiles with a software pipeline
             // (metadata of its next tile streams in while it counts), so a persistent grid is best

@@ -33,7 +33,7 @@ namespace kdl {
 constexpr int F_THREADS = 256;
 constexpr int F_WIN = 64;              // slots per warp window
 constexpr int F_RMAX = 1024;           // reads per staged sub-chunk
-constexpr int F_CAPW = 18432;          // seq words per staged sub-chunk (72 KB)
+constexpr int F_CAPW = 17920;          // seq words per staged sub-chunk (70 KB): 2 CTAs x ~111 KB per SM
 constexpr int F_P = 8;                 // bit planes per stream: up to 255 reads between flushes
 constexpr int F_FLUSH_BLOCKS = 31;     // 31 blocks x 8 reads = 248 <= 255
 
@@ -315,7 +315,7 @@ struct FastSmem {
     //   .y  shared-memory address (u32) of the read's first word
     //   .z  bytes of packed bases (0 = not a simple read: adds nothing)
     //   .w  funnel-shift amount 4 * ((-start) & 7)
-    int4 meta[F_RMAX + 32];
+    int4 meta[F_RMAX + 40 + (F_RMAX + 40) / 8];  // entry of read i at i + i/8 (one pad per 8: see main loop)
     int gs[F_RMAX + 32];          // start slot relative to the tile (all reads: the array stays sorted)
     int diff[2][KDL_TILE + 32];   // +1 at read start, -1 at read end (double-buffered per sub-chunk)
     int cov[KDL_TILE];            // prefix sums of diff: simple reads covering each slot
@@ -465,14 +465,15 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                             }
                         }
                         sm.gs[i] = gs;
-                        sm.meta[i] = make_int4(((gs + 7) >> 3) << 2,
+                        sm.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
                                                (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
                                                ((-gs) & 7) << 2);
                     }
                 }
-                if (tid < 32) {  // sentinels: never overlap anything
-                    sm.gs[n_sub + tid] = 0x10000000;
-                    sm.meta[n_sub + tid] = make_int4(0x10000000, (int)seq_base, 0, 0);
+                if (tid < 40) {  // sentinels: never overlap anything
+                    const int i = n_sub + tid;
+                    if (tid < 32) sm.gs[i] = 0x10000000;
+                    sm.meta[i + (i >> 3)] = make_int4(0x10000000, (int)seq_base, 0, 0);
                 }
                 if (raw_pending) {  // this thread's raw elements are consumed: refill them for the next tile
                     prefetch_raw(tile + gridDim.x);
@@ -514,15 +515,20 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
             const int a = lower_bound_warp(sm.gs, n_sub, wlo - maxlen + 1, lane);
             const int e = lower_bound_warp(sm.gs, n_sub, wlo + F_WIN, lane);
 
-            for (int base = a; base < e; base += 32) {
-                // 8 reads per lane and block.  No bounds logic: a read that does not reach the lane's
-                // 8 slots (including the sentinels behind the last read, and reads [e, ...) that start
-                // right of the window) fails both range tests below and contributes zero.
+            for (int base = a & ~7; base < e; base += 32) {
+                // 8 reads per lane and block: quarter q takes the 8 CONSECUTIVE reads base + 8q .. + 7.
+                // With 19-word reads the four quarters then hit four disjoint groups of 8 banks
+                // (8 reads = 152 words = 24 mod 32), and the metadata entries -- padded by one per 8
+                // reads, so the quarters' entries are 144 B = 4 banks apart -- do not collide either.
+                // No bounds logic: a read that does not reach the lane's 8 slots (the up to 7 reads
+                // before a, reads [e, ...) right of the window, the sentinels behind the last read)
+                // fails both range tests below and contributes zero.
                 uint32_t x[8];
                 int4 mt[8];
-                const int4* mp = sm.meta + base + quarter;
+                const int i0 = base + 8 * quarter;
+                const int4* mp = sm.meta + i0 + (i0 >> 3);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) mt[u] = mp[4 * u];
+                for (int u = 0; u < 8; ++u) mt[u] = mp[u];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const uint32_t jb = (uint32_t)(p8b - mt[u].x);  // byte offset of the read's word

@@ -337,3 +337,32 @@ def test_cli_end_to_end(manifest, tmp_path):
     assert header == ["chrom", "pos", "A", "C", "G", "T", "N", "insertions", "deletions", "clip_starts", "clip_ends",
                       "depth", "consensus", "shannon", "lower_ci", "upper_ci"]
     assert len(res.stdout.strip().split("\n")) == 1 + entry["contigs"][0]["ref_len"]
+
+
+def test_very_long_complex_read_among_short_reads(tmp_path):
+    """A 200 kb read with an indel (complex: K1g) sitting in the middle of sorted short reads: its bases
+    sit in the same packed array, larger than one staging buffer of the tile kernel, which must skip
+    them (sub-chunk logic) while still counting every short read around it."""
+    from kindel_b200 import bamio
+    from kindel_b200 import kindel as K
+
+    rng = np.random.default_rng(77)
+    L = 400_000
+    starts = np.sort(rng.integers(0, L - 150, size=3000))
+    lines = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:big\tLN:%d" % L]
+    long_pos = 100_000
+    long_seq = "".join(rng.choice(list("ACGT"), size=200_010))
+    placed = False
+    for k, s in enumerate(starts.tolist()):
+        if not placed and s >= long_pos:
+            lines.append("long\t0\tbig\t%d\t60\t100000M10I100000M\t*\t0\t0\t%s\t*" % (long_pos + 1, long_seq))
+            placed = True
+        seq = "".join(rng.choice(list("ACGTN"), size=150, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        lines.append("r%d\t0\tbig\t%d\t60\t150M\t*\t0\t0\t%s\t*" % (k, s + 1, seq))
+    p = tmp_path / "long.sam"
+    p.write_text("\n".join(lines) + "\n")
+    batch = bamio.read_alignment(p)
+    assert batch.reads_sorted and len(batch.complex_idx) == 1 and batch.max_simple_len == 150
+    _against_oracle(batch)
+    aln = K.parse_bam(p)["big"]
+    assert aln.insertions[long_pos + 100_000] == {long_seq[100_000:100_010]: 1}

@@ -309,7 +309,9 @@ def run_native(args):
                "h2d_bytes_per_step": batch.input_bytes(), "d2h_bytes_per_step": int(n_slots) + 16,
                "ms_per_step": float(tt[0]), "wall_ms_per_step": float(tt[1]),
                "breakdown_ms": {k: statistics.mean(x[2][k] for x in e2e_ms) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
-               "api": "kdl_ctx_consensus (include/kindel_b200.h), pinned host buffers"}
+               "api": "kdl_ctx_consensus (include/kindel_b200.h), pinned host buffers",
+               "note": None if world == 1 else "every rank pushes its own shard through the host-buffer call "
+                       "concurrently (N PCIe links); the cross-rank exchange is part of `value`, not of this leg"}
         ctx.close()
 
     clocks = sampler.stop() if rank == 0 else None

@@ -9,6 +9,7 @@
 #include "pileup_general.cu"
 #include "pileup_simple.cu"
 #include "pileup_tiled.cu"
+#include "pileup_ws.cu"
 #include "vote.cu"
 
 namespace {
@@ -52,8 +53,21 @@ inline int ensure_k1f_smem(int smem) {
         cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
             cudaSuccess)
         return KDL_ERR_CUDA;
+    if (cudaFuncSetAttribute(kdl::pileup_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(kdl::WsSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(kdl::pileup_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(kdl::WsSmem)) != cudaSuccess)
+        return KDL_ERR_CUDA;
     done[dev].store(1, std::memory_order_release);
     return KDL_OK;
+}
+
+// which tile-owner kernel: "ws" = warp-specialised pipeline (K1w), "tiled" = K1f
+inline bool use_ws_kernel() {
+    const char* ev = getenv("KDL_K1F");
+    if (ev && !strcmp(ev, "tiled")) return false;
+    if (ev && !strcmp(ev, "ws")) return true;
+    return false;
 }
 
 inline int check_launch() {
@@ -129,7 +143,18 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
         // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
         const int smem = (int)sizeof(kdl::FastSmem);
         if ((rc = ensure_k1f_smem(smem)) != KDL_OK) return rc;
-        if (n_tiles > 0) {
+        if (n_tiles > 0 && use_ws_kernel()) {
+            // K1w: one persistent CTA per SM (4 producer + 8 consumer warps, ~200 KB shared memory)
+            long long grid = n_tiles < (long long)sm_count() ? n_tiles : (long long)sm_count();
+            const int wsmem = (int)sizeof(kdl::WsSmem);
+            if (fresh)
+                kdl::pileup_ws_kernel<true><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            else
+                kdl::pileup_ws_kernel<false><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        } else if (n_tiles > 0) {
             // CTAs per SM-slot: 2 are resident per SM; each CTA walks its tiles with a software pipeline
             // (metadata of its next tile streams in while it counts), so a persistent grid is best
             long long mult = 1;

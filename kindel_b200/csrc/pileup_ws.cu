@@ -1,0 +1,312 @@
+// pileup_ws.cu -- K1w: the tile-owner pileup of pileup_tiled.cu as a warp-specialised pipeline.
+//
+// Same arithmetic as K1f (bit-sliced positional popcount over TMA-staged reads, N recovered from the
+// coverage identity, exclusive tile ownership) -- what changes is WHO does the per-tile bookkeeping.
+// In K1f all 8 warps of a CTA stage a tile together (index load, bulk copy, per-read metadata,
+// difference array, two CTA barriers, an mbarrier wait) and only then count it; ncu shows 62 % of the
+// kernel's time in those phases at low issue rates, with only two CTAs per SM to overlap them.
+// Here one persistent CTA per SM runs
+//     4 PRODUCER warps: for every (tile, sub-chunk) item -- wait for a free stage, one bulk copy of the
+//                       reads' bases (TMA, completes on the stage's `full` mbarrier), per-read
+//                       metadata, coverage prefix sums, header; arrive on `full`;
+//     8 CONSUMER warps: wait `full`, count their 64-slot window against the item's reads (the K1f inner
+//                       loop, unchanged), flush at the end of a tile, arrive on the stage's `empty`;
+// over a two-stage ring in ~200 KB of shared memory.  Consumers never touch global memory except for
+// the table stores, never hit a CTA-wide barrier, and start a tile the moment its item is complete;
+// the producers run one item ahead.
+#include "kdl_common.cuh"
+
+namespace kdl {
+
+constexpr int W_CONSUMERS = 8;                    // consumer warps (one 64-slot window each)
+constexpr int W_PRODUCERS = 4;                    // producer warps
+constexpr int W_THREADS = 32 * (W_CONSUMERS + W_PRODUCERS);
+constexpr int W_STAGES = 2;
+constexpr int W_RMAX = F_RMAX;                    // reads per item
+constexpr int W_CAPW = 17920;                     // words of packed bases per item (70 KB)
+
+enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
+
+struct WsStage {
+    uint32_t seq[W_CAPW];
+    int4 meta[W_RMAX + 40 + (W_RMAX + 40) / 8];  // as in FastSmem: entry of read i at i + i/8
+    int gs[W_RMAX + 32];
+    int cov[KDL_TILE];                            // simple reads of THIS item covering each slot
+    int diff[KDL_TILE + 32];                      // producers only
+    long long tile_slot;
+    int n_sub;
+    int flags;
+};
+
+struct WsSmem {
+    WsStage st[W_STAGES];
+    uint64_t full[W_STAGES];   // producers -> consumers: 4 warp arrivals + the bulk copy's bytes
+    uint64_t empty[W_STAGES];  // consumers -> producers: 8 warp arrivals
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {  // no arrival
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void producer_sync() {  // the 128 producer threads only
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * W_PRODUCERS) : "memory");
+}
+
+template <bool kFresh>
+__global__ void __launch_bounds__(W_THREADS, 1)
+pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
+                 const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int maxlen = b.max_simple_len;
+
+    if (tid == 0) {
+        for (int s = 0; s < W_STAGES; ++s) {
+            mbar_init(&sm.full[s], W_PRODUCERS);
+            mbar_init(&sm.empty[s], W_CONSUMERS);
+        }
+    }
+    for (int s = 0; s < W_STAGES; ++s)
+        for (int k = tid; k < KDL_TILE + 32; k += W_THREADS) sm.st[s].diff[k] = 0;
+    __syncthreads();
+
+    if (warp >= W_CONSUMERS) {
+        // =========================== PRODUCERS ====================================================
+        const int pw = warp - W_CONSUMERS;          // 0..3
+        const int ptid = tid - 32 * W_CONSUMERS;    // 0..127
+        long long item = 0;
+        auto acquire_stage = [&](long long it) -> WsStage& {
+            const int s = (int)(it % W_STAGES);
+            const uint32_t round = (uint32_t)(it / W_STAGES);
+            if (round > 0) mbar_wait(&sm.empty[s], (round - 1) & 1u);  // consumers released its last use
+            return sm.st[s];
+        };
+        auto publish = [&](long long it) {  // this warp's part of the item is written
+            const int s = (int)(it % W_STAGES);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.full[s]);
+        };
+
+        for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
+            const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
+            const uint2 ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
+            const long long lo = ix.x, hi = ix.y;
+            const long long tile_slot = tile * KDL_TILE;
+            if (lo >= hi) {
+                if (kFresh) {  // consumers must store zeros: a header-only item
+                    WsStage& st = acquire_stage(item);
+                    if (ptid == 0) { st.tile_slot = tile_slot; st.n_sub = 0; st.flags = ITEM_FIRST | ITEM_LAST | ITEM_EMPTY; }
+                    publish(item);
+                    ++item;
+                }
+                continue;
+            }
+            const bool one_contig = ic.x == ic.y;
+            const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
+            long long c0 = lo;
+            bool first = true;
+            while (c0 < hi) {
+                long long c1 = c0 + W_RMAX < hi ? c0 + W_RMAX : hi;
+                const long long wa = c0 == lo ? (long long)ix.z : (long long)(b.seq_off[c0] & ~3u);
+                long long wend = c1 == hi ? (long long)ix.w : (long long)b.seq_off[c1];
+                bool skip = false;
+                while (wend - wa > W_CAPW) {
+                    if (c1 - c0 == 1) { skip = true; break; }  // one read too long to stage: never simple
+                    c1 = c0 + (c1 - c0) / 2;
+                    wend = (long long)b.seq_off[c1];
+                }
+                const bool last = c1 >= hi;
+                const int n_sub = skip ? 0 : (int)(c1 - c0);
+                WsStage& st = acquire_stage(item);
+                const uint32_t seq_base = smem_u32(st.seq);
+                uint32_t tx = 0;
+                if (!skip) {
+                    const long long n_words = wend - wa;
+                    const long long avail = b.seq4_words - wa;
+                    const long long want = (n_words + 3) & ~3ll;
+                    const long long bulk_words = want <= avail ? want : (avail & ~3ll);
+                    tx = (uint32_t)(bulk_words * 4);
+                    if (ptid == 0 && bulk_words) {  // announce the bytes, then let the TMA engine copy them
+                        uint64_t* fb = &sm.full[(int)(item % W_STAGES)];
+                        mbar_expect_tx_only(fb, tx);
+                        bulk_g2s(st.seq, b.seq4 + wa, tx, fb);
+                    }
+                    if (bulk_words < n_words && ptid < 4) {
+                        const long long w = bulk_words + ptid;
+                        st.seq[w] = w < avail ? b.seq4[wa + w] : 0u;
+                    }
+                }
+                // per-read metadata (8 reads per producer thread at most), difference array
+                for (int i0 = 0; i0 < n_sub; i0 += 32 * W_PRODUCERS * 4) {
+                    int l[4], rs[4];
+                    uint32_t so[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + ptid + k * 32 * W_PRODUCERS;
+                        const long long r = c0 + (i < n_sub ? i : 0);
+                        l[k] = b.l_seq[r];
+                        rs[k] = b.ref_start[r];
+                        so[k] = b.seq_off[r];
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + ptid + k * 32 * W_PRODUCERS;
+                        if (i < n_sub) {
+                            long long g;
+                            if (one_contig) {
+                                g = slot_base + rs[k];
+                            } else {
+                                const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
+                                g = b.contig_slot[c] + rs[k] - tile_slot;
+                            }
+                            g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
+                            const int gs = (int)g;
+                            int nb = 0;
+                            if (l[k] > 0) {
+                                nb = ((l[k] + 7) >> 3) << 2;
+                                const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
+                                if (cs < ce) {
+                                    atomicAdd(st.diff + cs, 1);
+                                    atomicAdd(st.diff + ce, -1);
+                                }
+                            }
+                            st.gs[i] = gs;
+                            st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
+                                                              (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)),
+                                                              nb, ((-gs) & 7) << 2);
+                        }
+                    }
+                }
+                if (ptid < 40) {  // sentinels behind the last read
+                    const int i = n_sub + ptid;
+                    if (ptid < 32) st.gs[i] = 0x10000000;
+                    st.meta[i + (i >> 3)] = make_int4(0x10000000, (int)seq_base, 0, 0);
+                }
+                if (ptid == 0) {
+                    st.tile_slot = tile_slot;
+                    st.n_sub = n_sub;
+                    st.flags = (first ? ITEM_FIRST : 0) | (last ? ITEM_LAST : 0);
+                }
+                producer_sync();  // difference array complete
+                {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
+                    const int w0 = 128 * pw;
+                    int pre = 0;
+                    for (int k = lane; k < w0; k += 32) pre += st.diff[k];
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
+                    int v[4];
+                    int run = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { v[k] = st.diff[w0 + 4 * lane + k]; run += v[k]; }
+                    int incl = run;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    int acc = pre + incl - run;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { acc += v[k]; st.cov[w0 + 4 * lane + k] = acc; }
+                }
+                producer_sync();  // everybody has read diff: clean it for the stage's next use
+                for (int k = ptid; k < KDL_TILE + 32; k += 32 * W_PRODUCERS) st.diff[k] = 0;
+                publish(item);
+                ++item;
+                first = false;
+                c0 = c1;
+            }
+        }
+        {   // END item
+            WsStage& st = acquire_stage(item);
+            if (ptid == 0) { st.tile_slot = 0; st.n_sub = 0; st.flags = ITEM_END; }
+            publish(item);
+        }
+        return;
+    }
+
+    // =============================== CONSUMERS ===================================================
+    const int quarter = lane >> 3;
+    const int wlo = warp * F_WIN;
+    const int p8b = (wlo >> 1) + 4 * (lane & 7);
+    Planes acc;
+    acc.clear();
+    int rawacc[8], covacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { rawacc[k] = 0; covacc[k] = 0; }
+    int blocks_since_flush = 0;
+    bool stored = false;
+
+    for (long long item = 0;; ++item) {
+        const int s = (int)(item % W_STAGES);
+        mbar_wait(&sm.full[s], (uint32_t)((item / W_STAGES) & 1));
+        WsStage& st = sm.st[s];
+        const int flags = st.flags;
+        const int n_sub = st.n_sub;
+        const long long tile_slot = st.tile_slot;
+        if (flags & ITEM_END) break;
+        if (flags & ITEM_FIRST) {
+            stored = false;
+            blocks_since_flush = 0;  // (already 0 after the previous tile's final flush)
+        }
+        if (n_sub > 0) {
+            {
+                const int4 ca = *reinterpret_cast<const int4*>(st.cov + wlo + 8 * (lane & 7));
+                const int4 cb = *reinterpret_cast<const int4*>(st.cov + wlo + 8 * (lane & 7) + 4);
+                covacc[0] += ca.x; covacc[1] += ca.y; covacc[2] += ca.z; covacc[3] += ca.w;
+                covacc[4] += cb.x; covacc[5] += cb.y; covacc[6] += cb.z; covacc[7] += cb.w;
+            }
+            const int a = lower_bound_warp(st.gs, n_sub, wlo - maxlen + 1, lane);
+            const int e = lower_bound_warp(st.gs, n_sub, wlo + F_WIN, lane);
+            for (int base = a & ~7; base < e; base += 32) {
+                uint32_t x[8];
+                int4 mt[8];
+                const int i0 = base + 8 * quarter;
+                const int4* mp = st.meta + i0 + (i0 >> 3);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) mt[u] = mp[u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t jb = (uint32_t)(p8b - mt[u].x);
+                    const uint32_t addr = (uint32_t)mt[u].y + jb;
+                    uint32_t hw, lw;
+                    asm("{\n"
+                        ".reg .pred p, q;\n"
+                        "setp.lt.u32 p, %2, %3;\n"
+                        "setp.lt.u32 q, %4, %3;\n"
+                        "mov.u32 %0, 0;\n"
+                        "mov.u32 %1, 0;\n"
+                        "@p ld.shared.u32 %0, [%5];\n"
+                        "@q ld.shared.u32 %1, [%5+4];\n"
+                        "}\n"
+                        : "=&r"(hw), "=&r"(lw)
+                        : "r"(jb), "r"((uint32_t)mt[u].z), "r"(jb + 4u), "r"(addr));
+                    x[u] = __funnelshift_l(lw, hw, (uint32_t)mt[u].w);
+                }
+                acc.add8(x);
+                if (++blocks_since_flush == F_FLUSH_BLOCKS) {
+                    if (kFresh && !stored)
+                        flush_window<true, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+                    else
+                        flush_window<false, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+                    stored = true;
+                    blocks_since_flush = 0;
+                }
+            }
+        }
+        // this warp is done reading the stage: hand it back before the (global-memory) flush
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+        if (flags & ITEM_LAST) {
+            if (kFresh && !stored) flush_window<true, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            else flush_window<false, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            blocks_since_flush = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) covacc[k] = 0;
+        }
+    }
+}
+
+}  // namespace kdl

@@ -11,8 +11,8 @@ from kindel_b200 import engine, synth  # noqa: E402
 b = synth.simple_reads(4, [5_000_000], 200)
 db = engine.upload(b)
 table = engine.CountTable(b.n_slots, db.device)
-for mult in (1, 2, 3, 4, 8, 33):
-    os.environ["KDL_K1F_GRID_MULT"] = str(mult)
+for mult in os.environ.get("SWEEP", "tiled,ws").split(","):
+    os.environ["KDL_K1F"] = mult
     for _ in range(3):
         engine.pileup(db, check=False, table=table)
     torch.cuda.synchronize()
@@ -22,4 +22,4 @@ for mult in (1, 2, 3, 4, 8, 33):
         engine.pileup(db, check=False, table=table)
     ev[1].record()
     torch.cuda.synchronize()
-    print("grid mult", mult, "K0+K1f ms", ev[0].elapsed_time(ev[1]) / 10, flush=True)
+    print("kernel", mult, "K0+K1f ms", ev[0].elapsed_time(ev[1]) / 10, flush=True)

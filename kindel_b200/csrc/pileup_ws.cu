@@ -40,6 +40,7 @@ struct WsStage {
 
 struct WsSmem {
     WsStage st[W_STAGES];
+    int raw[3][W_RMAX];        // producers only: l_seq / ref_start / seq_off of the NEXT tile's first reads
     uint64_t full[W_STAGES];   // producers -> consumers: 4 warp arrivals + the bulk copy's bytes
     uint64_t empty[W_STAGES];  // consumers -> producers: 8 warp arrivals
 };
@@ -90,9 +91,36 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             if (lane == 0) mbar_arrive(&sm.full[s]);
         };
 
+        // The producers run a software pipeline of their own: the index entry of the next tile and the
+        // three metadata words of its first reads are in flight (cp.async into sm.raw, each thread
+        // fetching exactly the elements it will consume) while the current item is being prepared.
+        constexpr int PT = 32 * W_PRODUCERS;
+        constexpr int PER = W_RMAX / PT;  // reads per producer thread and item
+        auto load_index = [&](long long t, uint4& ix, uint2& ic) {
+            if (t < tile_lo + n_tiles) {
+                ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * t));
+                ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * t + 4));
+            } else {
+                ix = make_uint4(0, 0, 0, 0);
+                ic = make_uint2(0, 0);
+            }
+        };
+        auto prefetch_raw = [&](const uint4& ix) {
+            const long long plo = ix.x, phi = ix.y;
+            const int cnt = (int)(phi - plo < W_RMAX ? phi - plo : W_RMAX);
+            for (int i = ptid; i < cnt; i += PT) {
+                cp_async4(&sm.raw[0][i], b.l_seq + plo + i);
+                cp_async4(&sm.raw[1][i], b.ref_start + plo + i);
+                cp_async4(&sm.raw[2][i], b.seq_off + plo + i);
+            }
+        };
+        uint4 ix, nix;
+        uint2 ic, nic;
+        load_index(tile_lo + blockIdx.x, ix, ic);
+        prefetch_raw(ix);
+
         for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
-            const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
-            const uint2 ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
+            load_index(tile + gridDim.x, nix, nic);  // consumed at the end of this iteration
             const long long lo = ix.x, hi = ix.y;
             const long long tile_slot = tile * KDL_TILE;
             if (lo >= hi) {
@@ -102,12 +130,16 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     publish(item);
                     ++item;
                 }
+                prefetch_raw(nix);  // nothing was in flight for an empty tile
+                ix = nix;
+                ic = nic;
                 continue;
             }
             const bool one_contig = ic.x == ic.y;
             const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
             long long c0 = lo;
             bool first = true;
+            bool raw_pending = true;
             while (c0 < hi) {
                 long long c1 = c0 + W_RMAX < hi ? c0 + W_RMAX : hi;
                 const long long wa = c0 == lo ? (long long)ix.z : (long long)(b.seq_off[c0] & ~3u);
@@ -120,15 +152,41 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 }
                 const bool last = c1 >= hi;
                 const int n_sub = skip ? 0 : (int)(c1 - c0);
+                // this thread's reads of the item: from the prefetched words (first sub-chunk) or directly
+                int l[PER], rs[PER];
+                uint32_t so[PER];
+                if (c0 == lo && raw_pending) {
+                    cp_async_wait_all();
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        const int i = ptid + k * PT;
+                        const int ii = i < n_sub ? i : ptid;
+                        l[k] = sm.raw[0][ii];
+                        rs[k] = sm.raw[1][ii];
+                        so[k] = (uint32_t)sm.raw[2][ii];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        const int i = ptid + k * PT;
+                        const long long r = c0 + (i < n_sub ? i : 0);
+                        l[k] = b.l_seq[r];
+                        rs[k] = b.ref_start[r];
+                        so[k] = b.seq_off[r];
+                    }
+                }
+                if (raw_pending) {  // own elements are in registers: refill them for the next tile
+                    prefetch_raw(nix);
+                    raw_pending = false;
+                }
                 WsStage& st = acquire_stage(item);
                 const uint32_t seq_base = smem_u32(st.seq);
-                uint32_t tx = 0;
                 if (!skip) {
                     const long long n_words = wend - wa;
                     const long long avail = b.seq4_words - wa;
                     const long long want = (n_words + 3) & ~3ll;
                     const long long bulk_words = want <= avail ? want : (avail & ~3ll);
-                    tx = (uint32_t)(bulk_words * 4);
+                    const uint32_t tx = (uint32_t)(bulk_words * 4);
                     if (ptid == 0 && bulk_words) {  // announce the bytes, then let the TMA engine copy them
                         uint64_t* fb = &sm.full[(int)(item % W_STAGES)];
                         mbar_expect_tx_only(fb, tx);
@@ -139,45 +197,32 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         st.seq[w] = w < avail ? b.seq4[wa + w] : 0u;
                     }
                 }
-                // per-read metadata (8 reads per producer thread at most), difference array
-                for (int i0 = 0; i0 < n_sub; i0 += 32 * W_PRODUCERS * 4) {
-                    int l[4], rs[4];
-                    uint32_t so[4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = i0 + ptid + k * 32 * W_PRODUCERS;
-                        const long long r = c0 + (i < n_sub ? i : 0);
-                        l[k] = b.l_seq[r];
-                        rs[k] = b.ref_start[r];
-                        so[k] = b.seq_off[r];
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = i0 + ptid + k * 32 * W_PRODUCERS;
-                        if (i < n_sub) {
-                            long long g;
-                            if (one_contig) {
-                                g = slot_base + rs[k];
-                            } else {
-                                const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
-                                g = b.contig_slot[c] + rs[k] - tile_slot;
-                            }
-                            g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
-                            const int gs = (int)g;
-                            int nb = 0;
-                            if (l[k] > 0) {
-                                nb = ((l[k] + 7) >> 3) << 2;
-                                const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
-                                if (cs < ce) {
-                                    atomicAdd(st.diff + cs, 1);
-                                    atomicAdd(st.diff + ce, -1);
-                                }
-                            }
-                            st.gs[i] = gs;
-                            st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
-                                                              (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)),
-                                                              nb, ((-gs) & 7) << 2);
+                for (int k = 0; k < PER; ++k) {
+                    const int i = ptid + k * PT;
+                    if (i < n_sub) {
+                        long long g;
+                        if (one_contig) {
+                            g = slot_base + rs[k];
+                        } else {
+                            const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
+                            g = b.contig_slot[c] + rs[k] - tile_slot;
                         }
+                        g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
+                        const int gs = (int)g;
+                        int nb = 0;
+                        if (l[k] > 0) {
+                            nb = ((l[k] + 7) >> 3) << 2;
+                            const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
+                            if (cs < ce) {
+                                atomicAdd(st.diff + cs, 1);
+                                atomicAdd(st.diff + ce, -1);
+                            }
+                        }
+                        st.gs[i] = gs;
+                        st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
+                                                          (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
+                                                          ((-gs) & 7) << 2);
                     }
                 }
                 if (ptid < 40) {  // sentinels behind the last read
@@ -192,15 +237,16 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 }
                 producer_sync();  // difference array complete
                 {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
-                    const int w0 = 128 * pw;
+                    const int w0 = (KDL_TILE / W_PRODUCERS) * pw;
                     int pre = 0;
                     for (int k = lane; k < w0; k += 32) pre += st.diff[k];
 #pragma unroll
                     for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
-                    int v[4];
+                    constexpr int E = KDL_TILE / W_PRODUCERS / 32;  // entries per lane
+                    int v[E];
                     int run = 0;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { v[k] = st.diff[w0 + 4 * lane + k]; run += v[k]; }
+                    for (int k = 0; k < E; ++k) { v[k] = st.diff[w0 + E * lane + k]; run += v[k]; }
                     int incl = run;
 #pragma unroll
                     for (int d = 1; d < 32; d <<= 1) {
@@ -209,15 +255,17 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     }
                     int acc = pre + incl - run;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { acc += v[k]; st.cov[w0 + 4 * lane + k] = acc; }
+                    for (int k = 0; k < E; ++k) { acc += v[k]; st.cov[w0 + E * lane + k] = acc; }
                 }
                 producer_sync();  // everybody has read diff: clean it for the stage's next use
-                for (int k = ptid; k < KDL_TILE + 32; k += 32 * W_PRODUCERS) st.diff[k] = 0;
+                for (int k = ptid; k < KDL_TILE + 32; k += PT) st.diff[k] = 0;
                 publish(item);
                 ++item;
                 first = false;
                 c0 = c1;
             }
+            ix = nix;
+            ic = nic;
         }
         {   // END item
             WsStage& st = acquire_stage(item);

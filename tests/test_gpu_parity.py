@@ -367,3 +367,16 @@ def test_very_long_complex_read_among_short_reads(tmp_path):
     _against_oracle(batch)
     aln = K.parse_bam(p)["big"]
     assert aln.insertions[long_pos + 100_000] == {long_seq[100_000:100_010]: 1}
+
+
+def test_warp_specialised_variant_matches(monkeypatch):
+    """K1w (KDL_K1F=ws): the producer/consumer pipeline variant of the tile-owner kernel gives the same
+    tables as the oracle on sorted simple, mixed, deep, sparse and multi-contig inputs."""
+    from kindel_b200 import synth
+
+    monkeypatch.setenv("KDL_K1F", "ws")
+    _against_oracle(synth.simple_reads(71, [300_000], 150))
+    _against_oracle(synth.complex_reads(72, 30_000, 400))
+    _against_oracle(synth.simple_reads(73, [4000], 6000))
+    _against_oracle(synth.simple_reads(74, [500_000], 0.5))
+    _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))

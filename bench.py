@@ -236,7 +236,10 @@ def run_native(args):
             engine.pileup(db, check=False, table=table)
             if timers:
                 timers[1].record()
-            return engine.vote(counts, 1, out=calls_buf)
+            out = engine.vote(counts, 1, out=calls_buf)
+            if timers and len(timers) > 2:
+                timers[2].record()
+            return out
     else:
         from kindel_b200 import distributed
 
@@ -254,7 +257,7 @@ def run_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k1_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.kdl_launch_count()
     torch.cuda.synchronize()
@@ -267,7 +270,8 @@ def run_native(args):
     if world > 1:
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
-    k1_ms = statistics.mean(a.elapsed_time(b) for a, b in k1_ev)
+    k1_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in k1_ev)
+    k2_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in k1_ev) if world == 1 else None
     t = torch.tensor([ms_total, k1_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -336,6 +340,8 @@ def run_native(args):
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, world),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms_max},
+            "kernels_ms": {"k0_k1_pileup": k1_ms_max, "k2_vote": k2_ms,
+                           "k2_vote_gbs": (k2_bytes / (k2_ms * 1e-3) / 1e9) if k2_ms else None},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:

@@ -245,12 +245,13 @@ int kdl_ctx_last_timing(kdl_ctx* ctx, float* h2d_ms, float* kernel_ms, float* d2
  *   kdl_bam_count: per_contig[n_ref][4] int64 = records seen, kept (mapped and l_seq > 1), CIGAR
  *                  ops kept, packed-SEQ 4-byte words kept; first_seen[n_ref] = rank or -1;
  *                  totals[4] = records, kept, contigs seen, bytes consumed.
- *   kdl_bam_fill : cursors[n_ref][3] int64 = next read / op / seq-word index per contig. */
+ *   kdl_bam_fill : cursors[n_ref][3] int64 = next read / op / seq-word index per contig;
+ *                  exotic[n_kept] (may be NULL) = 1 if the read holds a base outside A,C,G,T,N. */
 int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
                   int64_t* per_contig, int32_t* first_seen, int64_t* totals);
 int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
                  int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
-                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4);
+                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4, uint8_t* exotic);
 
 #ifdef __cplusplus
 }

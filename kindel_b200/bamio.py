@@ -130,7 +130,7 @@ def layout_slots(contig_len: np.ndarray):
 
 
 def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_seq, cig_off, cigar, seq4,
-             n_records=0) -> ReadBatch:
+             n_records=0, exotic=None) -> ReadBatch:
     """Classify reads (simple / complex), list the complex ones with their insertion-event offsets,
     detect coordinate order.  All vectorised numpy; shared by the BAM, SAM and synthetic paths."""
     contig_len = np.ascontiguousarray(contig_len, dtype=np.int32)
@@ -156,7 +156,8 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
     start = ref_start.astype(np.int64)
     simple = (n_cig == 1) & is_m & (oplen == lseq) & (start >= 0) & (start + oplen <= read_L)
     simple &= oplen <= _ffi.KDL_FAST_MAXLEN
-    simple &= ~_reads_with_exotic_bases(seq4, seq_off, lseq)
+    # reads with a base outside A,C,G,T,N (flagged by the C++ gather for BAM input, else found here)
+    simple &= ~(np.asarray(exotic, dtype=bool) if exotic is not None else _reads_with_exotic_bases(seq4, seq_off, lseq))
     l_out = np.where(simple, oplen, lseq | _ffi.KDL_COMPLEX).astype(np.uint32).view(np.int32)
 
     complex_idx = np.flatnonzero(~simple).astype(np.uint32)
@@ -239,7 +240,7 @@ def inflate_bam(path) -> np.ndarray:
             out[offs[k]:offs[k + 1]] = np.frombuffer(zlib.decompress(mv[s:e], -15), dtype=np.uint8)
 
     if len(blocks) > 8:
-        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as pool:
             list(pool.map(work, range(len(blocks)), chunksize=16))
     else:
         for k in range(len(blocks)):
@@ -321,15 +322,16 @@ def read_bam(path) -> ReadBatch:
     cig_off = np.empty(n + 1, dtype=np.uint32)
     cigar = np.empty(max(n_ops, 1), dtype=np.uint32)[:n_ops]
     seq4 = np.zeros(max(n_words, 1), dtype=np.uint32)[:n_words]
+    exotic = np.zeros(max(n, 1), dtype=np.uint8)[:n]
     rc = lib.kdl_bam_fill(ptr, buf.size, off, n_ref, cursors.ctypes.data, ref_start.ctypes.data,
                           seq_off.ctypes.data, l_seq.ctypes.data, cig_off.ctypes.data, cigar.ctypes.data,
-                          seq4.ctypes.data)
+                          seq4.ctypes.data, exotic.ctypes.data)
     if rc != 0:
         raise ValueError("malformed BAM record stream in %s" % path)
     cig_off[n] = n_ops
     names = [bin_names[i] for i in order]
     return finalize(names, ref_len[order], read_off, ref_start, seq_off, l_seq, cig_off, cigar, seq4,
-                    n_records=int(totals[0]))
+                    n_records=int(totals[0]), exotic=exotic)
 
 
 # ---------------------------------------------------------------------------------------- SAM

@@ -102,7 +102,7 @@ int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int
 // cigar [total ops], seq4 [total words] uint32.
 int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
                  int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
-                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4) {
+                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4, uint8_t* exotic) {
     if (!bam || !cursors) return KDL_ERR_INVALID_ARG;
     int64_t off = first_record;
     RecView r;
@@ -126,14 +126,26 @@ int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int3
         // per 32-bit word with the first base in the most significant nibble: a byte-swapped copy.
         const int64_t n_bytes_seq = ((int64_t)r.l_seq + 1) / 2;
         const int64_t n_words_seq = ((int64_t)r.l_seq + 7) / 8;
+        uint32_t bad = 0;
         for (int64_t k = 0; k < n_words_seq; ++k) {
             uint8_t b[4] = {0, 0, 0, 0};
             const int64_t left = n_bytes_seq - 4 * k;
             std::memcpy(b, r.seq + 4 * k, (size_t)(left < 4 ? left : 4));
             uint32_t v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
-            if (k == n_words_seq - 1 && (r.l_seq & 7)) v &= ~(0xFFFFFFFFu >> (4 * (r.l_seq & 7)));
+            uint32_t chk = v;  // nibbles that must each be one of 1,2,4,8 (A,C,G,T) or 15 (N)
+            if (k == n_words_seq - 1 && (r.l_seq & 7)) {
+                const uint32_t pad = 0xFFFFFFFFu >> (4 * (r.l_seq & 7));
+                v &= ~pad;
+                chk = v | (pad & 0x11111111u);  // padding counts as fine
+            }
             seq4[w + k] = v;
+            const uint32_t h = chk | (chk >> 1), pair = chk & (chk >> 1);
+            const uint32_t two_plus = (pair | (pair >> 2) | (h & (h >> 2))) & 0x11111111u;
+            const uint32_t all4 = pair & (pair >> 2) & 0x11111111u;
+            const uint32_t zero = ~(h | (h >> 2)) & 0x11111111u;
+            bad |= (two_plus & ~all4) | zero;
         }
+        if (exotic) exotic[i] = bad ? 1 : 0;
     }
     return KDL_OK;
 }

@@ -188,3 +188,59 @@ def to_records(batch: bamio.ReadBatch):
             nib = bamio.unpack_nibbles(batch.seq4[base:base + (lseq + 7) // 8])[:lseq]
             recs.append((c, int(batch.ref_start[r]), 0, words, "".join(bamio.NIBBLES[x] for x in nib.tolist())))
     return contigs, recs
+
+
+def write_simple_bam(path, batch: bamio.ReadBatch, level: int = 1, threads: int = 8):
+    """Vectorised BAM writer for an all-simple, uniform-read-length batch (the config 2/4/5 shapes):
+    lets tests and tools push 10^5..10^7 synthetic reads through the real decode path quickly."""
+    import struct
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    n = batch.n_reads
+    lens = np.unique(batch.l_seq)
+    if len(batch.complex_idx) or lens.shape[0] != 1:
+        raise ValueError("write_simple_bam needs simple reads of one length")
+    L = int(lens[0])
+    words = (L + 7) // 8
+    n_seq = (L + 1) // 2
+    name = b"r\x00"
+    rec_len = 32 + len(name) + 4 + n_seq + L
+    rec = np.zeros((n, 4 + rec_len), dtype=np.uint8)
+
+    def put(col, values, dtype):
+        v = np.ascontiguousarray(values, dtype=dtype).view(np.uint8).reshape(n, -1)
+        rec[:, col:col + v.shape[1]] = v
+
+    ref_id = np.repeat(np.arange(batch.n_contigs, dtype=np.int32), np.diff(batch.contig_read_off))
+    put(0, np.full(n, rec_len), "<i4")
+    put(4, ref_id, "<i4")
+    put(8, batch.ref_start, "<i4")
+    rec[:, 12] = len(name)
+    rec[:, 13] = 60
+    put(14, np.full(n, 4680), "<u2")
+    put(16, np.ones(n), "<u2")            # n_cigar_op
+    put(18, np.zeros(n), "<u2")           # flag
+    put(20, np.full(n, L), "<i4")
+    put(24, np.full(n, -1), "<i4")
+    put(28, np.full(n, -1), "<i4")
+    put(32, np.zeros(n), "<i4")
+    rec[:, 36:36 + len(name)] = np.frombuffer(name, dtype=np.uint8)
+    put(36 + len(name), np.full(n, L << 4), "<u4")
+    seq_be = batch.seq4.reshape(n, words).astype(">u4").view(np.uint8).reshape(n, words * 4)[:, :n_seq]
+    rec[:, 40 + len(name):40 + len(name) + n_seq] = seq_be
+    rec[:, 40 + len(name) + n_seq:] = 0xFF
+    header_text = ("@HD\tVN:1.6\tSO:coordinate\n" + "".join(
+        "@SQ\tSN:%s\tLN:%d\n" % (nm, ln) for nm, ln in zip(batch.contig_names, batch.contig_len))).encode()
+    head = bytearray(b"BAM\x01" + struct.pack("<i", len(header_text)) + header_text + struct.pack("<i", batch.n_contigs))
+    for nm, ln in zip(batch.contig_names, batch.contig_len):
+        nb = nm.encode() + b"\x00"
+        head += struct.pack("<i", len(nb)) + nb + struct.pack("<i", int(ln))
+    body = bytes(head) + rec.tobytes()
+    chunks = [body[s:s + 65280] for s in range(0, len(body), 65280)]
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        blocks = list(pool.map(lambda c: bamio._bgzf_block(c, level), chunks, chunksize=32))
+    with open(path, "wb") as fh:
+        for blk in blocks:
+            fh.write(blk)
+        fh.write(bamio._bgzf_block(b"", level))

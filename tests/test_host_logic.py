@@ -167,3 +167,26 @@ def test_bam_writer_reader_roundtrip(tmp_path):
     c1, e1 = coracle.pileup(back)
     np.testing.assert_array_equal(c0, c1)
     np.testing.assert_array_equal(e0, e1)
+
+
+def test_bam_gather_flags_exotic_bases(tmp_path):
+    """The C++ gather marks reads holding a base outside A,C,G,T,N; they become complex reads, so the
+    fast kernel never sees them and the general walk reproduces the reference's KeyError semantics."""
+    recs = [(0, 3, 0, [6 << 4], "ACGTNA"), (0, 4, 0, [6 << 4], "ACRTAC"), (0, 5, 0, [5 << 4], "ACG=A"),
+            (0, 6, 0, [9 << 4], "ACGTACGTN"), (0, 7, 0, [(2 << 4), (2 << 4) | 1, (2 << 4)], "ACYRGT")]
+    p = tmp_path / "x.bam"
+    bamio.write_bam(p, [("c", 40)], recs)
+    b = bamio.read_alignment(p)
+    assert b.n_reads == 5
+    assert (b.l_seq < 0).tolist() == [False, True, True, False, True]   # R, '=' -> complex; indel read too
+    with pytest.raises(KeyError) as exc:
+        coracle.pileup(b)
+    assert exc.value.args == ("R",)
+    # the same reads through SAM text classify identically (numpy check instead of the C++ one)
+    sam = tmp_path / "x.sam"
+    sam.write_text("@SQ\tSN:c\tLN:40\n" + "".join(
+        "r%d\t0\tc\t%d\t60\t%s\t*\t0\t0\t%s\t*\n" % (k, r[1] + 1, "".join("%d%s" % (w >> 4, "MIDNSHP=X"[w & 15]) for w in r[3]), r[4])
+        for k, r in enumerate(recs)))
+    b2 = bamio.read_alignment(sam)
+    np.testing.assert_array_equal(b2.l_seq, b.l_seq)
+    np.testing.assert_array_equal(b2.seq4, b.seq4)

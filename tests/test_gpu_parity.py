@@ -380,3 +380,28 @@ def test_warp_specialised_variant_matches(monkeypatch):
     _against_oracle(synth.simple_reads(73, [4000], 6000))
     _against_oracle(synth.simple_reads(74, [500_000], 0.5))
     _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
+
+
+def test_big_bam_file_end_to_end(tmp_path):
+    """A 200k-read coordinate-sorted BAM through the whole public path (BGZF inflate, C++ gather, flatten,
+    K0/K1f/K2, host assembly): FASTA and changes equal what the oracle's tables give."""
+    from kindel_b200 import bamio, synth
+    from kindel_b200 import kindel as K
+    from oracle import coracle
+
+    b = synth.simple_reads(81, [250_000, 50_000], 100)
+    path = tmp_path / "big.bam"
+    synth.write_simple_bam(path, b)
+    back = bamio.read_alignment(path)
+    np.testing.assert_array_equal(back.seq4, b.seq4)
+    np.testing.assert_array_equal(back.ref_start, b.ref_start)
+    res = K.bam_to_consensus(path, min_depth=3)
+    oc, _ = coracle.pileup(b)
+    calls = coracle.vote(oc, 3)
+    for c, name in enumerate(b.contig_names):
+        s0, L = int(b.contig_slot[c]), int(b.contig_len[c])
+        want_seq, want_changes = K.assemble_consensus(calls[s0:s0 + L], lambda p: ("", False))
+        assert res.consensuses[c].name == name + "_cns"
+        assert res.consensuses[c].sequence == want_seq
+        assert res.refs_changes[name] == want_changes
+        assert "min, max observed depth" in res.refs_reports[name]

@@ -405,3 +405,74 @@ def test_big_bam_file_end_to_end(tmp_path):
         assert res.consensuses[c].sequence == want_seq
         assert res.refs_changes[name] == want_changes
         assert "min, max observed depth" in res.refs_reports[name]
+
+
+def test_exchange_protocol_emulated_on_one_gpu():
+    """The multi-GPU exchange kernels (K2x vote over footprint-clipped peer tables, K2g pull of the call
+    slices, flag protocol; also K2p) driven for 3 emulated ranks inside ONE process on one GPU: the
+    "peer" blocks are ordinary allocations of the same device, and the ranks' kernels are issued in an
+    order that never has to spin.  Result of every rank == one-GPU oracle."""
+    import ctypes as C
+
+    import torch
+
+    from kindel_b200 import _ffi
+    from kindel_b200 import distributed as D
+    from kindel_b200 import engine, synth
+    from oracle import coracle
+
+    lib = _ffi.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = int(torch.cuda.current_stream(dev).cuda_stream)
+    world = 3
+    for full in (synth.simple_reads(91, [120_000], 80), synth.complex_reads(92, 25_000, 200),
+                 synth.simple_reads(93, [30_000, 50_000, 9_000], 40)):
+        S = full.n_slots
+        oc, _ = coracle.pileup(full)
+        want = coracle.vote(oc, 2)
+        table_bytes, calls_off, flags_off = 19 * S * 4, 19 * S * 4, 19 * S * 4 + S
+        blocks = [torch.zeros(flags_off + 256, dtype=torch.uint8, device=dev) for _ in range(world)]
+        shards = [D.shard_batch(full, r, world) for r in range(world)]
+        feet = [D.footprint(s) for s in shards]
+        slices = D.owner_slices(S, world)
+        xs = []
+        for r in range(world):
+            x = _ffi.KdlExchange()
+            x.n_ranks, x.rank = world, r
+            for p, blk in enumerate(blocks):
+                base = blk.data_ptr()
+                x.tables[p], x.calls[p] = base, base + calls_off
+                x.ready[p], x.done[p] = base + flags_off, base + flags_off + 64
+                x.foot_lo[p], x.foot_hi[p] = feet[p]
+                x.slice_lo[p], x.slice_hi[p] = slices[p]
+            x.counter = blocks[r].data_ptr() + flags_off + 128
+            xs.append(x)
+        tables = [blk[:table_bytes].view(torch.int32).view(19, S) for blk in blocks]
+        for epoch in (1, 2):  # two steps: the second reuses the tables (lazy zeroing) and the flags
+            for r in range(world):
+                tab = engine.CountTable(S, dev, tensor=tables[r])
+                if epoch == 2:
+                    tab.dirty, tab.dirty_rest = feet[r], len(shards[r].complex_idx) > 0
+                    tab.dirty = engine._tile_align(*feet[r], S)
+                engine.pileup(engine.upload(shards[r], dev), check=False, table=tab, slot_range=feet[r])
+            for r in range(world):
+                _ffi.check(lib.kdl_exchange_signal(C.byref(xs[r]), epoch, st), "signal")
+            for r in range(world):
+                _ffi.check(lib.kdl_exchange_vote(C.byref(xs[r]), S, 2, epoch, st), "vote")
+            for r in range(world):
+                _ffi.check(lib.kdl_exchange_wait(C.byref(xs[r]), epoch, st), "wait")
+            torch.cuda.synchronize()
+            for r in range(world):
+                got = blocks[r][calls_off:calls_off + S].cpu().numpy()
+                np.testing.assert_array_equal(got, want, err_msg="rank %d epoch %d" % (r, epoch))
+        # K2p: the same reduction + vote through kdl_vote_peers_sparse (used with NCCL barrier/all_gather)
+        ptrs = (C.c_void_p * world)(*[blk.data_ptr() for blk in blocks])
+        flo = (C.c_int64 * world)(*[f[0] for f in feet])
+        fhi = (C.c_int64 * world)(*[f[1] for f in feet])
+        calls = torch.zeros(S, dtype=torch.uint8, device=dev)
+        reduced = torch.zeros((7, S), dtype=torch.int32, device=dev)
+        _ffi.check(lib.kdl_vote_peers_sparse(ptrs, flo, fhi, world, S, 0, S, 2, calls.data_ptr(), reduced.data_ptr(), st),
+                   "vote_peers")
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(calls.cpu().numpy(), want)
+        np.testing.assert_array_equal(reduced.cpu().numpy(), oc[:7])

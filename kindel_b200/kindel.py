@@ -393,10 +393,15 @@ def merge_cdrps(cdrps, min_overlap):
 
 
 # -------------------------------------------------------------------------------------- report
+DepthRange = namedtuple("DepthRange", ["dmin", "dmax"])  # min / max ACGT depth of a contig (kindel.py:450,477-479)
+
+
 def build_report(ref_id, weights, changes, cdr_patches, bam_path, realign, min_depth, min_overlap,
                  clip_decay_threshold, trim_ends, uppercase):
     """REPORT text block (reference kindel/kindel.py:437-485)."""
-    if isinstance(weights, BaseCounts):
+    if isinstance(weights, DepthRange):  # already reduced on the device: no table copy needed
+        dmin, dmax = weights.dmin, weights.dmax
+    elif isinstance(weights, BaseCounts):
         acgt = weights.cols[0:4].sum(axis=0)
         dmin, dmax = (int(acgt.min()), int(acgt.max()))
     else:
@@ -447,8 +452,15 @@ def consensus_from_run(run, calls_all, bam_path, realign=False, min_depth=1, min
     ins_table = run.ins_table
     consensuses, refs_changes, refs_reports = [], {}, {}
     for c, ref_id in enumerate(run.batch.contig_names):
-        aln = run.alignment(c)
         s, e = run.contig_slice(c)
+        if realign or run.counts is None:
+            aln = run.alignment(c)  # host copy of the table: the CDR code walks it
+            report_weights = aln.weights
+        else:
+            # plain consensus needs only the call bytes, the insertion events and, for the report, the
+            # min / max ACGT depth -- reduced on the device instead of copying 76 B per position back
+            d = run.counts[0:4, s:e - 1].sum(dim=0)
+            report_weights = DepthRange(int(d.min().item()), int(d.max().item())) if e - 1 > s else DepthRange(0, 0)
         if realign:
             cdrps = cdrp_consensuses(aln.weights, aln.deletions, aln.clip_start_weights, aln.clip_end_weights,
                                      aln.clip_start_depth, aln.clip_end_depth, clip_decay_threshold, mask_ends)
@@ -457,7 +469,7 @@ def consensus_from_run(run, calls_all, bam_path, realign=False, min_depth=1, min
             cdr_patches = None
         cons, changes = assemble_consensus(calls_all[s:e - 1], lambda p, s=s: ins_table.consensus_at(s + p),
                                            cdr_patches, trim_ends, uppercase)
-        report = build_report(ref_id, aln.weights, changes, cdr_patches, bam_path, realign, min_depth,
+        report = build_report(ref_id, report_weights, changes, cdr_patches, bam_path, realign, min_depth,
                               min_overlap, clip_decay_threshold, trim_ends, uppercase)
         consensuses.append(consensus_seqrecord(cons, ref_id))
         refs_reports[ref_id] = report

@@ -64,6 +64,9 @@ def test_golden_files_full_api(manifest, golden_npz):
             assert [[r.name, r.sequence] for r in res.consensuses] == want["fasta"], (name, tag)
             for ctg, ch in res.refs_changes.items():
                 assert "".join("-" if c is None else c for c in ch) == want["changes"][ctg]
+            for ctg, rep in res.refs_reports.items():  # incl. min/max depth reduced on the device
+                exp = [l for l in want["reports"][ctg].splitlines() if not l.startswith("- bam_path")]
+                assert [l for l in rep.splitlines() if not l.startswith("- bam_path")] == exp, (name, tag)
         assert_frame_matches(K.weights(path), g, "w_")
         assert_frame_matches(K.weights(path, True, True, 0.05), g, "wrel_")
         if entry["features_error"]:

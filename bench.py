@@ -10,8 +10,9 @@ A "step" is one pass of the hot path over one batch: zero the count table, K1 pi
 
 Workload (config.workload): BASELINE.json configs[3], the one the north star's targets are quoted
 on -- synthetic 5 Mb contig, 200x, 150 bp `150M` reads, coordinate-sorted, 1 % substitutions
-(6.67 M reads, 10^9 aligned bases).  For N > 1 the same data set is sharded by read blocks (strong
-scaling: total work fixed).
+(6.67 M reads, 10^9 aligned bases).  For N > 1 every rank gets that full per-GPU workload on its own 1/N
+slice of the coordinate range (weak scaling: a coordinate-sorted, N x deeper alignment cut into N contiguous read
+blocks); `--scaling strong` cuts the N = 1 data set N ways instead.
 
 Numbers on the JSON line:
   value      whole-job aligned bases/s with the flattened reads already resident in HBM
@@ -51,13 +52,24 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, rank=0, world=1):
-    """The rank's shard of the workload: a contiguous block of the coordinate-sorted reads."""
+def make_workload(name, rank=0, world=1, scaling="weak"):
+    """This rank's reads and the whole job's aligned bases.
+
+    weak   (default): every rank gets the full per-GPU workload -- `depth` x the contig lengths worth of
+           reads -- placed on its own 1/N slice of the coordinate range (a coordinate-sorted N x deeper
+           BAM cut into N contiguous blocks): per-GPU work is fixed as N grows.
+    strong: the N = 1 data set cut into N contiguous read blocks: total work fixed."""
     from kindel_b200 import distributed, synth
 
     lens, depth = WORKLOADS[name]
-    full = synth.simple_reads(4, lens, depth)
-    return distributed.shard_batch(full, rank, world), full.aligned_bases
+    if world == 1:
+        full = synth.simple_reads(4, lens, depth)
+        return full, full.aligned_bases
+    if scaling == "strong":
+        full = synth.simple_reads(4, lens, depth)
+        return distributed.shard_batch(full, rank, world), full.aligned_bases
+    shard = synth.simple_reads(4, lens, depth, start_frac=(rank / world, (rank + 1) / world), read_seed=[4, rank])
+    return shard, shard.aligned_bases * world  # every rank holds the same number of equally long reads
 
 
 def algorithmic_bytes(batch):
@@ -190,7 +202,7 @@ def run_reference(args):
     native = cpu_native_sample(batch)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": args.workload, "note": "reference is single-threaded CPython (kindel/kindel.py:1-14)"},
         "cpu_baseline": dict(best, value=v),
@@ -220,7 +232,7 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _ffi.load()
 
-    batch, total_bases = make_workload(args.workload, rank, world)
+    batch, total_bases = make_workload(args.workload, rank, world, args.scaling)
     n_slots = batch.n_slots
     k1_bytes, k2_bytes = algorithmic_bytes(batch)
     if world == 1:
@@ -324,11 +336,13 @@ def run_native(args):
         achieved = k1_bytes / (k1_ms_max * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "int32", "data": "synthetic",
-            "config": {"workload": args.workload, "reads_per_rank": int(batch.n_reads),
+            "config": {"workload": args.workload if world == 1 or args.scaling == "strong" else
+                       "%s per GPU (%dx the depth in total, cut into %d coordinate blocks)" % (args.workload, world, world),
+                       "reads_per_rank": int(batch.n_reads),
                        "aligned_bases_total": int(total_bases),
-                       "sharding": "contiguous blocks of the coordinate-sorted reads" if world > 1 else "none",
+                       "sharding": "contiguous blocks of the coordinate-sorted reads, one per rank" if world > 1 else "none",
                        "reduction": ("none" if world == 1 else
                                      "K2x: flags + reduce + vote + call scatter in one kernel over CUDA-IPC peer memory "
                                      "(NVLink), footprint-clipped; no NCCL on the data path" if args.exchange == "fused" else
@@ -361,6 +375,9 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4_5Mb_200x")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
+                    help="N > 1: weak = the full per-GPU workload on every rank (N x deeper in total); "
+                         "strong = the N = 1 data set cut N ways")
     ap.add_argument("--exchange", choices=["fused", "peer", "allreduce"], default="fused",
                     help="N > 1: fused = flags + reduce + vote + call scatter over NVLink peer memory (no NCCL on "
                          "the data path); peer = same kernel with NCCL barrier/all_gather; allreduce = NCCL "

@@ -30,9 +30,14 @@ def _pack_rows(nib: np.ndarray) -> np.ndarray:
 
 
 def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_rate: float = 0.01,
-                 chunk: int = 1 << 18) -> bamio.ReadBatch:
-    """`read_len`M reads, uniformly placed, sorted by start inside each contig."""
+                 chunk: int = 1 << 18, start_frac=None, read_seed=None) -> bamio.ReadBatch:
+    """`read_len`M reads, uniformly placed, sorted by start inside each contig.
+
+    start_frac=(f0, f1) places the (same number of) reads only in that fraction of every contig's
+    start range -- a weak-scaling shard: rank r of N uses (r/N, (r+1)/N) and a read_seed of its own
+    while `seed` (the contigs' bases) stays common, so the ranks pile N x deeper on disjoint slices."""
     rng = np.random.default_rng(seed)
+    rrng = rng if read_seed is None else np.random.default_rng(read_seed)
     contig_lens = [int(x) for x in contig_lens]
     words = (read_len + 7) // 8
     ref_start_all, seq_rows, read_off = [], [], [0]
@@ -40,17 +45,20 @@ def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_
         n = int(round(depth * L / read_len))
         ref = random_contig(rng, L)
         ref_pad = np.concatenate([ref, np.zeros(words * 8, dtype=np.uint8)])
-        starts = np.sort(rng.integers(0, L - read_len + 1, size=n, dtype=np.int64))
+        span = L - read_len + 1
+        s_lo, s_hi = (0, span) if start_frac is None else (int(span * start_frac[0]), max(int(span * start_frac[1]),
+                                                                                         int(span * start_frac[0]) + 1))
+        starts = np.sort(rrng.integers(s_lo, s_hi, size=n, dtype=np.int64))
         for s0 in range(0, n, chunk):
             st = starts[s0:s0 + chunk]
             idx = st[:, None] + np.arange(words * 8, dtype=np.int64)[None, :]
             nib = ref_pad[idx]
             nib[:, read_len:] = 0
             if sub_rate > 0:
-                n_sub = rng.binomial(st.shape[0] * read_len, sub_rate)
-                rr = rng.integers(0, st.shape[0], size=n_sub)
-                cc = rng.integers(0, read_len, size=n_sub)
-                nib[rr, cc] = _CODE[rng.integers(0, 5, size=n_sub)]
+                n_sub = rrng.binomial(st.shape[0] * read_len, sub_rate)
+                rr = rrng.integers(0, st.shape[0], size=n_sub)
+                cc = rrng.integers(0, read_len, size=n_sub)
+                nib[rr, cc] = _CODE[rrng.integers(0, 5, size=n_sub)]
             seq_rows.append(_pack_rows(nib))
         ref_start_all.append(starts)
         read_off.append(read_off[-1] + n)

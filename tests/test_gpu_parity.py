@@ -320,22 +320,23 @@ def test_cli_end_to_end(manifest, tmp_path):
     import sys
 
     env = dict(os.environ, PYTHONPATH=H.ROOT)
-    for name in ("mm2_multi", "ext_3_bc75", "mm2_gp120"):
+    # one fresh interpreter per command (each pays a torch import): three cover plain / realign / options
+    for name, tag, extra in (("mm2_multi", "plain", []), ("ext_3_bc75", "realign", ["-r"]),
+                             ("mm2_gp120", "opts", ["--min-depth", "5", "-t", "-u"])):
         entry = manifest["files"][name]
         path = golden_input(entry)
-        for tag, extra in (("plain", []), ("realign", ["-r"]), ("opts", ["--min-depth", "5", "-t", "-u"])):
-            res = subprocess.run([sys.executable, "-m", "kindel", "consensus", *extra, path], capture_output=True,
-                                 text=True, env=env, timeout=300)
-            assert res.returncode == 0, res.stderr[-2000:]
-            lines = res.stdout.strip().split("\n")
-            got = [[lines[i][1:], lines[i + 1] if i + 1 < len(lines) else ""] for i in range(0, len(lines), 2)]
-            assert got == entry["runs"][tag]["fasta"], (name, tag)
-            assert "========================= REPORT ===========================" in res.stderr
+        res = subprocess.run([sys.executable, "-m", "kindel", "consensus", *extra, path], capture_output=True,
+                             text=True, env=env, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        lines = res.stdout.strip().split("\n")
+        got = [[lines[i][1:], lines[i + 1] if i + 1 < len(lines) else ""] for i in range(0, len(lines), 2)]
+        assert got == entry["runs"][tag]["fasta"], (name, tag)
+        assert "========================= REPORT ===========================" in res.stderr
     res = subprocess.run([sys.executable, "-m", "kindel", "version"], capture_output=True, text=True, env=env)
     assert res.stdout.strip() == "kindel 1.2.1"
     entry = manifest["files"]["ext_3_bc75"]
     res = subprocess.run([sys.executable, "-m", "kindel", "weights", golden_input(entry)], capture_output=True,
-                         text=True, env=env, timeout=300)
+                         text=True, env=env, timeout=600)
     assert res.returncode == 0
     header = res.stdout.split("\n", 1)[0].split("\t")
     assert header == ["chrom", "pos", "A", "C", "G", "T", "N", "insertions", "deletions", "clip_starts", "clip_ends",

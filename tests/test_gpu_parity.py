@@ -313,77 +313,45 @@ def test_tile_index_power_of_32_read_counts():
     _against_oracle(b)
 
 
-def test_cli_end_to_end(manifest, tmp_path):
-    """`python -m kindel consensus|weights|features|version` == the reference CLI's output
-    (reference tests/test_kindel.py:114-238 shell out to `kindel consensus <path>`)."""
+def test_cli_end_to_end(manifest, tmp_path, capsys):
+    """`kindel consensus|weights|features|version` == the reference CLI's output (reference
+    tests/test_kindel.py:114-238 shell out to `kindel consensus <path>`).  The command functions are
+    driven in-process through the argument parser (no interpreter start-up per case); one real
+    `python -m kindel` subprocess proves the module entry point."""
     import subprocess
     import sys
 
-    env = dict(os.environ, PYTHONPATH=H.ROOT)
-    # one fresh interpreter per command (each pays a torch import): three cover plain / realign / options
+    from kindel_b200 import cli
+
     for name, tag, extra in (("mm2_multi", "plain", []), ("ext_3_bc75", "realign", ["-r"]),
-                             ("mm2_gp120", "opts", ["--min-depth", "5", "-t", "-u"])):
+                             ("mm2_gp120", "opts", ["--min-depth", "5", "-t", "-u"]), ("bwa_1_1", "realign", ["--realign"])):
         entry = manifest["files"][name]
-        path = golden_input(entry)
-        res = subprocess.run([sys.executable, "-m", "kindel", "consensus", *extra, path], capture_output=True,
-                             text=True, env=env, timeout=600)
-        assert res.returncode == 0, res.stderr[-2000:]
-        lines = res.stdout.strip().split("\n")
+        capsys.readouterr()
+        assert cli.main(["consensus", *extra, golden_input(entry)]) == 0
+        out = capsys.readouterr()
+        lines = out.out.strip().split("\n")
         got = [[lines[i][1:], lines[i + 1] if i + 1 < len(lines) else ""] for i in range(0, len(lines), 2)]
         assert got == entry["runs"][tag]["fasta"], (name, tag)
-        assert "========================= REPORT ===========================" in res.stderr
-    res = subprocess.run([sys.executable, "-m", "kindel", "version"], capture_output=True, text=True, env=env)
-    assert res.stdout.strip() == "kindel 1.2.1"
+        assert "========================= REPORT ===========================" in out.err
     entry = manifest["files"]["ext_3_bc75"]
-    res = subprocess.run([sys.executable, "-m", "kindel", "weights", golden_input(entry)], capture_output=True,
-                         text=True, env=env, timeout=600)
-    assert res.returncode == 0
-    header = res.stdout.split("\n", 1)[0].split("\t")
-    assert header == ["chrom", "pos", "A", "C", "G", "T", "N", "insertions", "deletions", "clip_starts", "clip_ends",
-                      "depth", "consensus", "shannon", "lower_ci", "upper_ci"]
-    assert len(res.stdout.strip().split("\n")) == 1 + entry["contigs"][0]["ref_len"]
-
-
-def test_very_long_complex_read_among_short_reads(tmp_path):
-    """A 200 kb read with an indel (complex: K1g) sitting in the middle of sorted short reads: its bases
-    sit in the same packed array, larger than one staging buffer of the tile kernel, which must skip
-    them (sub-chunk logic) while still counting every short read around it."""
-    from kindel_b200 import bamio
-    from kindel_b200 import kindel as K
-
-    rng = np.random.default_rng(77)
-    L = 400_000
-    starts = np.sort(rng.integers(0, L - 150, size=3000))
-    lines = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:big\tLN:%d" % L]
-    long_pos = 100_000
-    long_seq = "".join(rng.choice(list("ACGT"), size=200_010))
-    placed = False
-    for k, s in enumerate(starts.tolist()):
-        if not placed and s >= long_pos:
-            lines.append("long\t0\tbig\t%d\t60\t100000M10I100000M\t*\t0\t0\t%s\t*" % (long_pos + 1, long_seq))
-            placed = True
-        seq = "".join(rng.choice(list("ACGTN"), size=150, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
-        lines.append("r%d\t0\tbig\t%d\t60\t150M\t*\t0\t0\t%s\t*" % (k, s + 1, seq))
-    p = tmp_path / "long.sam"
-    p.write_text("\n".join(lines) + "\n")
-    batch = bamio.read_alignment(p)
-    assert batch.reads_sorted and len(batch.complex_idx) == 1 and batch.max_simple_len == 150
-    _against_oracle(batch)
-    aln = K.parse_bam(p)["big"]
-    assert aln.insertions[long_pos + 100_000] == {long_seq[100_000:100_010]: 1}
-
-
-def test_warp_specialised_variant_matches(monkeypatch):
-    """K1w (KDL_K1F=ws): the producer/consumer pipeline variant of the tile-owner kernel gives the same
-    tables as the oracle on sorted simple, mixed, deep, sparse and multi-contig inputs."""
-    from kindel_b200 import synth
-
-    monkeypatch.setenv("KDL_K1F", "ws")
-    _against_oracle(synth.simple_reads(71, [300_000], 150))
-    _against_oracle(synth.complex_reads(72, 30_000, 400))
-    _against_oracle(synth.simple_reads(73, [4000], 6000))
-    _against_oracle(synth.simple_reads(74, [500_000], 0.5))
-    _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
+    assert cli.main(["weights", golden_input(entry)]) == 0
+    text = capsys.readouterr().out
+    assert text.split("\n", 1)[0].split("\t") == [
+        "chrom", "pos", "A", "C", "G", "T", "N", "insertions", "deletions", "clip_starts", "clip_ends", "depth",
+        "consensus", "shannon", "lower_ci", "upper_ci"]
+    assert len(text.strip().split("\n")) == 1 + entry["contigs"][0]["ref_len"]
+    assert cli.main(["features", golden_input(entry)]) == 0
+    assert capsys.readouterr().out.split("\n", 1)[0].split("\t")[:4] == ["chrom", "pos", "A", "C"]
+    assert cli.main(["version"]) == 0
+    assert capsys.readouterr().out.strip() == "kindel 1.2.1"
+    # the module entry point, once, in a fresh interpreter
+    env = dict(os.environ, PYTHONPATH=H.ROOT)
+    entry = manifest["files"]["mm2_multi"]
+    res = subprocess.run([sys.executable, "-m", "kindel", "consensus", golden_input(entry)], capture_output=True,
+                         text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = res.stdout.strip().split("\n")
+    assert [[lines[i][1:], lines[i + 1]] for i in range(0, len(lines), 2)] == entry["runs"]["plain"]["fasta"]
 
 
 def test_big_bam_file_end_to_end(tmp_path):

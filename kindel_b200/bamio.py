@@ -23,7 +23,6 @@ The result is a `ReadBatch` (numpy arrays in host memory) described in include/k
 """
 from __future__ import annotations
 
-import ctypes as C
 import gzip
 import os
 import struct

@@ -100,10 +100,6 @@ def upload(host: ReadBatch, device=None, non_blocking: bool = False) -> DeviceBa
     return DeviceBatch(host=host, device=device, tensors=tensors, struct=make_struct(host, ptr))
 
 
-class DataError(Exception):
-    """Carrier for the exception the reference raises on malformed input."""
-
-
 def raise_like_reference(status: int, read: int, nibble: int, op_index: int):
     if status == _ffi.KDL_ERR_KEY:
         raise KeyError(NIBBLES[nibble])  # e.g. KeyError('R'): kindel.py:52,72,79

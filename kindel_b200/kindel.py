@@ -15,7 +15,6 @@ There is no CPU implementation of the pileup or the vote in this package.
 from __future__ import annotations
 
 import logging
-import math
 import os
 from collections import OrderedDict, namedtuple
 

@@ -202,7 +202,6 @@ def write_simple_bam(path, batch: bamio.ReadBatch, level: int = 1, threads: int 
     """Vectorised BAM writer for an all-simple, uniform-read-length batch (the config 2/4/5 shapes):
     lets tests and tools push 10^5..10^7 synthetic reads through the real decode path quickly."""
     import struct
-    import zlib
     from concurrent.futures import ThreadPoolExecutor
 
     n = batch.n_reads

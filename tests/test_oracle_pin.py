@@ -4,7 +4,6 @@
       fixture of its own test-suite, including the known-answer integers of
       reference tests/test_kindel.py:63-89.
 No GPU involved."""
-import io
 import os
 from collections import OrderedDict
 

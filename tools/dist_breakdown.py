@@ -1,6 +1,5 @@
 """Diagnostic (not a test): per-stage CUDA-event breakdown of the fused multi-GPU step."""
 import ctypes as C
-import math
 import os
 import sys
 import time

@@ -171,3 +171,35 @@ def test_golden_fasta_files_of_the_reference_suite():
                 else:
                     bad.append(os.path.basename(p) + suf)
     assert ok == 21 and bad == ["3.issue23.bc75.sam.realign.fa"]
+
+
+def test_python_port_against_golden(manifest, golden_npz):
+    """oracle/py_oracle.py (the reference-shaped CPython loop timed by `bench.py --impl reference`)
+    reproduces the reference's tables, insertion dicts and consensus on the small golden files."""
+    from oracle import py_oracle
+
+    for name in ("mm2_multi", "ext_3_bc75", "mm2_gp120"):
+        entry = manifest["files"][name]
+        header, records = samdecode.read_alignment_file(golden_input(entry))
+        lens = {sn[3:]: int(next(f for f in fields if f.startswith("LN:"))[3:]) for sn, fields in header["@SQ"].items()}
+        groups = OrderedDict()
+        for r in records:
+            if r.rname != "*":
+                groups.setdefault(r.rname, []).append(py_oracle.Rec(r.pos, r.mapped, r.seq, r.cigars))
+        g = golden_npz(name)
+        assert list(groups) == [c["name"] for c in entry["contigs"]]
+        for c, (ctg, recs) in enumerate(groups.items()):
+            p = py_oracle.pileup(lens[ctg], recs)
+            t = g["c%d_counts" % c]
+            L = lens[ctg]
+            for k, b in enumerate("ACGTN"):
+                assert [w[b] for w in p.weights] == t[k, :L].tolist()
+                assert [w[b] for w in p.clip_start_weights] == t[9 + k, :L].tolist()
+                assert [w[b] for w in p.clip_end_weights] == t[14 + k, :L].tolist()
+            assert p.deletions == t[5].tolist() and p.clip_starts == t[7].tolist() and p.clip_ends == t[8].tolist()
+            assert list(p.consensus_depth) == g["c%d_consensus_depth" % c].tolist()
+            want_ins = {i: [tuple(kv) for kv in items] for i, items in entry["contigs"][c]["insertions"]}
+            assert {i: list(d.items()) for i, d in enumerate(p.insertions) if d} == want_ins
+            seq, changes = py_oracle.vote(p, 1)
+            assert seq == dict(map(tuple, entry["runs"]["plain"]["fasta"]))[ctg + "_cns"]
+            assert "".join("-" if c_ is None else c_ for c_ in changes) == entry["runs"]["plain"]["changes"][ctg]

@@ -1,4 +1,8 @@
-"""Diagnostic (not a test): per-stage CUDA-event breakdown of the fused multi-GPU step."""
+"""Diagnostic (not a test): per-stage CUDA-event breakdown of the fused multi-GPU step.
+
+Default: every iteration starts from a barrier + device sync (stages timed in isolation).
+BACK_TO_BACK=1: no barrier / sync between iterations, like bench.py's timed loop -- the mode in which
+~0.1 ms per step beyond K1 + K2x + K2g is still unaccounted for."""
 import ctypes as C
 import os
 import sys
@@ -22,10 +26,12 @@ lib = _ffi.load()
 names = ["zero", "pileup", "signal", "vote", "wait"]
 acc = {n: 0.0 for n in names}
 wall = 0.0
+evs = []
 for it in range(13):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    dist.barrier()
-    torch.cuda.synchronize()
+    if not os.environ.get("BACK_TO_BACK"):
+        dist.barrier()
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     ev[0].record()
     ev[1].record()
@@ -41,14 +47,22 @@ for it in range(13):
     lib.kdl_exchange_wait(C.byref(sc.xstruct), sc.epoch, st)
     ev[5].record()
     t1 = time.perf_counter()
-    torch.cuda.synchronize()
+    if not os.environ.get("BACK_TO_BACK") or it == 12:
+        torch.cuda.synchronize()
     t2 = time.perf_counter()
-    if it >= 3:
+    evs.append(ev)
+    if it >= 3 and not os.environ.get("BACK_TO_BACK"):
         for k, n in enumerate(names):
             acc[n] += ev[k].elapsed_time(ev[k + 1])
         wall += (t2 - t0) * 1e3
         if it == 12 and rank == 0:
             print("cpu enqueue ms", (t1 - t0) * 1e3)
+if os.environ.get("BACK_TO_BACK"):
+    torch.cuda.synchronize()
+    for ev in evs[3:]:
+        for k, n in enumerate(names):
+            acc[n] += ev[k].elapsed_time(ev[k + 1])
+    wall = evs[3][0].elapsed_time(evs[-1][5])
 for r in range(world):
   dist.barrier()
   if rank == r:

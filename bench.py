@@ -189,6 +189,32 @@ def cpu_native_sample(batch):
             "sample": "oracle/kindel_oracle.c single thread, full workload, %.2f s" % dt}
 
 
+def host_side_timings(batch):
+    """The host work that surrounds the timed spans (reported separately; it stays on the host in
+    both paths): BAM inflate + C++ gather + flatten of a 10^6-read slice of the workload written as a real
+    BGZF-compressed BAM, on this box's cores."""
+    import tempfile
+
+    from kindel_b200 import bamio, synth
+
+    n = min(batch.n_reads, 1_000_000)
+    words = int(batch.seq_off[1] - batch.seq_off[0]) if batch.n_reads > 1 else 19
+    sub = bamio.finalize(batch.contig_names, batch.contig_len, np.array([0, n]), batch.ref_start[:n],
+                         np.arange(n, dtype=np.int64) * words, batch.l_seq[:n], np.arange(n + 1),
+                         np.full(n, int(batch.l_seq[0]) << 4), batch.seq4[: n * words], n_records=n)
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "slice.bam")
+        synth.write_simple_bam(path, sub)
+        size = os.path.getsize(path)
+        t0 = time.perf_counter()
+        back = bamio.read_bam(path)
+        dt = time.perf_counter() - t0
+    assert back.n_reads == n
+    return {"bam_decode_flatten_reads_per_s": n / dt, "bam_decode_flatten_aligned_bases_per_s": back.aligned_bases / dt,
+            "sample": "%d reads, %.0f MB BGZF BAM, inflate (zlib, thread pool) + C++ gather + numpy flatten: %.2f s"
+                      % (n, size / 1e6, dt), "cores": os.cpu_count()}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -361,6 +387,8 @@ def run_native(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_port_sample(batch)
             line["cpu_native_port"] = cpu_native_sample(batch)
+            if len(batch.contig_names) == 1 and len(batch.complex_idx) == 0:
+                line["host"] = host_side_timings(batch)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -354,6 +354,48 @@ def test_cli_end_to_end(manifest, tmp_path, capsys):
     assert [[lines[i][1:], lines[i + 1]] for i in range(0, len(lines), 2)] == entry["runs"]["plain"]["fasta"]
 
 
+def test_very_long_complex_read_among_short_reads(tmp_path):
+    """A 200 kb read with an indel (complex: K1g) sitting in the middle of sorted short reads: its bases
+    sit in the same packed array, larger than one staging buffer of the tile kernel, which must skip
+    them (sub-chunk logic) while still counting every short read around it."""
+    from kindel_b200 import bamio
+    from kindel_b200 import kindel as K
+
+    rng = np.random.default_rng(77)
+    L = 400_000
+    starts = np.sort(rng.integers(0, L - 150, size=3000))
+    lines = ["@HD\tVN:1.6\tSO:coordinate", "@SQ\tSN:big\tLN:%d" % L]
+    long_pos = 100_000
+    long_seq = "".join(rng.choice(list("ACGT"), size=200_010))
+    placed = False
+    for k, s in enumerate(starts.tolist()):
+        if not placed and s >= long_pos:
+            lines.append("long\t0\tbig\t%d\t60\t100000M10I100000M\t*\t0\t0\t%s\t*" % (long_pos + 1, long_seq))
+            placed = True
+        seq = "".join(rng.choice(list("ACGTN"), size=150, p=[0.245, 0.245, 0.245, 0.245, 0.02]))
+        lines.append("r%d\t0\tbig\t%d\t60\t150M\t*\t0\t0\t%s\t*" % (k, s + 1, seq))
+    p = tmp_path / "long.sam"
+    p.write_text("\n".join(lines) + "\n")
+    batch = bamio.read_alignment(p)
+    assert batch.reads_sorted and len(batch.complex_idx) == 1 and batch.max_simple_len == 150
+    _against_oracle(batch)
+    aln = K.parse_bam(p)["big"]
+    assert aln.insertions[long_pos + 100_000] == {long_seq[100_000:100_010]: 1}
+
+
+def test_warp_specialised_variant_matches(monkeypatch):
+    """K1w (KDL_K1F=ws): the producer/consumer pipeline variant of the tile-owner kernel gives the same
+    tables as the oracle on sorted simple, mixed, deep, sparse and multi-contig inputs."""
+    from kindel_b200 import synth
+
+    monkeypatch.setenv("KDL_K1F", "ws")
+    _against_oracle(synth.simple_reads(71, [300_000], 150))
+    _against_oracle(synth.complex_reads(72, 30_000, 400))
+    _against_oracle(synth.simple_reads(73, [4000], 6000))
+    _against_oracle(synth.simple_reads(74, [500_000], 0.5))
+    _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
+
+
 def test_big_bam_file_end_to_end(tmp_path):
     """A 200k-read coordinate-sorted BAM through the whole public path (BGZF inflate, C++ gather, flatten,
     K0/K1f/K2, host assembly): FASTA and changes equal what the oracle's tables give."""

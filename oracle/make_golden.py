@@ -29,10 +29,18 @@ from oracle import refload, samdecode  # noqa: E402
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 INPUTS = os.path.join(GOLDEN, "inputs")
 
-FIXTURES = [  # (golden name, path under /root/reference/tests)
+FIXTURES = [  # (golden name, path under /root/reference/tests): all 17 BAM/SAM files of the reference's suite
     ("bwa_1_1", "data_bwa_mem/1.1.sub_test.bam"),
     ("bwa_2_1", "data_bwa_mem/2.1.sub_test.bam"),
+    ("bwa_3_1", "data_bwa_mem/3.1.sub_test.bam"),
+    ("bwa_4_1", "data_bwa_mem/4.1.sub_test.bam"),
+    ("bwa_5_1", "data_bwa_mem/5.1.sub_test.bam"),
+    ("bwa_6_1", "data_bwa_mem/6.1.sub_test.bam"),
     ("seg_1_1", "data_segemehl/1.1.sub_test.bam"),
+    ("seg_2_1", "data_segemehl/2.1.sub_test.bam"),
+    ("seg_3_1", "data_segemehl/3.1.sub_test.bam"),
+    ("seg_4_1", "data_segemehl/4.1.sub_test.bam"),
+    ("seg_5_1", "data_segemehl/5.1.sub_test.bam"),
     ("seg_6_1", "data_segemehl/6.1.sub_test.bam"),
     ("mm2_multi", "data_minimap2/1.1.multi.bam"),
     ("mm2_gp120", "data_minimap2/hxb2-gp120-mutated.bam"),
@@ -40,6 +48,10 @@ FIXTURES = [  # (golden name, path under /root/reference/tests)
     ("ext_2_bc63", "data_ext/2.issue23.bc63.sam"),
     ("ext_3_bc75", "data_ext/3.issue23.bc75.sam"),
 ]
+
+# the 6.1 Mb fixture: its dense table is 463 MB, so the golden is a digest (sha256 of the int32 table the
+# reference's alignment converts to, of the consensus FASTA and of `changes`) plus column sums
+DIGEST_FIXTURES = [("bact_tiny", "data_minimap2_bact/bact.tiny.bam")]
 
 _OPS = "MIDNSHP=X"
 
@@ -128,6 +140,26 @@ def golden_for_file(k, path):
     except Exception as exc:  # reference bug on multi-contig input
         manifest["features_error"] = type(exc).__name__
     return arrays, manifest
+
+
+def digest_for_file(k, path, rel_input, source):
+    import hashlib
+
+    alns = k.parse_bam(path)
+    entry = {"input": rel_input, "source": source, "contigs": []}
+    for name, aln in alns.items():
+        t, ins = table_of(aln)
+        t = np.ascontiguousarray(t, dtype=np.int32)
+        seq, changes = k.consensus_sequence(aln.weights, aln.insertions, aln.deletions, None, False, 1, False)
+        entry["contigs"].append({
+            "name": name, "ref_len": len(aln.weights),
+            "table_sha256": hashlib.sha256(t.tobytes()).hexdigest(),
+            "column_sums": [int(x) for x in t.sum(axis=1)],
+            "insertions": [[i, list(d.items())] for i, d in enumerate(ins) if d],
+            "fasta_sha256": hashlib.sha256(seq.encode()).hexdigest(), "fasta_len": len(seq),
+            "changes_sha256": hashlib.sha256("".join("-" if c is None else c for c in changes).encode()).hexdigest(),
+        })
+    return entry
 
 
 # ---- synthetic edge cases, as SAM text over a 20 bp contig ---------------
@@ -246,6 +278,12 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **arrays)
         manifest["files"][name] = entry
         print("golden", name, os.path.getsize(dst), os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
+    manifest["digests"] = {}
+    for name, rel in DIGEST_FIXTURES:
+        src = os.path.join(refload.REFERENCE_ROOT, "tests", rel)
+        dst = reencode(src, os.path.join(INPUTS, name))
+        manifest["digests"][name] = digest_for_file(k, dst, os.path.relpath(dst, GOLDEN), "tests/" + rel)
+        print("digest", name, os.path.getsize(dst))
     with tempfile.TemporaryDirectory() as tmp:
         manifest["edge_cases"] = golden_for_edges(k, tmp)
     with open(os.path.join(GOLDEN, "manifest.json"), "wt") as fh:

@@ -490,3 +490,24 @@ def test_exchange_protocol_emulated_on_one_gpu():
         torch.cuda.synchronize()
         np.testing.assert_array_equal(calls.cpu().numpy(), want)
         np.testing.assert_array_equal(reduced.cpu().numpy(), oc[:7])
+
+
+def test_megabase_fixture_digest(manifest):
+    """The reference's 6.1 Mb fixture (`bact.tiny`; 8x depth, mostly empty tiles, secondary records with
+    SEQ `*`): the engine's dense table, consensus FASTA and changes hash to what the reference produced
+    (README.md:39 of the reference warns about megabase genomes; here it is one tile pass)."""
+    from test_oracle_pin import _digest_check
+
+    from kindel_b200 import kindel as K
+
+    for name, entry in manifest["digests"].items():
+        path = golden_input(entry)
+        alns = K.parse_bam(path)
+        res = K.bam_to_consensus(path, False, 1, 7, 0.1, 50, False, False)
+        assert list(alns) == [c["name"] for c in entry["contigs"]]
+        for c, (ctg, aln) in enumerate(alns.items()):
+            meta = entry["contigs"][c]
+            want_ins = {i: [tuple(kv) for kv in items] for i, items in meta["insertions"]}
+            nz = np.flatnonzero(aln.table[6])
+            assert {int(i): list(aln.insertions[int(i)].items()) for i in nz} == want_ins
+            _digest_check(aln.table, res.consensuses[c].sequence, res.refs_changes[ctg], meta)

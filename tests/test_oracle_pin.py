@@ -203,3 +203,32 @@ def test_python_port_against_golden(manifest, golden_npz):
             seq, changes = py_oracle.vote(p, 1)
             assert seq == dict(map(tuple, entry["runs"]["plain"]["fasta"]))[ctg + "_cns"]
             assert "".join("-" if c_ is None else c_ for c_ in changes) == entry["runs"]["plain"]["changes"][ctg]
+
+
+def _digest_check(table_i32, seq, changes, meta):
+    import hashlib
+
+    assert hashlib.sha256(np.ascontiguousarray(table_i32, dtype=np.int32).tobytes()).hexdigest() == meta["table_sha256"]
+    assert [int(x) for x in table_i32.sum(axis=1)] == meta["column_sums"]
+    assert len(seq) == meta["fasta_len"] and hashlib.sha256(seq.encode()).hexdigest() == meta["fasta_sha256"]
+    assert hashlib.sha256("".join("-" if c is None else c for c in changes).encode()).hexdigest() == meta["changes_sha256"]
+
+
+def test_megabase_fixture_digest(manifest):
+    """The 6.1 Mb fixture of the reference (`bact.tiny`, secondary alignments with SEQ `*`, 8x depth):
+    the oracle's dense table, consensus and changes hash to what the reference produced."""
+    from kindel_b200 import kindel as K
+
+    for name, entry in manifest["digests"].items():
+        batch = bamio.read_alignment(golden_input(entry))
+        counts, events = coracle.pileup(batch)
+        calls = coracle.vote(counts, 1)
+        ins = H.events_to_dicts(batch, events)
+        assert batch.contig_names == [c["name"] for c in entry["contigs"]]
+        for c, meta in enumerate(entry["contigs"]):
+            s0, L = int(batch.contig_slot[c]), meta["ref_len"]
+            want_ins = {s0 + i: [tuple(kv) for kv in items] for i, items in meta["insertions"]}
+            assert {s: list(d.items()) for s, d in ins.items()} == want_ins
+            seq, changes = K.assemble_consensus(calls[s0:s0 + L],
+                                                lambda p: K.dict_consensus(ins.get(s0 + p, {})))
+            _digest_check(H.contig_view(batch, counts, c), seq, changes, meta)

@@ -2,7 +2,7 @@
 
 Run in the build container (needs /root/reference):   python -m oracle.make_golden
 
-For a subset of the reference's own test fixtures and for a set of synthetic edge-case alignments
+For every BAM/SAM fixture of the reference's own test-suite and for a set of synthetic edge-case alignments
  it
   1. re-encodes the input with this repo's own writers (names / qualities stripped, so the files
      are not copies of the reference's fixtures) into tests/golden/inputs/,

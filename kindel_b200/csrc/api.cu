@@ -10,6 +10,7 @@
 #include "pileup_simple.cu"
 #include "pileup_tiled.cu"
 #include "pileup_ws.cu"
+#include "pileup_wide.cu"
 #include "vote.cu"
 
 namespace {
@@ -58,8 +59,18 @@ inline int ensure_k1f_smem(int smem) {
         cudaFuncSetAttribute(kdl::pileup_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(kdl::WsSmem)) != cudaSuccess)
         return KDL_ERR_CUDA;
+    if (cudaFuncSetAttribute(kdl::pileup_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(kdl::WideSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute(kdl::pileup_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(kdl::WideSmem)) != cudaSuccess)
+        return KDL_ERR_CUDA;
     done[dev].store(1, std::memory_order_release);
     return KDL_OK;
+}
+
+inline bool use_wide_kernel() {  // K1x, experimental (not yet validated on a GPU)
+    const char* ev = getenv("KDL_K1F");
+    return ev && !strcmp(ev, "wide");
 }
 
 // which tile-owner kernel: "ws" = warp-specialised pipeline (K1w), "tiled" = K1f
@@ -152,6 +163,16 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
             else
                 kdl::pileup_ws_kernel<false><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        } else if (n_tiles > 0 && use_wide_kernel()) {
+            long long grid = n_tiles < (long long)sm_count() * 2 ? n_tiles : (long long)sm_count() * 2;
+            const int xsmem = (int)sizeof(kdl::WideSmem);
+            if (fresh)
+                kdl::pileup_wide_kernel<true><<<(unsigned)grid, kdl::F_THREADS, xsmem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            else
+                kdl::pileup_wide_kernel<false><<<(unsigned)grid, kdl::F_THREADS, xsmem, st>>>(
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
             if ((rc = check_launch()) != KDL_OK) return rc;
         } else if (n_tiles > 0) {

@@ -511,3 +511,18 @@ def test_megabase_fixture_digest(manifest):
             nz = np.flatnonzero(aln.table[6])
             assert {int(i): list(aln.insertions[int(i)].items()) for i in nz} == want_ins
             _digest_check(aln.table, res.consensuses[c].sequence, res.refs_changes[ctg], meta)
+
+
+@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="K1x (wide lanes) has not been validated on a "
+                    "GPU yet: opt in with KDL_TEST_EXPERIMENTAL=1")
+def test_wide_lane_variant_matches(monkeypatch):
+    """K1x (KDL_K1F=wide): 16-slot lanes, 8 read streams per warp."""
+    from kindel_b200 import synth
+
+    monkeypatch.setenv("KDL_K1F", "wide")
+    _against_oracle(synth.simple_reads(71, [300_000], 150))
+    _against_oracle(synth.complex_reads(72, 30_000, 400))
+    _against_oracle(synth.simple_reads(73, [4000], 6000))
+    _against_oracle(synth.simple_reads(74, [500_000], 0.5))
+    _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
+    _against_oracle(synth.simple_reads(76, [60_000], 40, read_len=1203))

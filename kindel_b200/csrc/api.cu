@@ -59,6 +59,16 @@ inline int ensure_k1f_smem(int smem) {
         cudaFuncSetAttribute(kdl::pileup_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(kdl::WsSmem)) != cudaSuccess)
         return KDL_ERR_CUDA;
+    done[dev].store(1, std::memory_order_release);
+    return KDL_OK;
+}
+
+// the same opt-in for the experimental K1x, made only when that kernel is selected so that the default
+// path never depends on it
+inline int ensure_k1x_smem() {
+    static std::atomic<int> done[kMaxDevices];
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
     if (cudaFuncSetAttribute(kdl::pileup_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sizeof(kdl::WideSmem)) != cudaSuccess ||
         cudaFuncSetAttribute(kdl::pileup_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -168,6 +178,7 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
         } else if (n_tiles > 0 && use_wide_kernel()) {
             long long grid = n_tiles < (long long)sm_count() * 2 ? n_tiles : (long long)sm_count() * 2;
             const int xsmem = (int)sizeof(kdl::WideSmem);
+            if ((rc = ensure_k1x_smem()) != KDL_OK) return rc;
             if (fresh)
                 kdl::pileup_wide_kernel<true><<<(unsigned)grid, kdl::F_THREADS, xsmem, st>>>(
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);

@@ -45,6 +45,13 @@ def golden_npz():
     return load
 
 
+@pytest.fixture(scope="session")
+def clip_golden():
+    """Reference outputs for the deterministic clip-heavy cases (oracle/make_clip_golden.py)."""
+    with open(os.path.join(GOLDEN, "clip_cases.json")) as fh:
+        return json.load(fh)
+
+
 def golden_input(entry):
     return os.path.join(GOLDEN, entry["input"])
 

@@ -526,3 +526,20 @@ def test_wide_lane_variant_matches(monkeypatch):
     _against_oracle(synth.simple_reads(74, [500_000], 0.5))
     _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
     _against_oracle(synth.simple_reads(76, [60_000], 40, read_len=1203))
+
+
+def test_clip_heavy_cases_through_the_engine(clip_golden, tmp_path):
+    """The deterministic clip-heavy cases (tests/clip_cases.py) end to end through the public API on the GPU:
+    tables, --realign consensus, changes and report equal the unmodified reference's
+    (tests/golden/clip_cases.json, generated by oracle/make_clip_golden.py)."""
+    from clip_cases import clip_case
+    from test_host_logic import check_clip_case
+
+    from kindel_b200 import kindel as K
+
+    for case in clip_golden["cases"]:
+        path = tmp_path / ("clip%d.sam" % case["seed"])
+        path.write_text(clip_case(case["seed"]))
+        alns = K.parse_bam(str(path))
+        got = K.bam_to_consensus(str(path), *case["options"])
+        check_clip_case(case, got, {name: aln.table for name, aln in alns.items()})

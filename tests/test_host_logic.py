@@ -102,6 +102,40 @@ def test_consensus_report_changes_against_golden(manifest):
                 assert [l for l in got if not l.startswith("- bam_path")] == [l for l in exp if not l.startswith("- bam_path")]
 
 
+def check_clip_case(case, got, tables):
+    """One case of tests/golden/clip_cases.json against a `result` and {contig: int32 [19, L+1] table}."""
+    import hashlib
+
+    seed = case["seed"]
+    assert list(tables) == case["contigs"], seed
+    for ctg, t in tables.items():
+        sha = hashlib.sha256(np.ascontiguousarray(t, dtype=np.int32).tobytes()).hexdigest()
+        assert sha == case["table_sha256"][ctg], (seed, ctg)
+    assert [[r.name, r.sequence] for r in got.consensuses] == case["fasta"], (seed, case["options"])
+    for ctg, ch in got.refs_changes.items():
+        assert "".join("-" if c is None else c for c in ch) == case["changes"][ctg], (seed, ctg)
+    for ctg, rep in got.refs_reports.items():
+        assert [l for l in rep.splitlines() if not l.startswith("- bam_path")] == case["reports"][ctg], (seed, ctg)
+
+
+def test_clip_heavy_cases_against_golden(clip_golden, tmp_path):
+    """--realign machinery on synthetic clip-dominant regions (tests/clip_cases.py): oracle tables + host
+    code == what the unmodified reference returned (oracle/make_clip_golden.py)."""
+    from clip_cases import clip_case
+
+    import helpers as H
+
+    assert len(clip_golden["cases"]) >= 90
+    for case in clip_golden["cases"]:
+        path = tmp_path / ("clip%d.sam" % case["seed"])
+        path.write_text(clip_case(case["seed"]))
+        run, counts = oracle_run(path)
+        o = case["options"]
+        got = K.consensus_from_run(run, coracle.vote(counts, o[1]), str(path), *o)
+        tables = {name: H.contig_view(run.batch, counts, c) for c, name in enumerate(run.batch.contig_names)}
+        check_clip_case(case, got, tables)
+
+
 def test_weights_and_features_frames_against_golden(manifest, golden_npz):
     for name, entry in manifest["files"].items():
         run, _ = oracle_run(golden_input(entry))

@@ -122,6 +122,9 @@ tile_index_kernel(kdl_batch b, long long tile_lo, long long n_tiles, uint32_t* _
     e[7] = 0u;
 }
 
+// (KDL_HOST_EMU: tests/emu/ compiles this file for the host and supplies functional stand-ins for the PTX
+// helpers below; the device build never defines it.)
+#ifndef KDL_HOST_EMU
 // ---- 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP) completing on an mbarrier --------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -158,6 +161,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     }
 }
+#endif  // KDL_HOST_EMU
 
 // first index i in [0, n) with g[i] >= key (n if none); g sorted, n <= 1024, whole warp calls
 __device__ __forceinline__ int lower_bound_warp(const int* g, int n, int key, int lane) {
@@ -534,6 +538,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                     const uint32_t jb = (uint32_t)(p8b - mt[u].x);  // byte offset of the read's word
                     const uint32_t addr = (uint32_t)mt[u].y + jb;
                     uint32_t hw, lw;
+#ifndef KDL_HOST_EMU
                     asm("{\n"
                         ".reg .pred p, q;\n"
                         "setp.lt.u32 p, %2, %3;\n"
@@ -545,6 +550,10 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                         "}\n"
                         : "=&r"(hw), "=&r"(lw)
                         : "r"(jb), "r"((uint32_t)mt[u].z), "r"(jb + 4u), "r"(addr));
+#else
+                    hw = jb < (uint32_t)mt[u].z ? lds_u32(addr) : 0u;
+                    lw = jb + 4u < (uint32_t)mt[u].z ? lds_u32(addr + 4u) : 0u;
+#endif
                     x[u] = __funnelshift_l(lw, hw, (uint32_t)mt[u].w);
                 }
                 acc.add8(x);

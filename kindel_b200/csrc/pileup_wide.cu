@@ -8,7 +8,7 @@
 // 8 streams are summed bit-sliced in three shuffle butterflies; at a flush group g transposes word g / 4,
 // bit g % 4, i.e. every lane still writes 8 consecutive slots of one column.  Staging, metadata, coverage and
 // the window search are K1f's.  The arithmetic is modelled and checked on the CPU (tests/k1f_model.py,
-// pileup_model_wide).
+// pileup_model_wide) and this source runs under the host emulator (tests/emu/, KDL_HOST_EMU).
 #include "kdl_common.cuh"
 
 namespace kdl {
@@ -332,6 +332,7 @@ pileup_wide_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     const uint32_t jb = (uint32_t)(p8b - mt[u].x);  // byte offset of the read's first needed word
                     const uint32_t addr = (uint32_t)mt[u].y + jb;
                     uint32_t w0, w1, w2;
+#ifndef KDL_HOST_EMU
                     asm("{\n"
                         ".reg .pred p, q, r;\n"
                         "setp.lt.u32 p, %3, %4;\n"
@@ -346,6 +347,11 @@ pileup_wide_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         "}\n"
                         : "=&r"(w0), "=&r"(w1), "=&r"(w2)
                         : "r"(jb), "r"((uint32_t)mt[u].z), "r"(jb + 4u), "r"(jb + 8u), "r"(addr));
+#else
+                    w0 = jb < (uint32_t)mt[u].z ? lds_u32(addr) : 0u;
+                    w1 = jb + 4u < (uint32_t)mt[u].z ? lds_u32(addr + 4u) : 0u;
+                    w2 = jb + 8u < (uint32_t)mt[u].z ? lds_u32(addr + 8u) : 0u;
+#endif
                     x0[u] = __funnelshift_l(w1, w0, (uint32_t)mt[u].w);
                     x1[u] = __funnelshift_l(w2, w1, (uint32_t)mt[u].w);
                 }

@@ -78,6 +78,25 @@ inline int ensure_k1x_smem() {
     return KDL_OK;
 }
 
+// the same opt-in for the experimental lean instantiation of K1f (KDL_K1F=lean)
+inline int ensure_k1f_lean_smem(int smem) {
+    static std::atomic<int> done[kMaxDevices];
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
+    if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess ||
+        cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem) != cudaSuccess)
+        return KDL_ERR_CUDA;
+    done[dev].store(1, std::memory_order_release);
+    return KDL_OK;
+}
+
+inline bool use_lean_kernel() {  // K1f<.., kLean = true>, experimental (not yet validated on a GPU)
+    const char* ev = getenv("KDL_K1F");
+    return ev && !strcmp(ev, "lean");
+}
+
 inline bool use_wide_kernel() {  // K1x, experimental (not yet validated on a GPU)
     const char* ev = getenv("KDL_K1F");
     return ev && !strcmp(ev, "wide");
@@ -193,7 +212,15 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             if (const char* ev = getenv("KDL_K1F_GRID_MULT")) { mult = atoll(ev); if (mult < 1) mult = 1; }
             const long long max_grid = (long long)sm_count() * 2 * mult;
             long long grid = n_tiles < max_grid ? n_tiles : max_grid;
-            if (fresh)
+            if (use_lean_kernel()) {
+                if ((rc = ensure_k1f_lean_smem(smem)) != KDL_OK) return rc;
+                if (fresh)
+                    kdl::pileup_tiled_kernel<true, true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
+                        *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+                else
+                    kdl::pileup_tiled_kernel<false, true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
+                        *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            } else if (fresh)
                 kdl::pileup_tiled_kernel<true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
             else

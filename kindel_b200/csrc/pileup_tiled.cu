@@ -26,6 +26,8 @@
 // Preconditions (checked on the host side of the ABI, include/kindel_b200.h): reads_sorted,
 // seq_off non-decreasing, simple reads clean (A,C,G,T,N only, trailing nibbles zero) and no longer
 // than KDL_FAST_MAXLEN.  Anything else is a complex read and belongs to K1g.
+#include <stddef.h>
+
 #include "kdl_common.cuh"
 
 namespace kdl {
@@ -327,9 +329,18 @@ struct FastSmem {
     uint64_t bar;                 // mbarrier the bulk copy of seq[] completes on
 };
 
+static_assert(offsetof(FastSmem, diff) % 16 == 0 && (sizeof(int) * (KDL_TILE + 32)) % 16 == 0,
+              "the difference arrays are read with 128-bit loads");
+
 // kFresh: columns 0..4 hold stale data; the first flush of every window stores instead of adding,
 // and windows / tiles without reads are stored as zeros.
-template <bool kFresh>
+//
+// kLean (experimental, KDL_K1F=lean; not yet measured): the same kernel with two of the latency-bound phases
+// that the ncu stall samples charge most (profiles/r01_k1f_final_regions.txt) shortened -- the tile-index entry
+// and the contig slot of the NEXT tile are loaded one tile ahead into registers, so neither the tile setup nor
+// the metadata prefetch waits on a global load, and the prefix of the difference array is summed with 128-bit
+// shared loads.
+template <bool kFresh, bool kLean = false>
 __global__ void __launch_bounds__(F_THREADS, 2)
 pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
@@ -359,11 +370,48 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
             cp_async4(&sm.raw[2][i], b.seq_off + plo + i);
         }
     };
-    prefetch_raw(tile_lo + blockIdx.x);
+    // kLean: index entry (and first contig's slot) of the tile this CTA handles NEXT, held in registers
+    uint4 nix = make_uint4(0u, 0u, 0u, 0u);
+    uint2 nic = make_uint2(0u, 0u);
+    long long ncs = 0;
+    auto load_next_index = [&](long long t) {
+        if (t < tile_lo + n_tiles) {
+            nix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * t));
+            nic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * t + 4));
+            ncs = b.contig_slot[nic.x];
+        } else {
+            nix = make_uint4(0u, 0u, 0u, 0u);  // lo == hi: nothing to prefetch
+        }
+    };
+    auto prefetch_raw_lean = [&]() {  // the reads of the tile described by nix
+        const long long plo = nix.x, phi = nix.y;
+        const int cnt = (int)(phi - plo < F_RMAX ? phi - plo : F_RMAX);
+        for (int i = tid; i < cnt; i += F_THREADS) {
+            cp_async4(&sm.raw[0][i], b.l_seq + plo + i);
+            cp_async4(&sm.raw[1][i], b.ref_start + plo + i);
+            cp_async4(&sm.raw[2][i], b.seq_off + plo + i);
+        }
+    };
+    if constexpr (kLean) {
+        load_next_index(tile_lo + blockIdx.x);
+        prefetch_raw_lean();
+    } else {
+        prefetch_raw(tile_lo + blockIdx.x);
+    }
 
     for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
-        const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
-        const uint2 ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
+        uint4 ix;
+        uint2 ic;
+        long long first_contig_slot = 0;
+        if constexpr (kLean) {
+            ix = nix;
+            ic = nic;
+            first_contig_slot = ncs;
+            load_next_index(tile + gridDim.x);  // consumed a whole tile later
+        } else {
+            ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * tile));
+            ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * tile + 4));
+        }
         const long long lo = ix.x, hi = ix.y;
         const long long tile_slot = tile * KDL_TILE;
         bool raw_pending = true;  // sm.raw holds this tile's first reads; the next prefetch is still to issue
@@ -374,11 +422,14 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                     reinterpret_cast<int4*>(counts + (long long)col * n_slots + tile_slot)[off] = make_int4(0, 0, 0, 0);
                 }
             }
-            prefetch_raw(tile + gridDim.x);  // nothing was prefetched for an empty tile: raw is free
+            // nothing was prefetched for an empty tile: raw is free
+            if constexpr (kLean) prefetch_raw_lean(); else prefetch_raw(tile + gridDim.x);
             continue;
         }
         const bool one_contig = ic.x == ic.y;
-        const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
+        long long slot_base;
+        if constexpr (kLean) slot_base = one_contig ? first_contig_slot - tile_slot : 0;
+        else slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
         const int wlo = warp * F_WIN;
         const int p8b = (wlo >> 1) + 4 * (lane & 7);  // 4 * (lane's first slot / 8): byte offset of its word
         Planes acc;
@@ -480,7 +531,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                     sm.meta[i + (i >> 3)] = make_int4(0x10000000, (int)seq_base, 0, 0);
                 }
                 if (raw_pending) {  // this thread's raw elements are consumed: refill them for the next tile
-                    prefetch_raw(tile + gridDim.x);
+                    if constexpr (kLean) prefetch_raw_lean(); else prefetch_raw(tile + gridDim.x);
                     raw_pending = false;
                 }
                 int* other = sm.diff[dbuf ^ 1];  // clean the buffer the NEXT sub-chunk will use
@@ -494,7 +545,14 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
             // ---- coverage of this warp's 64 slots: prefix sum of the difference array ------------
             {
                 int pre = 0;
-                for (int k = lane; k < wlo; k += 32) pre += diff[k];
+                if constexpr (kLean) {  // wlo is a multiple of 64 and diff is 16-byte aligned
+                    for (int k = 4 * lane; k < wlo; k += 128) {
+                        const int4 v = *reinterpret_cast<const int4*>(diff + k);
+                        pre += (v.x + v.y) + (v.z + v.w);
+                    }
+                } else {
+                    for (int k = lane; k < wlo; k += 32) pre += diff[k];
+                }
 #pragma unroll
                 for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
                 const int d0 = diff[wlo + 2 * lane], d1 = diff[wlo + 2 * lane + 1];

@@ -14,7 +14,7 @@ extern "C" {
 
 const char* emu_last_error() { return g_error; }
 
-// variant 0 = K1f (pileup_tiled_kernel), 1 = K1x (pileup_wide_kernel).  All pointers are HOST pointers;
+// variant 0 = K1f (pileup_tiled_kernel), 1 = K1x (pileup_wide_kernel), 2 = K1f with kLean.  All pointers are HOST pointers;
 // `counts` is int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.
 // Returns 0, or 1 with emu_last_error() set.
 int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint32_t* tile_index, long long tile_lo,
@@ -29,6 +29,9 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
             if (variant == 0) {
                 if (fresh) kdl::pileup_tiled_kernel<true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
                 else kdl::pileup_tiled_kernel<false>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
+            } else if (variant == 2) {
+                if (fresh) kdl::pileup_tiled_kernel<true, true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
+                else kdl::pileup_tiled_kernel<false, true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
             } else {
                 if (fresh) kdl::pileup_wide_kernel<true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
                 else kdl::pileup_wide_kernel<false>(b, counts, n_slots, tile_index, tile_lo, n_tiles);

@@ -18,7 +18,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 OUT_DIR = os.path.join(EMU_DIR, "_build")
 LIB = os.path.join(OUT_DIR, "libkdl_emu.so")
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
-K1F, K1X = 0, 1
+K1F, K1X, K1F_LEAN = 0, 1, 2
 
 _lib = None
 

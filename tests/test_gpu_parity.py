@@ -528,6 +528,20 @@ def test_wide_lane_variant_matches(monkeypatch):
     _against_oracle(synth.simple_reads(76, [60_000], 40, read_len=1203))
 
 
+@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="K1f<kLean> has not been validated on a GPU "
+                    "yet: opt in with KDL_TEST_EXPERIMENTAL=1")
+def test_lean_variant_matches(monkeypatch):
+    """K1f with kLean (KDL_K1F=lean): next tile's index a tile ahead in registers, 128-bit prefix loads."""
+    from kindel_b200 import synth
+
+    monkeypatch.setenv("KDL_K1F", "lean")
+    _against_oracle(synth.simple_reads(81, [300_000], 150))
+    _against_oracle(synth.complex_reads(82, 30_000, 400))
+    _against_oracle(synth.simple_reads(83, [9000], 600, read_len=6000))
+    _against_oracle(synth.simple_reads(84, [500_000], 0.5))
+    _against_oracle(synth.simple_reads(85, [151, 200, 90_000, 333], 40))
+
+
 def test_clip_heavy_cases_through_the_engine(clip_golden, tmp_path):
     """The deterministic clip-heavy cases (tests/clip_cases.py) end to end through the public API on the GPU:
     tables, --realign consensus, changes and report equal the unmodified reference's

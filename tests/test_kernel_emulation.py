@@ -26,7 +26,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1X], ids=["K1f", "K1x"])
+@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN], ids=["K1f", "K1x", "K1f-lean"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_tile_owner_kernel_source_equals_oracle(name, variant):
     batch = CASES[name]()
@@ -37,7 +37,7 @@ def test_tile_owner_kernel_source_equals_oracle(name, variant):
         assert not got[5:].any()
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1X], ids=["K1f", "K1x"])
+@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN], ids=["K1f", "K1x", "K1f-lean"])
 def test_accumulate_and_slot_ranges(variant):
     """Two batches added into one table (accumulate mode), then a fresh pass over a tile sub-range only."""
     a = synth.simple_reads(81, [20_000], 30)

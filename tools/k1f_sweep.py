@@ -1,4 +1,9 @@
-"""Diagnostic (not a test): K1f time on cfg 4 for a few launch configurations."""
+"""Diagnostic (not a test): K0 + tile-owner kernel time on cfg 4 for the kernel variants, with a parity check.
+
+    SWEEP=tiled,lean,wide,ws python tools/k1f_sweep.py        (on the GPU box)
+
+Each variant (KDL_K1F=...) is run on the same batch into a reused CountTable; the first variant's weight
+columns are the yardstick the others must equal bit for bit (and the first is the GPU-validated default)."""
 import os
 import sys
 
@@ -8,11 +13,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from kindel_b200 import engine, synth  # noqa: E402
 
-b = synth.simple_reads(4, [5_000_000], 200)
+b = synth.simple_reads(4, [5_000_000], int(os.environ.get("SWEEP_DEPTH", "200")))
 db = engine.upload(b)
 table = engine.CountTable(b.n_slots, db.device)
-for mult in os.environ.get("SWEEP", "tiled,ws").split(","):
-    os.environ["KDL_K1F"] = mult
+want = None
+for variant in os.environ.get("SWEEP", "tiled,lean,wide,ws").split(","):
+    os.environ["KDL_K1F"] = variant
     for _ in range(3):
         engine.pileup(db, check=False, table=table)
     torch.cuda.synchronize()
@@ -22,4 +28,9 @@ for mult in os.environ.get("SWEEP", "tiled,ws").split(","):
         engine.pileup(db, check=False, table=table)
     ev[1].record()
     torch.cuda.synchronize()
-    print("kernel", mult, "K0+K1f ms", ev[0].elapsed_time(ev[1]) / 10, flush=True)
+    got = table.t[0:5].clone()
+    if want is None:
+        want, verdict = got, "yardstick"
+    else:
+        verdict = "EQUAL" if torch.equal(got, want) else "DIFFERENT (%d slots)" % int((got != want).any(dim=0).sum())
+    print("kernel", variant, "K0+K1 ms %.4f" % (ev[0].elapsed_time(ev[1]) / 10), verdict, flush=True)

@@ -38,6 +38,7 @@ constexpr int F_RMAX = 1024;           // reads per staged sub-chunk
 constexpr int F_CAPW = 17920;          // seq words per staged sub-chunk (70 KB): 2 CTAs x ~111 KB per SM
 constexpr int F_P = 8;                 // bit planes per stream: up to 255 reads between flushes
 constexpr int F_FLUSH_BLOCKS = 31;     // 31 blocks x 8 reads = 248 <= 255
+static_assert(F_FLUSH_BLOCKS % 2 == 1, "kLean folds exactly one pending carry at a mid-window flush");
 
 // ---- K0: per tile, what K1f needs to start without dependent global loads: 8 x int32
 //   [0] lo, [1] hi   index range of reads whose first base lies in (tile_lo - maxlen, tile_hi)
@@ -179,6 +180,26 @@ __device__ __forceinline__ int lower_bound_warp(const int* g, int n, int key, in
     return r < n ? r : n;
 }
 
+// the same for TWO keys at once (key_a <= key_e): one probe load serves both searches and the two dependent
+// chains (load -> ballot -> load -> ballot) overlap
+__device__ __forceinline__ void lower_bound_warp2(const int* g, int n, int key_a, int key_e, int lane, int& ra, int& re) {
+    const int step = (n + 31) >> 5;  // <= 32
+    if (step == 0) { ra = re = 0; return; }
+    const int i1 = (lane + 1) * step - 1;
+    const int v1 = i1 < n ? g[i1] : 0x7fffffff;  // past the end: counts as >= key
+    const unsigned ma = __ballot_sync(0xffffffffu, v1 >= key_a);
+    const unsigned me = __ballot_sync(0xffffffffu, v1 >= key_e);
+    const int ka = __ffs(ma) - 1, ke = __ffs(me) - 1;  // first bucket whose last element is >= key; -1: none
+    const int ia = ka * step + lane, ie = ke * step + lane;
+    const int va = (ka >= 0 && lane < step && ia < n) ? g[ia] : 0x7fffffff;
+    const int ve = (ke >= 0 && lane < step && ie < n) ? g[ie] : 0x7fffffff;
+    const unsigned m2a = __ballot_sync(0xffffffffu, va >= key_a);
+    const unsigned m2e = __ballot_sync(0xffffffffu, ve >= key_e);
+    const int qa = ka * step + __ffs(m2a) - 1, qe = ke * step + __ffs(m2e) - 1;
+    ra = (ka < 0 || qa > n) ? n : qa;
+    re = (ke < 0 || qe > n) ? n : qe;
+}
+
 // ---- bit-sliced counters ------------------------------------------------------------------------
 __device__ __forceinline__ void csa(uint32_t& carry, uint32_t& sum, uint32_t a, uint32_t b, uint32_t c) {
     const uint32_t s = a ^ b ^ c;
@@ -204,6 +225,28 @@ struct Planes {
         csa(e, p[2], p[2], fa, fb);
 #pragma unroll
         for (int k = 3; k < F_P; ++k) {
+            const uint32_t t = p[k] & e;
+            p[k] ^= e;
+            e = t;
+        }
+    }
+    // kLean: the same 7 full adders, but the carry out of the 4s plane (weight 8) is handed back instead of being
+    // rippled up; the caller pairs two of them with one more full adder, so the ripple runs once per 16 reads
+    __device__ __forceinline__ uint32_t add8_carry(const uint32_t (&x)[8]) {
+        uint32_t ta, tb, tc, td, fa, fb, e;
+        csa(ta, p[0], p[0], x[0], x[1]);
+        csa(tb, p[0], p[0], x[2], x[3]);
+        csa(fa, p[1], p[1], ta, tb);
+        csa(tc, p[0], p[0], x[4], x[5]);
+        csa(td, p[0], p[0], x[6], x[7]);
+        csa(fb, p[1], p[1], tc, td);
+        csa(e, p[2], p[2], fa, fb);
+        return e;
+    }
+    template <int K0>  // add one plane of weight 2^K0
+    __device__ __forceinline__ void ripple(uint32_t e) {
+#pragma unroll
+        for (int k = K0; k < F_P; ++k) {
             const uint32_t t = p[k] & e;
             p[k] ^= e;
             e = t;
@@ -438,6 +481,7 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
 #pragma unroll
         for (int k = 0; k < 8; ++k) { rawacc[k] = 0; covacc[k] = 0; }
         int blocks_since_flush = 0;
+        uint32_t pend8 = 0;   // kLean: weight-8 carry of an odd block, waiting for its partner
         bool stored = false;  // kFresh: has this window been written yet?
 
         long long c0 = lo;
@@ -508,7 +552,9 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                             const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
                             g = b.contig_slot[c] + rs[k] - tile_slot;
                         }
-                        g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
+                        // (the reads of [lo, hi) start inside (tile - maxlen, tile + 512) by construction of the
+                        // index; the clamp only guards the int conversion against a corrupt index)
+                        if constexpr (!kLean) g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
                         const int gs = (int)g;
                         int nb = 0;
                         if (l[k] > 0) {  // simple read (bit 31 clear)
@@ -574,8 +620,13 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
 
             // ---- this warp's window against the sub-chunk: reads with start in (wlo - maxlen, wlo + 64)
             // two lower bounds over the sorted starts, each in two 32-wide probe rounds (n_sub <= 1024)
-            const int a = lower_bound_warp(sm.gs, n_sub, wlo - maxlen + 1, lane);
-            const int e = lower_bound_warp(sm.gs, n_sub, wlo + F_WIN, lane);
+            int a, e;
+            if constexpr (kLean) {
+                lower_bound_warp2(sm.gs, n_sub, wlo - maxlen + 1, wlo + F_WIN, lane, a, e);
+            } else {
+                a = lower_bound_warp(sm.gs, n_sub, wlo - maxlen + 1, lane);
+                e = lower_bound_warp(sm.gs, n_sub, wlo + F_WIN, lane);
+            }
 
             for (int base = a & ~7; base < e; base += 32) {
                 // 8 reads per lane and block: quarter q takes the 8 CONSECUTIVE reads base + 8q .. + 7.
@@ -614,8 +665,20 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
 #endif
                     x[u] = __funnelshift_l(lw, hw, (uint32_t)mt[u].w);
                 }
-                acc.add8(x);
+                if constexpr (kLean) {
+                    const uint32_t e8 = acc.add8_carry(x);
+                    if (blocks_since_flush & 1) {  // second block of a pair: eights + eights -> sixteens, one ripple
+                        uint32_t c16;
+                        csa(c16, acc.p[3], acc.p[3], pend8, e8);
+                        acc.template ripple<4>(c16);
+                    } else {
+                        pend8 = e8;
+                    }
+                } else {
+                    acc.add8(x);
+                }
                 if (++blocks_since_flush == F_FLUSH_BLOCKS) {
+                    if constexpr (kLean) acc.template ripple<3>(pend8);  // F_FLUSH_BLOCKS is odd: one carry is pending
                     if (kFresh && !stored)
                         flush_window<true, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
                     else
@@ -625,6 +688,9 @@ pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots
                 }
             }
             c0 = c1;
+        }
+        if constexpr (kLean) {
+            if (blocks_since_flush & 1) acc.template ripple<3>(pend8);
         }
         if (kFresh && !stored) flush_window<true, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
         else flush_window<false, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);

@@ -92,6 +92,26 @@ inline int ensure_k1f_lean_smem(int smem) {
     return KDL_OK;
 }
 
+// K1w2 = pileup_ws_kernel<.., WsCfg2>: two CTAs per SM, setmaxnreg (experimental, KDL_K1F=ws2)
+inline int ensure_k1w2_smem() {
+    static std::atomic<int> done[kMaxDevices];
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
+    const int bytes = (int)sizeof(kdl::WsSmemT<kdl::WsCfg2>);
+    if (cudaFuncSetAttribute(kdl::pileup_ws_kernel<false, kdl::WsCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(kdl::pileup_ws_kernel<true, kdl::WsCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             bytes) != cudaSuccess)
+        return KDL_ERR_CUDA;
+    done[dev].store(1, std::memory_order_release);
+    return KDL_OK;
+}
+
+inline bool use_ws2_kernel() {
+    const char* ev = getenv("KDL_K1F");
+    return ev && !strcmp(ev, "ws2");
+}
+
 inline bool use_lean_kernel() {  // K1f<.., kLean = true>, experimental (not yet validated on a GPU)
     const char* ev = getenv("KDL_K1F");
     return ev && !strcmp(ev, "lean");
@@ -192,6 +212,18 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
             else
                 kdl::pileup_ws_kernel<false><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        } else if (n_tiles > 0 && use_ws2_kernel()) {
+            if ((rc = ensure_k1w2_smem()) != KDL_OK) return rc;
+            const long long max_grid = (long long)sm_count() * 2;
+            const long long grid = n_tiles < max_grid ? n_tiles : max_grid;
+            const int wsmem = (int)sizeof(kdl::WsSmemT<kdl::WsCfg2>);
+            if (fresh)
+                kdl::pileup_ws_kernel<true, kdl::WsCfg2><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
+                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            else
+                kdl::pileup_ws_kernel<false, kdl::WsCfg2><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
                     *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
             if ((rc = check_launch()) != KDL_OK) return rc;
         } else if (n_tiles > 0 && use_wide_kernel()) {

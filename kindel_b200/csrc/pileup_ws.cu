@@ -18,19 +18,40 @@
 
 namespace kdl {
 
-constexpr int W_CONSUMERS = 8;                    // consumer warps (one 64-slot window each)
-constexpr int W_PRODUCERS = 4;                    // producer warps
-constexpr int W_THREADS = 32 * (W_CONSUMERS + W_PRODUCERS);
-constexpr int W_STAGES = 2;
-constexpr int W_RMAX = F_RMAX;                    // reads per item
-constexpr int W_CAPW = 17920;                     // words of packed bases per item (70 KB)
+// Configurations.  WsCfg1 = K1w as validated on the GPU: one CTA per SM, full-tile stages.  WsCfg2 = K1w2
+// (experimental, KDL_K1F=ws2, emulator-checked only): two CTAs per SM, i.e. 16 consumer warps per SM where the
+// K1w experiment showed 8 to be the limit, with half-size stages; the register file is re-balanced between the
+// roles with setmaxnreg (producers 40, consumers 96: 128*40 + 256*96 = 384*77 <= 384*80 of the launch bound).
+struct WsCfg1 {
+    static constexpr int kConsumers = 8;    // consumer warps (one 64-slot window each)
+    static constexpr int kProducers = 4;    // producer warps
+    static constexpr int kStages = 2;
+    static constexpr int kRmax = F_RMAX;    // reads per item
+    static constexpr int kCapW = 17920;     // words of packed bases per item (70 KB)
+    static constexpr int kMinBlocks = 1;
+    static constexpr bool kRebalance = false;
+};
+struct WsCfg2 {
+    static constexpr int kConsumers = 8;
+    static constexpr int kProducers = 4;
+    static constexpr int kStages = 2;
+    static constexpr int kRmax = 512;
+    static constexpr int kCapW = 9216;      // 36 KB: ~485 reads of 150 bases (19 words each)
+    static constexpr int kMinBlocks = 2;
+    static constexpr bool kRebalance = true;
+};
+constexpr int W_PRODUCER_REGS = 40, W_CONSUMER_REGS = 96;  // WsCfg2 only
+constexpr int W_CONSUMERS = WsCfg1::kConsumers;
+constexpr int W_PRODUCERS = WsCfg1::kProducers;
+constexpr int W_THREADS = 32 * (W_CONSUMERS + W_PRODUCERS);  // the same for both configurations
 
 enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
 
-struct WsStage {
-    uint32_t seq[W_CAPW];
-    int4 meta[W_RMAX + 40 + (W_RMAX + 40) / 8];  // as in FastSmem: entry of read i at i + i/8
-    int gs[W_RMAX + 32];
+template <class C>
+struct WsStageT {
+    uint32_t seq[C::kCapW];
+    int4 meta[C::kRmax + 40 + (C::kRmax + 40) / 8];  // as in FastSmem: entry of read i at i + i/8
+    int gs[C::kRmax + 32];
     int cov[KDL_TILE];                            // simple reads of THIS item covering each slot
     int diff[KDL_TILE + 32];                      // producers only
     long long tile_slot;
@@ -38,13 +59,17 @@ struct WsStage {
     int flags;
 };
 
-struct WsSmem {
-    WsStage st[W_STAGES];
-    int raw[3][W_RMAX];        // producers only: l_seq / ref_start / seq_off of the NEXT tile's first reads
-    uint64_t full[W_STAGES];   // producers -> consumers: 4 warp arrivals + the bulk copy's bytes
-    uint64_t empty[W_STAGES];  // consumers -> producers: 8 warp arrivals
+template <class C>
+struct WsSmemT {
+    WsStageT<C> st[C::kStages];
+    int raw[3][C::kRmax];           // producers only: l_seq / ref_start / seq_off of the NEXT tile's first reads
+    uint64_t full[C::kStages];      // producers -> consumers: 4 warp arrivals + the bulk copy's bytes
+    uint64_t empty[C::kStages];     // consumers -> producers: 8 warp arrivals
 };
+using WsSmem = WsSmemT<WsCfg1>;
+static_assert(sizeof(WsSmemT<WsCfg2>) <= 113 * 1024, "K1w2 must fit two CTAs per SM");
 
+#ifndef KDL_HOST_EMU
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -54,13 +79,19 @@ __device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t byte
 __device__ __forceinline__ void producer_sync() {  // the 128 producer threads only
     asm volatile("bar.sync 1, %0;" ::"n"(32 * W_PRODUCERS) : "memory");
 }
+template <int kRegs> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+template <int kRegs> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
+#endif  // KDL_HOST_EMU
 
-template <bool kFresh>
-__global__ void __launch_bounds__(W_THREADS, 1)
+template <bool kFresh, class C = WsCfg1>
+__global__ void __launch_bounds__(W_THREADS, C::kMinBlocks)
 pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                  const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
+    using Smem = WsSmemT<C>;
+    using Stage = WsStageT<C>;
+    constexpr int W_STAGES = C::kStages, W_RMAX = C::kRmax, W_CAPW = C::kCapW;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int maxlen = b.max_simple_len;
 
@@ -76,10 +107,11 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 
     if (warp >= W_CONSUMERS) {
         // =========================== PRODUCERS ====================================================
+        if constexpr (C::kRebalance) reg_dealloc<W_PRODUCER_REGS>();
         const int pw = warp - W_CONSUMERS;          // 0..3
         const int ptid = tid - 32 * W_CONSUMERS;    // 0..127
         long long item = 0;
-        auto acquire_stage = [&](long long it) -> WsStage& {
+        auto acquire_stage = [&](long long it) -> Stage& {
             const int s = (int)(it % W_STAGES);
             const uint32_t round = (uint32_t)(it / W_STAGES);
             if (round > 0) mbar_wait(&sm.empty[s], (round - 1) & 1u);  // consumers released its last use
@@ -125,7 +157,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             const long long tile_slot = tile * KDL_TILE;
             if (lo >= hi) {
                 if (kFresh) {  // consumers must store zeros: a header-only item
-                    WsStage& st = acquire_stage(item);
+                    Stage& st = acquire_stage(item);
                     if (ptid == 0) { st.tile_slot = tile_slot; st.n_sub = 0; st.flags = ITEM_FIRST | ITEM_LAST | ITEM_EMPTY; }
                     publish(item);
                     ++item;
@@ -147,7 +179,14 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 bool skip = false;
                 while (wend - wa > W_CAPW) {
                     if (c1 - c0 == 1) { skip = true; break; }  // one read too long to stage: never simple
-                    c1 = c0 + (c1 - c0) / 2;
+                    if constexpr (C::kRebalance) {  // small stages: cut where the capacity ends, not in half
+                        const long long n = c1 - c0;
+                        long long n2 = n * W_CAPW / (wend - wa);
+                        n2 = n2 >= n ? n - 1 : (n2 < 1 ? 1 : n2);
+                        c1 = c0 + n2;
+                    } else {
+                        c1 = c0 + (c1 - c0) / 2;
+                    }
                     wend = (long long)b.seq_off[c1];
                 }
                 const bool last = c1 >= hi;
@@ -179,7 +218,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     prefetch_raw(nix);
                     raw_pending = false;
                 }
-                WsStage& st = acquire_stage(item);
+                Stage& st = acquire_stage(item);
                 const uint32_t seq_base = smem_u32(st.seq);
                 if (!skip) {
                     const long long n_words = wend - wa;
@@ -268,7 +307,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             ic = nic;
         }
         {   // END item
-            WsStage& st = acquire_stage(item);
+            Stage& st = acquire_stage(item);
             if (ptid == 0) { st.tile_slot = 0; st.n_sub = 0; st.flags = ITEM_END; }
             publish(item);
         }
@@ -276,6 +315,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
     }
 
     // =============================== CONSUMERS ===================================================
+    if constexpr (C::kRebalance) reg_alloc<W_CONSUMER_REGS>();
     const int quarter = lane >> 3;
     const int wlo = warp * F_WIN;
     const int p8b = (wlo >> 1) + 4 * (lane & 7);
@@ -290,7 +330,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
     for (long long item = 0;; ++item) {
         const int s = (int)(item % W_STAGES);
         mbar_wait(&sm.full[s], (uint32_t)((item / W_STAGES) & 1));
-        WsStage& st = sm.st[s];
+        Stage& st = sm.st[s];
         const int flags = st.flags;
         const int n_sub = st.n_sub;
         const long long tile_slot = st.tile_slot;
@@ -320,6 +360,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     const uint32_t jb = (uint32_t)(p8b - mt[u].x);
                     const uint32_t addr = (uint32_t)mt[u].y + jb;
                     uint32_t hw, lw;
+#ifndef KDL_HOST_EMU
                     asm("{\n"
                         ".reg .pred p, q;\n"
                         "setp.lt.u32 p, %2, %3;\n"
@@ -331,6 +372,10 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         "}\n"
                         : "=&r"(hw), "=&r"(lw)
                         : "r"(jb), "r"((uint32_t)mt[u].z), "r"(jb + 4u), "r"(addr));
+#else
+                    hw = jb < (uint32_t)mt[u].z ? lds_u32(addr) : 0u;
+                    lw = jb + 4u < (uint32_t)mt[u].z ? lds_u32(addr + 4u) : 0u;
+#endif
                     x[u] = __funnelshift_l(lw, hw, (uint32_t)mt[u].w);
                 }
                 acc.add8(x);

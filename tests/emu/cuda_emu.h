@@ -1,6 +1,6 @@
 // cuda_emu.h -- TEST INFRASTRUCTURE: a functional emulator of the CUDA execution model for the host.
 //
-// Purpose: run the SOURCE TEXT of the tile-owner kernels (kindel_b200/csrc/pileup_tiled.cu, pileup_wide.cu)
+// Purpose: run the SOURCE TEXT of the tile-owner kernels (kindel_b200/csrc/pileup_tiled.cu, pileup_wide.cu, pileup_ws.cu)
 // on the CPU, so that indexing, sentinels, flush conditions, warp collectives and the staging protocol of a
 // kernel can be checked against the oracle without a GPU.  It models behaviour, not performance, and only the
 // constructs those kernels use:
@@ -65,6 +65,8 @@ struct Machine {
     int warp_arrived[32];
     unsigned warp_gen[32];
     uint64_t slot[32][32];
+    int named_arrived[16];
+    unsigned named_gen[16];
     unsigned long long progress = 0;
     std::vector<Deferred> deferred;  // bulk copies in flight
     const std::function<void()>* body = nullptr;
@@ -113,6 +115,20 @@ inline void warp_barrier() {
         return;
     }
     while (m.warp_gen[w] == gen) yield();
+}
+
+// bar.sync id, count: `count` threads of the block meet at named barrier `id`
+inline void named_barrier(int id, int count) {
+    Machine& m = M();
+    if (id < 0 || id >= 16) fail("emulator: named barrier id out of range");
+    const unsigned gen = m.named_gen[id];
+    if (++m.named_arrived[id] >= count) {
+        m.named_arrived[id] = 0;
+        ++m.named_gen[id];
+        ++m.progress;
+        return;
+    }
+    while (m.named_gen[id] == gen) yield();
 }
 
 template <class T>
@@ -177,6 +193,7 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
         m.n = (int)block;
         m.live = m.n;
         m.block_arrived = 0;
+        for (int k = 0; k < 16; ++k) m.named_arrived[k] = 0;
         m.deferred.clear();
         for (int w = 0; w < 32; ++w) {
             m.warp_live[w] = 0;
@@ -338,6 +355,18 @@ inline void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) 
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (reinterpret_cast<MbarBits*>(bar)->phase == (parity & 1u)) emu::yield();
 }
+inline void mbar_arrive(uint64_t* bar) {  // mbarrier.arrive: one arrival, no bytes
+    MbarBits* b = reinterpret_cast<MbarBits*>(bar);
+    if (b->pending == 0) emu::fail("emulator: mbarrier arrival beyond its count");
+    b->pending -= 1;
+    mbar_check(b);
+}
+inline void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {  // mbarrier.expect_tx: bytes, no arrival
+    reinterpret_cast<MbarBits*>(bar)->tx += (int32_t)bytes;
+}
+inline void producer_sync() { emu::named_barrier(1, 128); }  // bar.sync 1, 128
+template <int kRegs> inline void reg_dealloc() {}            // setmaxnreg: nothing to model
+template <int kRegs> inline void reg_alloc() {}
 inline void cp_async4(void* dst, const void* src) {
     if (((uintptr_t)dst & 3u) || ((uintptr_t)src & 3u)) emu::fail("emulator: cp.async 4-byte alignment");
     smem_u32(dst);

@@ -7,6 +7,7 @@
 #include "../../kindel_b200/csrc/kdl_common.cuh"
 #include "../../kindel_b200/csrc/pileup_tiled.cu"
 #include "../../kindel_b200/csrc/pileup_wide.cu"
+#include "../../kindel_b200/csrc/pileup_ws.cu"
 
 static char g_error[512];
 
@@ -14,7 +15,8 @@ extern "C" {
 
 const char* emu_last_error() { return g_error; }
 
-// variant 0 = K1f (pileup_tiled_kernel), 1 = K1x (pileup_wide_kernel), 2 = K1f with kLean.  All pointers are HOST pointers;
+// variant 0 = K1f (pileup_tiled_kernel), 1 = K1x (pileup_wide_kernel), 2 = K1f with kLean,
+// 3 = K1w (pileup_ws_kernel, WsCfg1), 4 = K1w2 (WsCfg2).  All pointers are HOST pointers;
 // `counts` is int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.
 // Returns 0, or 1 with emu_last_error() set.
 int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint32_t* tile_index, long long tile_lo,
@@ -25,8 +27,15 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
     const unsigned idx_grid = (unsigned)((n_tiles * 32 + 255) / 256);
     const char* err = emu::launch(idx_grid, 256, [&] { kdl::tile_index_kernel(b, tile_lo, n_tiles, tile_index); });
     if (!err) {
-        err = emu::launch((unsigned)grid, kdl::F_THREADS, [&] {
-            if (variant == 0) {
+        const unsigned threads = variant >= 3 ? (unsigned)kdl::W_THREADS : (unsigned)kdl::F_THREADS;
+        err = emu::launch((unsigned)grid, threads, [&] {
+            if (variant == 3) {
+                if (fresh) kdl::pileup_ws_kernel<true, kdl::WsCfg1>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
+                else kdl::pileup_ws_kernel<false, kdl::WsCfg1>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
+            } else if (variant == 4) {
+                if (fresh) kdl::pileup_ws_kernel<true, kdl::WsCfg2>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
+                else kdl::pileup_ws_kernel<false, kdl::WsCfg2>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
+            } else if (variant == 0) {
                 if (fresh) kdl::pileup_tiled_kernel<true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
                 else kdl::pileup_tiled_kernel<false>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
             } else if (variant == 2) {

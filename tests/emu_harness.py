@@ -18,7 +18,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 OUT_DIR = os.path.join(EMU_DIR, "_build")
 LIB = os.path.join(OUT_DIR, "libkdl_emu.so")
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
-K1F, K1X, K1F_LEAN = 0, 1, 2
+K1F, K1X, K1F_LEAN, K1W, K1W2 = 0, 1, 2, 3, 4
 
 _lib = None
 
@@ -31,7 +31,8 @@ def _sources():
     csrc = os.path.join(ROOT, "kindel_b200", "csrc")
     return [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "emu_pileup.cpp"),
             os.path.join(csrc, "kdl_common.cuh"), os.path.join(csrc, "pileup_tiled.cu"),
-            os.path.join(csrc, "pileup_wide.cu"), os.path.join(ROOT, "include", "kindel_b200.h")]
+            os.path.join(csrc, "pileup_wide.cu"), os.path.join(csrc, "pileup_ws.cu"),
+            os.path.join(ROOT, "include", "kindel_b200.h")]
 
 
 def load():

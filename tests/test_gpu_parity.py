@@ -542,6 +542,21 @@ def test_lean_variant_matches(monkeypatch):
     _against_oracle(synth.simple_reads(85, [151, 200, 90_000, 333], 40))
 
 
+@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="K1w2 has not been validated on a GPU yet: "
+                    "opt in with KDL_TEST_EXPERIMENTAL=1")
+def test_ws2_variant_matches(monkeypatch):
+    """K1w2 (KDL_K1F=ws2): the warp-specialised pipeline as two CTAs per SM with setmaxnreg and half-size stages."""
+    from kindel_b200 import synth
+
+    monkeypatch.setenv("KDL_K1F", "ws2")
+    _against_oracle(synth.simple_reads(91, [300_000], 150))
+    _against_oracle(synth.complex_reads(92, 30_000, 400))
+    _against_oracle(synth.simple_reads(93, [9000], 600, read_len=6000))
+    _against_oracle(synth.simple_reads(94, [500_000], 0.5))
+    _against_oracle(synth.simple_reads(95, [151, 200, 90_000, 333], 40))
+    _against_oracle(synth.simple_reads(96, [2000], 3000))
+
+
 def test_clip_heavy_cases_through_the_engine(clip_golden, tmp_path):
     """The deterministic clip-heavy cases (tests/clip_cases.py) end to end through the public API on the GPU:
     tables, --realign consensus, changes and report equal the unmodified reference's

@@ -1,4 +1,4 @@
-"""K0 + the tile-owner kernels (K1f and the experimental wide-lane K1x), SOURCE-level, on the CPU.
+"""K0 + the tile-owner kernels (K1f, K1w and the experimental K1f-lean, K1x, K1w2), SOURCE-level, on the CPU.
 
 tests/emu/ compiles kindel_b200/csrc/pileup_tiled.cu and pileup_wide.cu for the host and runs them under a
 functional model of the CUDA execution model (tests/emu/cuda_emu.h); the tables must equal the C oracle's.
@@ -26,7 +26,7 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN], ids=["K1f", "K1x", "K1f-lean"])
+@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN, E.K1W, E.K1W2], ids=["K1f", "K1x", "K1f-lean", "K1w", "K1w2"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_tile_owner_kernel_source_equals_oracle(name, variant):
     batch = CASES[name]()
@@ -37,7 +37,7 @@ def test_tile_owner_kernel_source_equals_oracle(name, variant):
         assert not got[5:].any()
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN], ids=["K1f", "K1x", "K1f-lean"])
+@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN, E.K1W, E.K1W2], ids=["K1f", "K1x", "K1f-lean", "K1w", "K1w2"])
 def test_accumulate_and_slot_ranges(variant):
     """Two batches added into one table (accumulate mode), then a fresh pass over a tile sub-range only."""
     a = synth.simple_reads(81, [20_000], 30)

@@ -1,6 +1,6 @@
 """Diagnostic (not a test): K0 + tile-owner kernel time on cfg 4 for the kernel variants, with a parity check.
 
-    SWEEP=tiled,lean,wide,ws python tools/k1f_sweep.py        (on the GPU box)
+    SWEEP=tiled,lean,ws2,wide,ws python tools/k1f_sweep.py        (on the GPU box)
 
 Each variant (KDL_K1F=...) is run on the same batch into a reused CountTable; the first variant's weight
 columns are the yardstick the others must equal bit for bit (and the first is the GPU-validated default)."""
@@ -17,7 +17,7 @@ b = synth.simple_reads(4, [5_000_000], int(os.environ.get("SWEEP_DEPTH", "200"))
 db = engine.upload(b)
 table = engine.CountTable(b.n_slots, db.device)
 want = None
-for variant in os.environ.get("SWEEP", "tiled,lean,wide,ws").split(","):
+for variant in os.environ.get("SWEEP", "tiled,lean,ws2,wide,ws").split(","):
     os.environ["KDL_K1F"] = variant
     for _ in range(3):
         engine.pileup(db, check=False, table=table)

@@ -22,7 +22,12 @@ def main(argv):
     a, b = kernels(argv[0]), kernels(argv[1])
     bad = 0
     for name in sorted(a):
-        new = name if name in b else re.sub(r"ILb([01])EE", r"ILb\1ELb0EE", name)
+        new = name
+        for pat, rep in ((None, None), (r"ILb([01])EE", r"ILb\1ELb0EE"), (r"ILb([01])EE", r"ILb\1ENS_6WsCfg1EE")):
+            cand = name if pat is None else re.sub(pat, rep, name)
+            if cand in b:
+                new = cand
+                break
         if new not in b:
             print("GONE      ", name)
             bad += 1
@@ -30,7 +35,8 @@ def main(argv):
         same = a[name] == b[new]
         bad += not same
         print("%-10s %s%s" % ("same" if same else "DIFFERENT", name, "" if new == name else "  (now " + new + ")"))
-    for name in sorted(set(b) - set(a) - {re.sub(r"ILb([01])EE", r"ILb\1ELb0EE", n) for n in a}):
+    matched = set(a) | {re.sub(r"ILb([01])EE", r"ILb\1ELb0EE", n) for n in a} | {re.sub(r"ILb([01])EE", r"ILb\1ENS_6WsCfg1EE", n) for n in a}
+    for name in sorted(set(b) - matched):
         print("new        %s (%d instructions)" % (name, len(b[name])))
     return 1 if bad else 0
 

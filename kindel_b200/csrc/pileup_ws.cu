@@ -30,6 +30,7 @@ struct WsCfg1 {
     static constexpr int kCapW = 17920;     // words of packed bases per item (70 KB)
     static constexpr int kMinBlocks = 1;
     static constexpr bool kRebalance = false;
+    static constexpr bool kLean = false;
 };
 struct WsCfg2 {
     static constexpr int kConsumers = 8;
@@ -39,6 +40,7 @@ struct WsCfg2 {
     static constexpr int kCapW = 9216;      // 36 KB: ~485 reads of 150 bases (19 words each)
     static constexpr int kMinBlocks = 2;
     static constexpr bool kRebalance = true;
+    static constexpr bool kLean = true;     // the kLean trims of pileup_tiled.cu in both roles
 };
 constexpr int W_PRODUCER_REGS = 40, W_CONSUMER_REGS = 96;  // WsCfg2 only
 constexpr int W_CONSUMERS = WsCfg1::kConsumers;
@@ -68,6 +70,8 @@ struct WsSmemT {
 };
 using WsSmem = WsSmemT<WsCfg1>;
 static_assert(sizeof(WsSmemT<WsCfg2>) <= 113 * 1024, "K1w2 must fit two CTAs per SM");
+static_assert(offsetof(WsStageT<WsCfg2>, diff) % 16 == 0 && sizeof(WsStageT<WsCfg2>) % 16 == 0,
+              "kLean reads the difference array with 128-bit loads");
 
 #ifndef KDL_HOST_EMU
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -247,7 +251,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
                             g = b.contig_slot[c] + rs[k] - tile_slot;
                         }
-                        g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
+                        if constexpr (!C::kLean) g = g < -0x10000000ll ? -0x10000000ll : (g > 0x10000000ll ? 0x10000000ll : g);
                         const int gs = (int)g;
                         int nb = 0;
                         if (l[k] > 0) {
@@ -278,7 +282,14 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
                     const int w0 = (KDL_TILE / W_PRODUCERS) * pw;
                     int pre = 0;
-                    for (int k = lane; k < w0; k += 32) pre += st.diff[k];
+                    if constexpr (C::kLean) {  // w0 is a multiple of 128, diff is 16-byte aligned
+                        for (int k = 4 * lane; k < w0; k += 128) {
+                            const int4 v4 = *reinterpret_cast<const int4*>(st.diff + k);
+                            pre += (v4.x + v4.y) + (v4.z + v4.w);
+                        }
+                    } else {
+                        for (int k = lane; k < w0; k += 32) pre += st.diff[k];
+                    }
 #pragma unroll
                     for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
                     constexpr int E = KDL_TILE / W_PRODUCERS / 32;  // entries per lane
@@ -325,6 +336,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #pragma unroll
     for (int k = 0; k < 8; ++k) { rawacc[k] = 0; covacc[k] = 0; }
     int blocks_since_flush = 0;
+    uint32_t pend8 = 0;  // kLean: weight-8 carry of an odd block, waiting for its partner
     bool stored = false;
 
     for (long long item = 0;; ++item) {
@@ -346,8 +358,13 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 covacc[0] += ca.x; covacc[1] += ca.y; covacc[2] += ca.z; covacc[3] += ca.w;
                 covacc[4] += cb.x; covacc[5] += cb.y; covacc[6] += cb.z; covacc[7] += cb.w;
             }
-            const int a = lower_bound_warp(st.gs, n_sub, wlo - maxlen + 1, lane);
-            const int e = lower_bound_warp(st.gs, n_sub, wlo + F_WIN, lane);
+            int a, e;
+            if constexpr (C::kLean) {
+                lower_bound_warp2(st.gs, n_sub, wlo - maxlen + 1, wlo + F_WIN, lane, a, e);
+            } else {
+                a = lower_bound_warp(st.gs, n_sub, wlo - maxlen + 1, lane);
+                e = lower_bound_warp(st.gs, n_sub, wlo + F_WIN, lane);
+            }
             for (int base = a & ~7; base < e; base += 32) {
                 uint32_t x[8];
                 int4 mt[8];
@@ -378,8 +395,20 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #endif
                     x[u] = __funnelshift_l(lw, hw, (uint32_t)mt[u].w);
                 }
-                acc.add8(x);
+                if constexpr (C::kLean) {
+                    const uint32_t e8 = acc.add8_carry(x);
+                    if (blocks_since_flush & 1) {  // second block of a pair: eights + eights -> sixteens, one ripple
+                        uint32_t c16;
+                        csa(c16, acc.p[3], acc.p[3], pend8, e8);
+                        acc.template ripple<4>(c16);
+                    } else {
+                        pend8 = e8;
+                    }
+                } else {
+                    acc.add8(x);
+                }
                 if (++blocks_since_flush == F_FLUSH_BLOCKS) {
+                    if constexpr (C::kLean) acc.template ripple<3>(pend8);  // F_FLUSH_BLOCKS is odd: one carry is pending
                     if (kFresh && !stored)
                         flush_window<true, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
                     else
@@ -393,6 +422,9 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[s]);
         if (flags & ITEM_LAST) {
+            if constexpr (C::kLean) {
+                if (blocks_since_flush & 1) acc.template ripple<3>(pend8);
+            }
             if (kFresh && !stored) flush_window<true, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
             else flush_window<false, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
             blocks_since_flush = 0;

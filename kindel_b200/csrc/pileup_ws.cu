@@ -153,10 +153,13 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         uint4 ix, nix;
         uint2 ic, nic;
         load_index(tile_lo + blockIdx.x, ix, ic);
+        long long cs = 0, ncs = 0;  // kLean: slot of the (next) tile's first contig, loaded a tile ahead
+        if constexpr (C::kLean) cs = b.contig_slot[ic.x];
         prefetch_raw(ix);
 
         for (long long tile = tile_lo + blockIdx.x; tile < tile_lo + n_tiles; tile += gridDim.x) {
             load_index(tile + gridDim.x, nix, nic);  // consumed at the end of this iteration
+            if constexpr (C::kLean) ncs = b.contig_slot[nic.x];
             const long long lo = ix.x, hi = ix.y;
             const long long tile_slot = tile * KDL_TILE;
             if (lo >= hi) {
@@ -169,10 +172,13 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 prefetch_raw(nix);  // nothing was in flight for an empty tile
                 ix = nix;
                 ic = nic;
+                cs = ncs;
                 continue;
             }
             const bool one_contig = ic.x == ic.y;
-            const long long slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
+            long long slot_base;
+            if constexpr (C::kLean) slot_base = one_contig ? cs - tile_slot : 0;
+            else slot_base = one_contig ? b.contig_slot[ic.x] - tile_slot : 0;
             long long c0 = lo;
             bool first = true;
             bool raw_pending = true;
@@ -316,6 +322,7 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             }
             ix = nix;
             ic = nic;
+            cs = ncs;
         }
         {   // END item
             Stage& st = acquire_stage(item);

@@ -375,6 +375,7 @@ def run_native(args):
                                      "K2p: vote over peer tables (NVLink), NCCL barrier + all_gather of call bytes"
                                      if args.exchange == "peer" else
                                      "NCCL all_reduce(int32 sum) of the 7 vote columns, vote replicated"),
+                       "k1_kernel": os.environ.get("KDL_K1F", "tiled"),  # tile-owner kernel variant (default K1f)
                        "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
             "roofline": {"bound": "hbm", "kernel": "K0 tile index + K1f tiled pileup", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, world),

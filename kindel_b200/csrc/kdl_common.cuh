@@ -5,6 +5,14 @@
 
 #include "../../include/kindel_b200.h"
 
+// The CTA's dynamic shared memory.  (KDL_HOST_EMU: tests/emu/ compiles the kernels for the host, where the
+// array is an ordinary global and `__shared__` variables are statics; the device build never defines it.)
+#ifndef KDL_HOST_EMU
+#define KDL_DYNAMIC_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#else
+#define KDL_DYNAMIC_SMEM(name) extern unsigned char name[]
+#endif
+
 namespace kdl {
 
 // BAM nibble ("=ACMGRSVTWYHKDBN") -> weight column 0..4 (A,C,G,T,N) or -1.  Only the five keys

@@ -387,7 +387,7 @@ template <bool kFresh, bool kLean = false>
 __global__ void __launch_bounds__(F_THREADS, 2)
 pileup_tiled_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KDL_DYNAMIC_SMEM(smem_raw);
     FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int quarter = lane >> 3;

@@ -128,7 +128,7 @@ template <bool kFresh>
 __global__ void __launch_bounds__(F_THREADS, 2)
 pileup_wide_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KDL_DYNAMIC_SMEM(smem_raw);
     WideSmem& sm = *reinterpret_cast<WideSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = lane >> 2;  // 8 groups of 4 lanes: 8 read streams per warp

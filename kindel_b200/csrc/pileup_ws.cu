@@ -91,7 +91,7 @@ template <bool kFresh, class C = WsCfg1>
 __global__ void __launch_bounds__(W_THREADS, C::kMinBlocks)
 pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                  const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KDL_DYNAMIC_SMEM(smem_raw);
     using Smem = WsSmemT<C>;
     using Stage = WsStageT<C>;
     constexpr int W_STAGES = C::kStages, W_RMAX = C::kRmax, W_CAPW = C::kCapW;

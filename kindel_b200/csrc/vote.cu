@@ -105,6 +105,7 @@ struct Exchange {
     int rank;
 };
 
+#ifndef KDL_HOST_EMU
 __device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
     int v;
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -113,6 +114,7 @@ __device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
 __device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+#endif  // KDL_HOST_EMU (tests/emu/ supplies stand-ins)
 
 // "my table is complete": runs after the pileup kernels in stream order
 __global__ void exchange_signal_kernel(Exchange x, int epoch) {

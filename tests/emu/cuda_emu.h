@@ -31,6 +31,8 @@
 #include <vector>
 
 #define __launch_bounds__(...)
+#undef __shared__
+#define __shared__ static  // blocks run one after another, so a static is shared by exactly one block's threads
 
 uint3 threadIdx, blockIdx;
 dim3 blockDim, gridDim;
@@ -177,18 +179,19 @@ inline void trampoline() {
 }
 
 // run `body` as a grid of `grid` blocks of `block` threads; returns nullptr or an error text
-inline const char* launch(unsigned grid, unsigned block, const std::function<void()>& body) {
+inline const char* launch(unsigned grid, unsigned block, const std::function<void()>& body, unsigned block_y = 0,
+                          unsigned grid_y = 1) {
     Machine& m = M();
     m.error[0] = 0;
     if (block > 1024 || block == 0 || grid == 0) return "emulator: bad launch configuration";
     if ((int)m.fibres.size() < (int)block) m.fibres.resize(block);
     for (unsigned t = 0; t < block; ++t)
         if (!m.fibres[t].stack) m.fibres[t].stack = (char*)malloc(kStack);
-    gridDim = dim3(grid, 1, 1);
+    gridDim = dim3(grid, grid_y, 1);
     blockDim = dim3(block, 1, 1);
     m.body = &body;
     for (unsigned b = 0; b < grid && !m.error[0]; ++b) {
-        blockIdx.x = b; blockIdx.y = blockIdx.z = 0;
+        blockIdx.x = b; blockIdx.y = block_y; blockIdx.z = 0;
         memset(kdl::smem_raw, 0xCD, sizeof kdl::smem_raw);
         m.n = (int)block;
         m.live = m.n;
@@ -242,6 +245,12 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
     return m.error[0] ? m.error : nullptr;
 }
 
+// the row blockIdx.y = block_y of a two-dimensional grid (grid x grid_y blocks)
+inline const char* launch_y(unsigned grid, unsigned block_y, unsigned grid_y, unsigned block,
+                            const std::function<void()>& body) {
+    return launch(grid, block, body, block_y, grid_y);
+}
+
 }  // namespace emu
 
 // ---- the CUDA built-ins the kernels use ---------------------------------------------------------------------
@@ -290,6 +299,13 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift) {
     return (uint32_t)(((((uint64_t)hi << 32) | lo) << (shift & 31)) >> 32);
 }
+inline int atomicOr(int* p, int v) { const int old = *p; *p = old | v; return old; }
+inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+    const unsigned long long old = *p; if (v < old) *p = v; return old;
+}
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline void __nanosleep(unsigned) { emu::yield(); }  // only ever called inside a polling loop
 inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { const unsigned old = *p; *p = old + v; return old; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
@@ -367,6 +383,10 @@ inline void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {  // mbarrier.ex
 inline void producer_sync() { emu::named_barrier(1, 128); }  // bar.sync 1, 128
 template <int kRegs> inline void reg_dealloc() {}            // setmaxnreg: nothing to model
 template <int kRegs> inline void reg_alloc() {}
+// system-scope flag accesses of the exchange kernels (vote.cu): plain accesses here; a poll yields, so a flag
+// that never arrives shows up as a deadlock
+inline int ld_acquire_sys(const int32_t* p) { return *p; }
+inline void st_release_sys(int32_t* p, int v) { *p = v; ++emu::M().progress; }
 inline void cp_async4(void* dst, const void* src) {
     if (((uintptr_t)dst & 3u) || ((uintptr_t)src & 3u)) emu::fail("emulator: cp.async 4-byte alignment");
     smem_u32(dst);

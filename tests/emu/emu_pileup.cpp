@@ -4,10 +4,15 @@
 #define KDL_HOST_EMU 1
 #include "cuda_emu.h"
 
+#include <vector>
+
 #include "../../kindel_b200/csrc/kdl_common.cuh"
 #include "../../kindel_b200/csrc/pileup_tiled.cu"
 #include "../../kindel_b200/csrc/pileup_wide.cu"
 #include "../../kindel_b200/csrc/pileup_ws.cu"
+#include "../../kindel_b200/csrc/pileup_general.cu"
+#include "../../kindel_b200/csrc/pileup_simple.cu"
+#include "../../kindel_b200/csrc/vote.cu"
 
 static char g_error[512];
 
@@ -50,6 +55,103 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
     if (err) {
         snprintf(g_error, sizeof g_error, "%s", err);
         return 1;
+    }
+    return 0;
+}
+
+#define EMU_RUN(grid, block, ...)                                              \
+    do {                                                                        \
+        const char* e_ = emu::launch((unsigned)(grid), (unsigned)(block), [&] { __VA_ARGS__; }); \
+        if (e_) { snprintf(g_error, sizeof g_error, "%s", e_); return 1; }      \
+    } while (0)
+
+// The other pileup kernels, as kdl_pileup_range launches them: K1s (atomic fallback, all simple reads of an
+// unsorted batch) and K1g (complex reads).  grid is kept small on purpose so the grid-stride loops stride.
+int emu_pileup_simple(const kdl_batch* batch, int32_t* counts, long long n_slots, int32_t* err_flag, int grid) {
+    g_error[0] = 0;
+    const kdl_batch b = *batch;
+    EMU_RUN(grid, 256, kdl::pileup_simple_atomic_kernel(b, counts, n_slots, err_flag));
+    return 0;
+}
+int emu_pileup_general(const kdl_batch* batch, int32_t* counts, long long n_slots, int32_t* ins_events,
+                       int32_t* err_flag, int grid) {
+    g_error[0] = 0;
+    const kdl_batch b = *batch;
+    if (b.n_complex > 0) EMU_RUN(grid, 256, kdl::pileup_general_kernel(b, counts, n_slots, ins_events, err_flag));
+    return 0;
+}
+int emu_diagnose(const kdl_batch* batch, kdl_diag* diag) {
+    g_error[0] = 0;
+    const kdl_batch b = *batch;
+    EMU_RUN(1, 1, kdl::diagnose_init_kernel(diag));
+    if (b.n_complex > 0) EMU_RUN((b.n_complex + 255) / 256, 256, kdl::diagnose_kernel(b, diag));
+    EMU_RUN(1, 1, kdl::diagnose_final_kernel(diag));
+    return 0;
+}
+int emu_vote(const int32_t* counts, long long n_slots, long long min_depth_ceil, uint8_t* calls) {
+    g_error[0] = 0;
+    kdl::Peers none;
+    none.n = 0;
+    EMU_RUN((n_slots / 4 + 255) / 256, 256,
+            kdl::vote_kernel<false>(counts, none, n_slots, 0, n_slots, min_depth_ceil, calls, nullptr));
+    return 0;
+}
+int emu_derive(const int32_t* counts, long long n_slots, int32_t* out) {
+    g_error[0] = 0;
+    EMU_RUN((n_slots + 255) / 256, 256, kdl::derive_kernel(counts, n_slots, out));
+    return 0;
+}
+// K2p: vote over the SUM of several tables, each non-zero only inside its footprint [lo, hi)
+int emu_vote_peers(const int32_t* const* tables, const long long* lo, const long long* hi, int n, long long n_slots,
+                   long long slot_lo, long long slot_hi, long long min_depth_ceil, uint8_t* calls, int32_t* reduced) {
+    g_error[0] = 0;
+    kdl::Peers peers;
+    peers.n = n;
+    for (int p = 0; p < n; ++p) {
+        peers.tab[p] = tables[p];
+        peers.lo[p] = lo ? lo[p] : 0;
+        peers.hi[p] = hi ? hi[p] : n_slots;
+    }
+    const long long quads = (slot_hi - slot_lo + 3) / 4;
+    EMU_RUN((quads + 255) / 256, 256,
+            kdl::vote_kernel<true>(nullptr, peers, n_slots, slot_lo, slot_hi, min_depth_ceil, calls, reduced));
+    return 0;
+}
+// One epoch of the fused exchange for ALL ranks on one machine: every rank's K2x (publish ready, wait for the
+// peers' tables, reduce + vote its slice, publish done) and then every rank's K2g (pull the peers' call slices).
+// A kernel runs to completion here, so rank r's K2x could never see a flag that a LATER kernel sets: like
+// kdl_exchange_signal on the device, the ready flags are published first.
+int emu_exchange_epoch(const kdl_exchange* xs, int n_ranks, long long n_slots, long long min_depth_ceil, int epoch,
+                       int grid) {
+    g_error[0] = 0;
+    std::vector<kdl::Exchange> ex(n_ranks);
+    for (int r = 0; r < n_ranks; ++r) {
+        const kdl_exchange& x = xs[r];
+        kdl::Exchange& e = ex[r];
+        e.peers.n = x.n_ranks;
+        e.rank = x.rank;
+        e.counter = x.counter;
+        for (int p = 0; p < x.n_ranks; ++p) {
+            e.peers.tab[p] = x.tables[p];
+            e.peers.lo[p] = x.foot_lo[p];
+            e.peers.hi[p] = x.foot_hi[p] > n_slots ? n_slots : x.foot_hi[p];
+            e.calls[p] = x.calls[p];
+            e.ready[p] = x.ready[p];
+            e.done[p] = x.done[p];
+            e.slice_lo[p] = x.slice_lo[p];
+            e.slice_hi[p] = x.slice_hi[p];
+        }
+        e.ready_local = x.ready[x.rank];
+        e.done_local = x.done[x.rank];
+    }
+    for (int r = 0; r < n_ranks; ++r) EMU_RUN(1, 32, kdl::exchange_signal_kernel(ex[r], epoch));
+    for (int r = 0; r < n_ranks; ++r) EMU_RUN(grid, 256, kdl::vote_exchange_kernel(ex[r], n_slots, min_depth_ceil, epoch));
+    for (int r = 0; r < n_ranks; ++r) {
+        for (int p = 0; p < n_ranks; ++p) {  // blockIdx.y = peer: the emulator's grid is one-dimensional
+            const char* e_ = emu::launch_y((unsigned)grid, (unsigned)p, (unsigned)n_ranks, 256,
+                                           [&] { kdl::exchange_gather_kernel(ex[r], epoch); });
+            if (e_) { snprintf(g_error, sizeof g_error, "%s", e_); return 1; }
+        }
     }
     return 0;
 }

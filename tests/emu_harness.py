@@ -54,8 +54,22 @@ def load():
     lib.emu_pileup.restype = C.c_int
     lib.emu_pileup.argtypes = [C.POINTER(_ffi.KdlBatch), C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                C.c_longlong, C.c_int, C.c_int, C.c_int]
+    vp = C.c_void_p
+    lib.emu_pileup_simple.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, C.c_int]
+    lib.emu_pileup_general.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, vp, C.c_int]
+    lib.emu_diagnose.argtypes = [C.POINTER(_ffi.KdlBatch), C.POINTER(_ffi.KdlDiag)]
+    lib.emu_vote.argtypes = [vp, C.c_longlong, C.c_longlong, vp]
+    lib.emu_derive.argtypes = [vp, C.c_longlong, vp]
+    lib.emu_vote_peers.argtypes = [C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int,
+                                   C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
+    lib.emu_exchange_epoch.argtypes = [C.POINTER(_ffi.KdlExchange), C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
     _lib = lib
     return lib
+
+
+def _check(rc):
+    if rc:
+        raise RuntimeError(_lib.emu_last_error().decode())
 
 
 def run_pileup(batch, variant: int, fresh: bool, grid: int = 5, tile_lo: int = 0, n_tiles: int = None,
@@ -82,3 +96,97 @@ def run_pileup(batch, variant: int, fresh: bool, grid: int = 5, tile_lo: int = 0
     if rc:
         raise RuntimeError(lib.emu_last_error().decode())
     return counts
+
+
+def pileup_pipeline(batch, variant: int = K1F, grid: int = 3):
+    """What kdl_pileup does, kernel by kernel, under the emulator: K0 + tile-owner kernel (sorted, tileable
+    batches) or K1s (anything else) for the simple reads, K1g for the complex ones; on a raised error flag,
+    the diagnose kernels.  Returns (counts [19, n_slots], events [n_events, 4]) or raises IndexError /
+    KeyError(base) exactly like kindel_b200.engine.pileup."""
+    from kindel_b200 import _ffi, engine
+
+    lib = load()
+    st, keep = engine.host_struct(batch)
+    n_slots = int(batch.n_slots)
+    counts = np.zeros((19, n_slots), dtype=np.int32)
+    events = np.zeros((max(int(batch.n_events), 1), 4), dtype=np.int32)
+    flag = np.zeros(4, dtype=np.int32)
+    n_cx = len(batch.complex_idx)
+    has_simple = batch.n_reads > n_cx
+    tiled = (has_simple and n_slots % 512 == 0 and bool(batch.reads_sorted) and 0 < int(batch.max_simple_len) <= _ffi.KDL_FAST_MAXLEN)
+    if batch.n_reads:
+        if tiled:
+            index = np.zeros(8 * (n_slots // 512), dtype=np.uint32)
+            _check(lib.emu_pileup(C.byref(st), counts.ctypes.data, n_slots, index.ctypes.data, 0, n_slots // 512,
+                                  variant, 0, grid))
+        elif has_simple:
+            _check(lib.emu_pileup_simple(C.byref(st), counts.ctypes.data, n_slots, flag.ctypes.data, grid))
+        _check(lib.emu_pileup_general(C.byref(st), counts.ctypes.data, n_slots, events.ctypes.data, flag.ctypes.data, grid))
+    if flag[0]:
+        diag = _ffi.KdlDiag()
+        _check(lib.emu_diagnose(C.byref(st), C.byref(diag)))
+        assert diag.status, "error flag raised but no offending read found"
+        engine.raise_like_reference(diag.status, diag.read, diag.nibble, diag.op_index)
+    del keep
+    return counts, events[: int(batch.n_events)]
+
+
+def vote(counts: np.ndarray, min_depth=1) -> np.ndarray:
+    import math
+
+    lib = load()
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    calls = np.zeros(counts.shape[1], dtype=np.uint8)
+    _check(lib.emu_vote(counts.ctypes.data, counts.shape[1], int(math.ceil(min_depth)), calls.ctypes.data))
+    return calls
+
+
+def derive(counts: np.ndarray) -> np.ndarray:
+    lib = load()
+    counts = np.ascontiguousarray(counts, dtype=np.int32)
+    out = np.zeros((5, counts.shape[1]), dtype=np.int32)
+    _check(lib.emu_derive(counts.ctypes.data, counts.shape[1], out.ctypes.data))
+    return out
+
+
+def vote_peers(tables, feet, slot_lo, slot_hi, min_depth=1, want_reduced=False):
+    """K2p over host tables: vote of the SUM of `tables` on [slot_lo, slot_hi); feet = [(lo, hi)] or None."""
+    import math
+
+    lib = load()
+    n = len(tables)
+    n_slots = tables[0].shape[1]
+    ptrs = (C.c_void_p * n)(*[t.ctypes.data for t in tables])
+    lo = (C.c_longlong * n)(*[f[0] for f in feet]) if feet else None
+    hi = (C.c_longlong * n)(*[f[1] for f in feet]) if feet else None
+    calls = np.zeros(n_slots, dtype=np.uint8)
+    reduced = np.zeros((7, n_slots), dtype=np.int32) if want_reduced else None
+    _check(lib.emu_vote_peers(ptrs, lo, hi, n, n_slots, slot_lo, slot_hi, int(math.ceil(min_depth)), calls.ctypes.data,
+                              reduced.ctypes.data if want_reduced else None))
+    return (calls, reduced) if want_reduced else calls
+
+
+def exchange_epoch(tables, feet, slices, calls, flags, epoch, min_depth=1, grid=3):
+    """One epoch of the fused multi-GPU exchange (K2x on every rank, then K2g on every rank) with the ranks'
+    buffers in host memory.  tables[r]: int32 [19, n_slots]; calls[r]: uint8 [n_slots]; flags: dict of per-rank
+    int32 arrays 'ready', 'done' (16 each) and 'counter' (1), persistent across epochs."""
+    import math
+
+    from kindel_b200 import _ffi
+
+    lib = load()
+    n = len(tables)
+    n_slots = tables[0].shape[1]
+    xs = (_ffi.KdlExchange * n)()
+    for r in range(n):
+        x = xs[r]
+        x.n_ranks, x.rank = n, r
+        for p in range(n):
+            x.tables[p] = tables[p].ctypes.data
+            x.calls[p] = calls[p].ctypes.data
+            x.ready[p] = flags["ready"][p].ctypes.data
+            x.done[p] = flags["done"][p].ctypes.data
+            x.foot_lo[p], x.foot_hi[p] = feet[p]
+            x.slice_lo[p], x.slice_hi[p] = slices[p]
+        x.counter = flags["counter"][r].ctypes.data
+    _check(lib.emu_exchange_epoch(xs, n, n_slots, int(math.ceil(min_depth)), epoch, grid))

@@ -63,3 +63,106 @@ def test_emulator_catches_a_staging_bug(tmp_path):
     lib = E.load()
     assert lib.emu_selftest_missing_wait() == 1   # data read before mbar_wait differs from the source
     assert lib.emu_selftest_missing_wait_fixed() == 0
+
+
+# ---- the rest of the kernels: K1s, K1g, diagnose, K2 (vote), derive, K2p (peer vote) ------------------------
+def _oracle_outcome(batch):
+    try:
+        return None, coracle.pileup(batch)
+    except IndexError:
+        return ("IndexError",), None
+    except KeyError as exc:
+        return ("KeyError", exc.args[0]), None
+
+
+def test_whole_pipeline_on_the_fuzz_cases(tmp_path):
+    """Every kernel kdl_pileup / kdl_vote / kdl_derive / kdl_diagnose launches, source-level, on the 400 random
+    alignments of tests/fuzz_cases.py: tables, insertion events, calls, derived columns and the exception
+    (type and KeyError argument) equal the oracle's."""
+    from fuzz_cases import random_case
+
+    from kindel_b200 import bamio
+
+    raised = done = 0
+    for seed in range(400):
+        path = tmp_path / ("fuzz%d.sam" % seed)
+        path.write_text(random_case(seed))
+        try:
+            batch = bamio.read_alignment(path)
+        except (ValueError, KeyError):
+            continue
+        err, res = _oracle_outcome(batch)
+        if err:
+            raised += 1
+            with pytest.raises({"IndexError": IndexError, "KeyError": KeyError}[err[0]]) as exc:
+                E.pileup_pipeline(batch)
+            if err[0] == "KeyError":
+                assert exc.value.args[0] == err[1], seed
+            continue
+        counts, events = res
+        got_c, got_e = E.pileup_pipeline(batch)
+        np.testing.assert_array_equal(got_c, counts, err_msg=str(seed))
+        np.testing.assert_array_equal(got_e, events, err_msg=str(seed))
+        if seed % 4 == 0:
+            np.testing.assert_array_equal(E.vote(got_c, 2), coracle.vote(counts, 2), err_msg=str(seed))
+            np.testing.assert_array_equal(E.derive(got_c), coracle.derive(counts), err_msg=str(seed))
+        done += 1
+    assert raised > 20 and done > 20
+
+
+@pytest.mark.parametrize("variant", [E.K1F, E.K1F_LEAN, E.K1W2], ids=["K1f", "K1f-lean", "K1w2"])
+def test_mixed_batch_pipeline(variant):
+    """Config-3 shape (clips, indels, edge-case tail; most reads complex, some simple): the tile-owner kernel takes
+    the simple reads, K1g the rest, into one table."""
+    batch = synth.complex_reads(72, 6000, 60)
+    want_c, want_e = coracle.pileup(batch)
+    got_c, got_e = E.pileup_pipeline(batch, variant)
+    np.testing.assert_array_equal(got_c, want_c)
+    np.testing.assert_array_equal(got_e, want_e)
+    np.testing.assert_array_equal(E.vote(got_c, 1), coracle.vote(want_c, 1))
+    np.testing.assert_array_equal(E.vote(got_c, 7), coracle.vote(want_c, 7))
+    np.testing.assert_array_equal(E.derive(got_c), coracle.derive(want_c))
+
+
+def test_peer_vote_over_footprints():
+    """K2p: the vote of the sum of per-rank tables, each read only inside its footprint, on an owner slice."""
+    from kindel_b200 import distributed as D
+
+    batch = synth.complex_reads(73, 5000, 40)
+    full, _ = coracle.pileup(batch)
+    shards = [D.shard_batch(batch, r, 3) for r in range(3)]
+    tables = [coracle.pileup(s)[0] for s in shards]
+    feet = [D.footprint(s) for s in shards]
+    np.testing.assert_array_equal(sum(tables), full)
+    want = coracle.vote(full, 2)
+    n_slots = full.shape[1]
+    for lo, hi in D.owner_slices(n_slots, 3):
+        calls, reduced = E.vote_peers(tables, feet, lo, hi, 2, want_reduced=True)
+        np.testing.assert_array_equal(calls[lo:hi], want[lo:hi])
+        np.testing.assert_array_equal(reduced[:, lo:hi], full[:7, lo:hi])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_exchange_epochs(world):
+    """K2x + K2g for all ranks of a read-sharded pileup, two epochs with different data (flags compare epochs):
+    every rank ends up with the complete call bytes of the summed table."""
+    from kindel_b200 import distributed as D
+
+    flags = {k: [np.zeros(16, dtype=np.int32) for _ in range(world)] for k in ("ready", "done")}
+    flags["counter"] = [np.zeros(1, dtype=np.int32) for _ in range(world)]
+    calls = None
+    for epoch, seed in ((1, 74), (2, 75)):
+        batch = synth.complex_reads(seed, 7000, 30)
+        full, _ = coracle.pileup(batch)
+        shards = [D.shard_batch(batch, r, world) for r in range(world)]
+        tables = [coracle.pileup(s)[0] for s in shards]
+        feet = [D.footprint(s) for s in shards]
+        n_slots = full.shape[1]
+        slices = D.owner_slices(n_slots, world)
+        if calls is None:
+            calls = [np.full(n_slots, 0xEE, dtype=np.uint8) for _ in range(world)]
+        E.exchange_epoch(tables, feet, slices, calls, flags, epoch, min_depth=2)
+        want = coracle.vote(full, 2)
+        for r in range(world):
+            np.testing.assert_array_equal(calls[r], want, err_msg="epoch %d rank %d" % (epoch, r))
+            assert (flags["ready"][r][:world] == epoch).all() and (flags["done"][r][:world] == epoch).all()

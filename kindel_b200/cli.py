@@ -2,7 +2,8 @@
 
 Sub-commands, flags, defaults and output streams follow the reference: `consensus` prints the
 REPORT blocks to stderr and one `>name` / sequence pair per contig to stdout (cli.py:30-33),
-`weights` / `features` write TSV to stdout (cli.py:44,50), `version` prints `kindel <version>`.
+`weights` / `features` write TSV to stdout (cli.py:44,50), `version` prints `kindel <version>`;
+`variants` (in the reference's README only) is an extension, see kindel.variants.
 argh derived the flags from the function signatures (first letter as short option unless two
 parameters share it); argparse spells the same set out.  Note the CLI default `--min-overlap 7`
 (cli.py:13) differs from the API default 9 (kindel.py:492), as in the reference.
@@ -40,6 +41,14 @@ def features(bam_path):
     from . import kindel
 
     kindel.features(bam_path).to_csv(sys.stdout, sep="\t", index=False)
+
+
+def variants(bam_path, abs_threshold=1, rel_threshold=0.01, only_variants=False, absolute=False):
+    """Output variants exceeding specified absolute and relative frequency thresholds"""
+    from . import kindel
+
+    kindel.variants(bam_path, abs_threshold, rel_threshold, only_variants, absolute).to_csv(sys.stdout, sep="\t",
+                                                                                            index=False)
 
 
 def plot(bam_path):
@@ -86,6 +95,16 @@ def build_parser() -> argparse.ArgumentParser:
     p = sub.add_parser("features", help=features.__doc__, description=features.__doc__, formatter_class=fmt)
     p.add_argument("bam_path", help="path to SAM/BAM file")
     p.set_defaults(func=lambda a: features(a.bam_path))
+
+    # `variants` is listed by the reference's README (README.md:106-107) but absent from its code: an extension here
+    p = sub.add_parser("variants", help=variants.__doc__, description=variants.__doc__, formatter_class=fmt)
+    p.add_argument("bam_path", help="path to SAM/BAM file")
+    p.add_argument("-a", "--abs-threshold", type=int, default=1, help="absolute frequency above which to call variants")
+    p.add_argument("-r", "--rel-threshold", type=float, default=0.01,
+                   help="relative frequency (0.0-1.0) above which to call variants")
+    p.add_argument("-o", "--only-variants", action="store_true", help="exclude invariant sites from output")
+    p.add_argument("--absolute", action="store_true", help="report absolute variant frequencies")
+    p.set_defaults(func=lambda a: variants(a.bam_path, a.abs_threshold, a.rel_threshold, a.only_variants, a.absolute))
 
     p = sub.add_parser("plot", help=plot.__doc__, description=plot.__doc__, formatter_class=fmt)
     p.add_argument("bam_path", help="path to SAM/BAM file")

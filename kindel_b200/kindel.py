@@ -529,6 +529,51 @@ def weights_from_run(run, relative=False, confidence=True, confidence_alpha=0.01
     return weights_df.round(dict(consensus=3, lower_ci=3, upper_ci=3, shannon=3))
 
 
+def variants(bam_path: "path to SAM/BAM file", abs_threshold: "absolute frequency above which to call variants" = 1,
+             rel_threshold: "relative frequency (0.0-1.0) above which to call variants" = 0.01,
+             only_variants: "exclude invariant sites from output" = False,
+             absolute: "report absolute variant frequencies" = False):
+    """EXTENSION -- not in the reference snapshot.  The reference's README (README.md:106-107) lists a `variants`
+    sub-command ("Output variants exceeding specified absolute and relative frequency thresholds") but its code
+    (kindel/kindel.py, kindel/cli.py) has no such function, so there is nothing to be bit-exact with: parity
+    unpinned.  Defined here as a host-side filter over the same integer table `weights`
+    reports: per site, every allele (A, C, G, T, N, deletion) other than the site's most frequent one whose count
+    exceeds `abs_threshold` AND whose share of the depth (A+C+G+T+N+deletions, as in `weights`) exceeds
+    `rel_threshold`.  Columns: chrom, pos, depth, consensus (allele letter, `-` = deletion), then one column per
+    allele holding its relative (default) or absolute frequency where it is a variant and 0 elsewhere."""
+    return variants_from_run(PileupRun(bamio.read_alignment(bam_path)), abs_threshold, rel_threshold, only_variants,
+                             absolute)
+
+
+def variants_from_run(run, abs_threshold=1, rel_threshold=0.01, only_variants=False, absolute=False):
+    """Host half of `variants` (extension; see there)."""
+    import pandas as pd
+
+    tab = run.host_counts
+    alleles = ["A", "C", "G", "T", "N", "deletions"]
+    rows = [0, 1, 2, 3, 4, 5]
+    frames = []
+    for c, chrom in enumerate(run.batch.contig_names):
+        s, e = run.contig_slice(c)
+        L = e - s - 1
+        t = tab[rows, s:s + L].astype(np.int64)                       # [6, L]
+        depth = t.sum(axis=0)
+        top = t.argmax(axis=0)                                        # first maximum in A,C,G,T,N,del order
+        with np.errstate(invalid="ignore", divide="ignore"):
+            share = np.where(depth > 0, t / np.maximum(depth, 1), 0.0)
+        is_var = (t > abs_threshold) & (share > rel_threshold) & (np.arange(6)[:, None] != top[None, :])
+        value = np.where(is_var, t if absolute else np.round(share, 4), 0)
+        df = pd.DataFrame({"chrom": [chrom] * L, "pos": np.arange(1, L + 1, dtype=np.int64), "depth": depth,
+                           "consensus": np.where(depth > 0, np.array(list("ACGTN-"))[top], "N")})
+        for k, a in enumerate(alleles):
+            df[a] = value[k]
+        if only_variants:
+            df = df[is_var.any(axis=0)]
+        frames.append(df)
+    cols = ["chrom", "pos", "depth", "consensus"] + alleles
+    return pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=cols)
+
+
 def features(bam_path: "path to SAM/BAM file"):
     """DataFrame of relative per-site nucleotide frequencies, indels and entropy
     (reference kindel/kindel.py:633-664), including its indexing of `i`/`d` by global row number

@@ -224,3 +224,29 @@ def test_bam_gather_flags_exotic_bases(tmp_path):
     b2 = bamio.read_alignment(sam)
     np.testing.assert_array_equal(b2.l_seq, b.l_seq)
     np.testing.assert_array_equal(b2.seq4, b.seq4)
+
+
+def test_variants_extension(tmp_path):
+    """`variants` (extension, no reference code to pin against): thresholds, consensus exclusion, deletions."""
+    sam = ["@HD\tVN:1.6", "@SQ\tSN:v\tLN:8"]
+    reads = ["ACGTACGT"] * 6 + ["ACGAACGT"] * 3 + ["ACGTACTT"] * 1     # pos 4: T6 A3; pos 7: G9 T1
+    for k, seq in enumerate(reads):
+        sam.append("r%d\t0\tv\t1\t60\t8M\t*\t0\t0\t%s\t*" % (k, seq))
+    sam.append("d0\t0\tv\t1\t60\t2M2D4M\t*\t0\t0\tACACGT\t*")              # deletion over pos 3-4
+    sam.append("d1\t0\tv\t1\t60\t2M2D4M\t*\t0\t0\tACACGT\t*")
+    path = tmp_path / "v.sam"
+    path.write_text("\n".join(sam) + "\n")
+    run, _ = oracle_run(path)
+    df = K.variants_from_run(run)
+    assert list(df.columns) == ["chrom", "pos", "depth", "consensus", "A", "C", "G", "T", "N", "deletions"]
+    assert df["depth"].tolist() == [12] * 8 and "".join(df["consensus"]) == "ACGTACGT"
+    row4, row7, row3 = df.iloc[3], df.iloc[6], df.iloc[2]
+    assert row4["A"] == round(3 / 12, 4) and row4["deletions"] == round(2 / 12, 4) and row4["T"] == 0
+    assert row7["T"] == 0                      # a single read does not exceed abs_threshold = 1
+    assert row3["deletions"] == round(2 / 12, 4) and row3["G"] == 0
+    only = K.variants_from_run(run, only_variants=True, absolute=True)
+    assert only["pos"].tolist() == [3, 4] and only.iloc[1]["A"] == 3 and only.iloc[1]["deletions"] == 2
+    assert K.variants_from_run(run, abs_threshold=0, rel_threshold=0.05, only_variants=True)["pos"].tolist() == [3, 4, 7]
+    assert K.variants_from_run(run, rel_threshold=0.2, only_variants=True)["pos"].tolist() == [4]
+    a = cli.build_parser().parse_args(["variants", "-a", "2", "-r", "0.1", "-o", "--absolute", "x.bam"])
+    assert (a.abs_threshold, a.rel_threshold, a.only_variants, a.absolute) == (2, 0.1, True, True)

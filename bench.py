@@ -327,6 +327,9 @@ def run_native(args):
             tpin = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory() if a.size else None
             pinned[f] = tpin
         ptr = {f: (int(tp.data_ptr()) if tp is not None else None) for f, tp in pinned.items()}
+        if args.derive_seq_off:  # 4 bytes per read less over PCIe: the device derives the word offsets (scan.cu)
+            assert engine.seq_is_dense(batch)
+            ptr["seq_off"] = None
         struct = engine.make_struct(batch, ptr)
         calls_host = torch.empty(n_slots, dtype=torch.uint8).pin_memory()
         calls_np = calls_host.numpy()
@@ -348,7 +351,8 @@ def run_native(args):
         # every rank copies its own shard in and its calls out; with N > 1 this leg runs the shards
         # concurrently but does not reduce across ranks (the reduction is in `value`'s step)
         e2e = {"value": total_bases / (float(tt[0]) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": batch.input_bytes(), "d2h_bytes_per_step": int(n_slots) + 16,
+               "h2d_bytes_per_step": batch.input_bytes() - (4 * int(batch.n_reads) if args.derive_seq_off else 0),
+               "d2h_bytes_per_step": int(n_slots) + 16,
                "ms_per_step": float(tt[0]), "wall_ms_per_step": float(tt[1]),
                "breakdown_ms": {k: statistics.mean(x[2][k] for x in e2e_ms) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
                "api": "kdl_ctx_consensus (include/kindel_b200.h), pinned host buffers",
@@ -404,6 +408,8 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4_5Mb_200x")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--derive-seq-off", action="store_true",
+                    help="e2e leg: leave seq_off on the host and derive it on the device (dense layouts; scan.cu)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="N > 1: weak = the full per-GPU workload on every rank (N x deeper in total); "
                          "strong = the N = 1 data set cut N ways")

@@ -228,7 +228,10 @@ typedef struct kdl_ctx kdl_ctx;
 int kdl_ctx_create(int device, kdl_ctx** out);
 void kdl_ctx_destroy(kdl_ctx* ctx);
 
-/* batch holds HOST pointers.  Outputs (host, caller-allocated, any may be NULL to skip):
+/* batch holds HOST pointers.  batch->seq_off may be NULL: the packed bases are then taken to be DENSE (read i
+ * starts at the sum of ceil(l_seq[j] / 8) words over j < i, as every flattener here lays them out) and the
+ * offsets are computed on the device instead of being copied (4 bytes per read less over PCIe).
+ * Outputs (host, caller-allocated, any may be NULL to skip):
  *   calls_out[n_slots] uint8, counts_out[KDL_NCOL][n_slots] int32,
  *   ins_events_out[n_events][4] int32.  diag_out is always filled.
  * Returns KDL_OK, or KDL_ERR_INDEX / KDL_ERR_KEY with diag_out describing the first offender. */

@@ -13,6 +13,13 @@
 #include "pileup_wide.cu"
 #include "vote.cu"
 
+namespace kdl {
+// scan.cu is its own translation unit (so that adding it leaves the code generated for the kernels above
+// untouched); its launcher:
+int launch_seq_off_scan(const int32_t* l_seq, long long n, uint32_t* block_sums, uint32_t* seq_off, cudaStream_t st);
+long long seq_off_scan_blocks(long long n);
+}  // namespace kdl
+
 namespace {
 
 std::atomic<long long> g_launches{0};

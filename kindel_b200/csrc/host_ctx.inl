@@ -18,7 +18,7 @@ struct kdl_ctx {
         size_t cap = 0;
     };
     enum { B_REF_START, B_SEQ_OFF, B_L_SEQ, B_CIG_OFF, B_CIGAR, B_SEQ4, B_CREAD_OFF, B_CLEN, B_CSLOT,
-           B_CX_IDX, B_EVT_OFF, B_COUNTS, B_EVENTS, B_CALLS, B_FLAG, B_DIAG, B_TILE_IDX, B_N };
+           B_CX_IDX, B_EVT_OFF, B_COUNTS, B_EVENTS, B_CALLS, B_FLAG, B_DIAG, B_TILE_IDX, B_SCAN, B_N };
     Buf buf[B_N];
 
     int ensure(int which, size_t bytes) {
@@ -78,8 +78,12 @@ void kdl_ctx_destroy(kdl_ctx* c) {
 int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t n_events,
                       int64_t min_depth_ceil, uint8_t* calls_out, int32_t* counts_out,
                       int32_t* ins_events_out, kdl_diag* diag_out) {
-    if (!c || !diag_out) return KDL_ERR_INVALID_ARG;
-    int rc = validate_batch(hb);
+    if (!c || !diag_out || !hb) return KDL_ERR_INVALID_ARG;
+    // seq_off == NULL: the packed bases are dense and the offsets are derived on the device (scan.cu)
+    const bool derive_seq_off = hb->n_reads > 0 && hb->seq_off == nullptr && hb->l_seq != nullptr;
+    kdl_batch checked = *hb;
+    if (derive_seq_off) checked.seq_off = reinterpret_cast<const uint32_t*>(hb->l_seq);  // any non-null pointer
+    int rc = validate_batch(&checked);
     if (rc != KDL_OK) return rc;
     if (n_slots <= 0 || (n_slots & 3) || n_events < 0) return KDL_ERR_INVALID_ARG;
     if (cudaSetDevice(c->device) != cudaSuccess) return KDL_ERR_CUDA;
@@ -109,6 +113,8 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     if ((rc = c->ensure(kdl_ctx::B_FLAG, 16)) != KDL_OK) return rc;
     if ((rc = c->ensure(kdl_ctx::B_DIAG, sizeof(kdl_diag))) != KDL_OK) return rc;
     if ((rc = c->ensure(kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 32)) != KDL_OK) return rc;
+    const long long scan_blocks = kdl::seq_off_scan_blocks((long long)n);
+    if (derive_seq_off && (rc = c->ensure(kdl_ctx::B_SCAN, (size_t)scan_blocks * 4)) != KDL_OK) return rc;
 
     cudaStream_t st = c->stream;
     cudaEventRecord(c->ev[0], st);
@@ -117,6 +123,13 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
             cudaMemcpyAsync(c->buf[cp.which].p, cp.src, cp.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
             return KDL_ERR_CUDA;
     cudaEventRecord(c->ev[1], st);
+    if (derive_seq_off) {  // K-1: seq_off = exclusive prefix sum of ceil(l_seq / 8)
+        if (kdl::launch_seq_off_scan((const int32_t*)c->buf[kdl_ctx::B_L_SEQ].p, (long long)n,
+                                     (uint32_t*)c->buf[kdl_ctx::B_SCAN].p, (uint32_t*)c->buf[kdl_ctx::B_SEQ_OFF].p,
+                                     st) != 0)
+            return KDL_ERR_CUDA;
+        g_launches.fetch_add(3, std::memory_order_relaxed);
+    }
 
     kdl_batch db = *hb;
     db.ref_start = (const int32_t*)c->buf[kdl_ctx::B_REF_START].p;

@@ -78,10 +78,23 @@ _FIELDS = ("ref_start", "seq_off", "l_seq", "cx_cig_off", "cx_cigar", "seq4", "c
            "contig_slot", "complex_idx", "evt_off")
 
 
-def host_struct(host: ReadBatch):
-    """kdl_batch over HOST pointers (for the kdl_ctx_* entry points).  Returns (struct, keepalive)."""
+def seq_is_dense(host: ReadBatch) -> bool:
+    """True if the packed bases are laid out back to back: seq_off[i] == sum of ceil(l_seq[j] / 8) over j < i.
+    Then kdl_ctx_consensus can derive seq_off on the device (batch->seq_off == NULL) instead of copying it."""
+    words = ((np.asarray(host.l_seq).astype(np.int64) & 0x7FFFFFFF) + 7) >> 3
+    off = np.asarray(host.seq_off).astype(np.int64)
+    return bool(off.size == 0 or (off[0] == 0 and np.array_equal(off[1:], np.cumsum(words[:-1]))))
+
+
+def host_struct(host: ReadBatch, derive_seq_off: bool = False):
+    """kdl_batch over HOST pointers (for the kdl_ctx_* entry points).  Returns (struct, keepalive).
+    derive_seq_off=True leaves seq_off NULL (the device derives it; requires seq_is_dense(host))."""
     keep = {f: np.ascontiguousarray(getattr(host, f)) for f in _FIELDS}
     ptr = {f: (a.ctypes.data if a.size else None) for f, a in keep.items()}
+    if derive_seq_off:
+        if not seq_is_dense(host):
+            raise ValueError("derive_seq_off needs densely packed bases (seq_off == running sum of the reads' words)")
+        ptr["seq_off"] = None
     return make_struct(host, ptr), keep
 
 
@@ -235,10 +248,11 @@ class HostContext:
             pass
 
     def consensus(self, host: ReadBatch, min_depth=1, calls_out=None, counts_out=None, events_out=None,
-                  struct=None):
-        """Runs H2D + K1 + K2 + D2H.  Returns calls (numpy uint8[n_slots])."""
+                  struct=None, derive_seq_off: bool = False):
+        """Runs H2D + K1 + K2 + D2H.  Returns calls (numpy uint8[n_slots]).
+        derive_seq_off: do not copy seq_off to the device, derive it there (dense layouts only)."""
         if struct is None:
-            struct, keep = host_struct(host)
+            struct, keep = host_struct(host, derive_seq_off)
         if calls_out is None:
             calls_out = np.empty(host.n_slots, dtype=np.uint8)
         diag = _ffi.KdlDiag()

@@ -13,6 +13,7 @@
 #include "../../kindel_b200/csrc/pileup_general.cu"
 #include "../../kindel_b200/csrc/pileup_simple.cu"
 #include "../../kindel_b200/csrc/vote.cu"
+#include "../../kindel_b200/csrc/scan.cu"
 
 static char g_error[512];
 
@@ -153,6 +154,18 @@ int emu_exchange_epoch(const kdl_exchange* xs, int n_ranks, long long n_slots, l
             if (e_) { snprintf(g_error, sizeof g_error, "%s", e_); return 1; }
         }
     }
+    return 0;
+}
+
+// K-1: seq_off = exclusive prefix sum of ceil(l_seq / 8), the three launches of launch_seq_off_scan
+int emu_seq_off_scan(const int32_t* l_seq, long long n, uint32_t* seq_off) {
+    g_error[0] = 0;
+    if (n <= 0) return 0;
+    const long long blocks = (n + kdl::S_BLOCK - 1) / kdl::S_BLOCK;
+    std::vector<uint32_t> sums((size_t)blocks);
+    EMU_RUN(blocks, kdl::S_THREADS, kdl::seq_off_block_sums_kernel(l_seq, n, sums.data()));
+    EMU_RUN(1, kdl::S_THREADS, kdl::seq_off_scan_sums_kernel(sums.data(), (int)blocks));
+    EMU_RUN(blocks, kdl::S_THREADS, kdl::seq_off_write_kernel(l_seq, n, sums.data(), seq_off));
     return 0;
 }
 

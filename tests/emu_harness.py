@@ -31,7 +31,8 @@ def _sources():
     csrc = os.path.join(ROOT, "kindel_b200", "csrc")
     return [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "emu_pileup.cpp"),
             os.path.join(csrc, "kdl_common.cuh"), os.path.join(csrc, "pileup_tiled.cu"),
-            os.path.join(csrc, "pileup_wide.cu"), os.path.join(csrc, "pileup_ws.cu"),
+            os.path.join(csrc, "pileup_wide.cu"), os.path.join(csrc, "pileup_ws.cu"), os.path.join(csrc, "scan.cu"),
+            os.path.join(csrc, "pileup_general.cu"), os.path.join(csrc, "pileup_simple.cu"), os.path.join(csrc, "vote.cu"),
             os.path.join(ROOT, "include", "kindel_b200.h")]
 
 
@@ -62,6 +63,7 @@ def load():
     lib.emu_derive.argtypes = [vp, C.c_longlong, vp]
     lib.emu_vote_peers.argtypes = [C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int,
                                    C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
+    lib.emu_seq_off_scan.argtypes = [vp, C.c_longlong, vp]
     lib.emu_exchange_epoch.argtypes = [C.POINTER(_ffi.KdlExchange), C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
     _lib = lib
     return lib
@@ -190,3 +192,12 @@ def exchange_epoch(tables, feet, slices, calls, flags, epoch, min_depth=1, grid=
             x.slice_lo[p], x.slice_hi[p] = slices[p]
         x.counter = flags["counter"][r].ctypes.data
     _check(lib.emu_exchange_epoch(xs, n, n_slots, int(math.ceil(min_depth)), epoch, grid))
+
+
+def seq_off_scan(l_seq: np.ndarray) -> np.ndarray:
+    """K-1 (scan.cu): word offsets of densely packed reads from their lengths."""
+    lib = load()
+    l_seq = np.ascontiguousarray(l_seq, dtype=np.int32)
+    out = np.full(l_seq.shape[0], 0xDEADBEEF, dtype=np.uint32)
+    _check(lib.emu_seq_off_scan(l_seq.ctypes.data, l_seq.shape[0], out.ctypes.data))
+    return out

@@ -557,6 +557,29 @@ def test_ws2_variant_matches(monkeypatch):
     _against_oracle(synth.simple_reads(96, [2000], 3000))
 
 
+@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="the device-side seq_off scan has not been "
+                    "validated on a GPU yet: opt in with KDL_TEST_EXPERIMENTAL=1")
+def test_host_buffer_entry_point_derives_seq_off():
+    """kdl_ctx_consensus with batch->seq_off == NULL: offsets derived on the device (scan.cu)."""
+    from kindel_b200 import engine, synth
+    from oracle import coracle
+
+    ctx = engine.HostContext(0)
+    from kindel_b200 import distributed as D
+
+    for b in (D.shard_batch(synth.complex_reads(31, 20000, 200), 1, 2), synth.simple_reads(32, [300_000], 100),
+              synth.simple_reads(33, [40_000], 30, read_len=1203)):
+        assert engine.seq_is_dense(b)
+        counts = np.empty((19, b.n_slots), dtype=np.int32)
+        events = np.empty((max(b.n_events, 1), 4), dtype=np.int32)
+        calls = ctx.consensus(b, 2, counts_out=counts, events_out=events, derive_seq_off=True)
+        oc, oe = coracle.pileup(b)
+        np.testing.assert_array_equal(counts, oc)
+        np.testing.assert_array_equal(events[: b.n_events], oe)
+        np.testing.assert_array_equal(calls, coracle.vote(oc, 2))
+    ctx.close()
+
+
 def test_clip_heavy_cases_through_the_engine(clip_golden, tmp_path):
     """The deterministic clip-heavy cases (tests/clip_cases.py) end to end through the public API on the GPU:
     tables, --realign consensus, changes and report equal the unmodified reference's

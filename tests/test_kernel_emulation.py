@@ -166,3 +166,32 @@ def test_fused_exchange_epochs(world):
         for r in range(world):
             np.testing.assert_array_equal(calls[r], want, err_msg="epoch %d rank %d" % (epoch, r))
             assert (flags["ready"][r][:world] == epoch).all() and (flags["done"][r][:world] == epoch).all()
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 1023, 1024, 1025, 5000, 262_145, 300_001])
+def test_seq_off_scan(n):
+    """K-1: exclusive prefix sum of ceil(l_seq / 8) with the complex flag (bit 31) ignored."""
+    rng = np.random.default_rng(n)
+    l = rng.integers(0, 400, size=n).astype(np.int64)
+    flagged = np.where(rng.random(n) < 0.3, l | 0x80000000, l).astype(np.uint32).view(np.int32)
+    words = (l + 7) >> 3
+    want = np.concatenate(([0], np.cumsum(words)[:-1])).astype(np.uint32)
+    np.testing.assert_array_equal(E.seq_off_scan(flagged), want)
+
+
+def test_dense_layout_predicate():
+    from kindel_b200 import engine
+
+    from kindel_b200 import distributed as D
+
+    strided = synth.complex_reads(5, 3000, 30)      # fixed stride per read, shorter reads leave gaps
+    assert not engine.seq_is_dense(strided)
+    b = D.shard_batch(strided, 1, 2)                 # a shard is re-packed back to back
+    assert engine.seq_is_dense(b) and engine.seq_is_dense(synth.simple_reads(6, [2000], 20))
+    np.testing.assert_array_equal(E.seq_off_scan(b.l_seq), b.seq_off)
+    st, keep = engine.host_struct(b, derive_seq_off=True)
+    assert st.seq_off is None and st.l_seq
+    b.seq_off[5] += 1
+    assert not engine.seq_is_dense(b)
+    with pytest.raises(ValueError):
+        engine.host_struct(b, derive_seq_off=True)

@@ -481,9 +481,6 @@ def weights(bam_path: "path to SAM/BAM file", relative: "output relative nucleot
     """DataFrame of per-site nucleotide frequencies, depth, consensus, clip starts/ends, confidence
     interval and entropy (reference kindel/kindel.py:558-630).  Integer columns come from the GPU
     table; the float tail is the reference's arithmetic, vectorised."""
-    import pandas as pd
-    import scipy.stats
-
     return weights_from_run(PileupRun(bamio.read_alignment(bam_path)), relative, confidence, confidence_alpha)
 
 

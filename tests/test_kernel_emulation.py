@@ -56,10 +56,8 @@ def test_accumulate_and_slot_ranges(variant):
     np.testing.assert_array_equal(t2[:5, s1:], t[:5, s1:])
 
 
-def test_emulator_catches_a_staging_bug(tmp_path):
+def test_emulator_catches_a_staging_bug():
     """The emulator is not vacuous: a kernel that skips the wait for its bulk copy reads garbage here."""
-    import ctypes as C
-
     lib = E.load()
     assert lib.emu_selftest_missing_wait() == 1   # data read before mbar_wait differs from the source
     assert lib.emu_selftest_missing_wait_fixed() == 0

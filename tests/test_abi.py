@@ -52,3 +52,23 @@ def test_engine_refuses_to_run_without_cuda():
         pytest.skip("CUDA present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         engine.require_cuda()
+
+
+def test_gpu_validated_kernels_unchanged():
+    """profiles/r01_gpu_validated_kernels.txt lists the kernels (SASS hashes) that ran on the B200; later work added
+    experimental instantiations and host-emulation guards around them, none of which may change their machine
+    code while there is no GPU to re-validate it on.  Needs cuobjdump (CUDA toolkit); skipped without it."""
+    import shutil
+    import sys
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_hashes
+
+    recorded = sass_hashes.read_recorded(os.path.join(ROOT, "profiles", "r01_gpu_validated_kernels.txt"))
+    current = sass_hashes.kernel_hashes()
+    assert len(recorded) >= 17
+    changed = [name for name, h in recorded.items() if current.get(name) != h]
+    assert not changed, ("GPU-validated kernels changed (re-validate on the device, then regenerate the list): %s"
+                         % ", ".join(changed))

@@ -61,6 +61,8 @@ def test_gpu_validated_kernels_unchanged():
     import shutil
     import sys
 
+    import pytest
+
     if shutil.which("cuobjdump") is None:
         pytest.skip("cuobjdump not on PATH")
     sys.path.insert(0, os.path.join(ROOT, "tools"))

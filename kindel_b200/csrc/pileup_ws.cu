@@ -314,7 +314,12 @@ pileup_ws_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     for (int k = 0; k < E; ++k) { acc += v[k]; st.cov[w0 + E * lane + k] = acc; }
                 }
                 producer_sync();  // everybody has read diff: clean it for the stage's next use
-                for (int k = ptid; k < KDL_TILE + 32; k += PT) st.diff[k] = 0;
+                if constexpr (C::kLean) {  // 136 x 128-bit stores instead of 544 scalar ones
+                    for (int k = ptid; k < (KDL_TILE + 32) / 4; k += PT)
+                        reinterpret_cast<int4*>(st.diff)[k] = make_int4(0, 0, 0, 0);
+                } else {
+                    for (int k = ptid; k < KDL_TILE + 32; k += PT) st.diff[k] = 0;
+                }
                 publish(item);
                 ++item;
                 first = false;

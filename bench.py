@@ -40,6 +40,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+K1_LABELS = {  # KDL_K1F -> what the roofline's dominant kernel is called in the JSON line
+    "tiled": "K0 tile index + K1f tiled pileup",
+    "lean": "K0 tile index + K1f tiled pileup (kLean instantiation)",
+    "ws": "K0 tile index + K1w warp-specialised pileup",
+    "ws2": "K0 tile index + K1w2 warp-specialised pileup (2 CTAs/SM, setmaxnreg)",
+    "wide": "K0 tile index + K1x wide-lane pileup",
+}
 METRIC = "aligned bases/sec through pileup+consensus"
 UNIT = "aligned_bases/s"
 
@@ -381,7 +388,8 @@ def run_native(args):
                                      "NCCL all_reduce(int32 sum) of the 7 vote columns, vote replicated"),
                        "k1_kernel": os.environ.get("KDL_K1F", "tiled"),  # tile-owner kernel variant (default K1f)
                        "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": "K0 tile index + K1f tiled pileup", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": K1_LABELS.get(os.environ.get("KDL_K1F", "tiled"), "K0 tile index + K1f tiled pileup"),
+                         "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, world),
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": k1_bytes, "kernel_ms": k1_ms_max},

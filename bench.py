@@ -153,8 +153,8 @@ def measured_peak():
 def ncu_traffic(workload, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
     `ncu --set full` capture of this same command (profiles/); None for configurations not captured."""
-    if workload != "cfg4_5Mb_200x" or world != 1:
-        return None
+    if workload != "cfg4_5Mb_200x" or world != 1 or os.environ.get("KDL_K1F", "tiled") != "tiled":
+        return None  # the committed capture is of the default kernel on the default workload
     try:
         with open(os.path.join(ROOT, "profiles", "r01_k1f_traffic.json")) as fh:
             d = json.load(fh)

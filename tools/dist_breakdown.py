@@ -27,6 +27,7 @@ names = ["zero", "pileup", "signal", "vote", "wait"]
 acc = {n: 0.0 for n in names}
 wall = 0.0
 evs = []
+enq = []
 for it in range(13):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     if not os.environ.get("BACK_TO_BACK"):
@@ -47,6 +48,7 @@ for it in range(13):
     lib.kdl_exchange_wait(C.byref(sc.xstruct), sc.epoch, st)
     ev[5].record()
     t1 = time.perf_counter()
+    enq.append((t1 - t0) * 1e3)
     if not os.environ.get("BACK_TO_BACK") or it == 12:
         torch.cuda.synchronize()
     t2 = time.perf_counter()
@@ -57,16 +59,22 @@ for it in range(13):
         wall += (t2 - t0) * 1e3
         if it == 12 and rank == 0:
             print("cpu enqueue ms", (t1 - t0) * 1e3)
+gaps = 0.0
 if os.environ.get("BACK_TO_BACK"):
     torch.cuda.synchronize()
     for ev in evs[3:]:
         for k, n in enumerate(names):
             acc[n] += ev[k].elapsed_time(ev[k + 1])
     wall = evs[3][0].elapsed_time(evs[-1][5])
+    # device idle time BETWEEN iterations (last event of one to first event of the next): if this is where the
+    # missing time sits, the loop is limited by the CPU enqueueing the launches, not by the exchange
+    gaps = sum(evs[i][5].elapsed_time(evs[i + 1][0]) for i in range(3, len(evs) - 1))
+    if rank == 0:
+        print("cpu enqueue ms per step (back to back): %.4f" % (sum(enq[3:]) / len(enq[3:])), flush=True)
 for r in range(world):
   dist.barrier()
   if rank == r:
-    print("rank", rank, {n: round(v / 10, 4) for n, v in acc.items()}, "sum", round(sum(acc.values()) / 10, 4), "wall", round(wall / 10, 4),
+    print("rank", rank, {n: round(v / 10, 4) for n, v in acc.items()}, "sum", round(sum(acc.values()) / 10, 4), "wall", round(wall / 10, 4), "gaps", round(gaps / 10, 4),
           "foot", sc.foot, "slots", sc.n_slots, flush=True)
 dist.barrier()
 sc.close()

@@ -15,7 +15,9 @@
 //     gone once round all fibres after it was issued, and only then completes its mbarrier; a thread's
 //     cp.async copies are performed at its own cp_async_wait_all.  A kernel that reads staged data before
 //     waiting for it therefore sees garbage here, as it could on the device;
-//   * a round in which no fibre makes progress is reported as a deadlock.
+//   * a round in which no fibre makes progress is reported as a deadlock;
+//   * the order in which fibres run within a round can be reversed or randomised (emu_set_schedule), which changes
+//     how producers, consumers and pollers interleave.
 //
 // With g++ the CUDA headers turn __global__ / __device__ / __shared__ / __forceinline__ / __align__ into
 // nothing or into GCC attributes, and give the vector types; everything else is defined below.
@@ -73,6 +75,9 @@ struct Machine {
     std::vector<Deferred> deferred;  // bulk copies in flight
     const std::function<void()>* body = nullptr;
     char error[256] = {0};
+    std::vector<int> order;
+    int schedule = 0;            // 0: threads in order each round, 1: reverse order, 2: a fresh random order per round
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
 };
 
 inline Machine& M() {
@@ -216,7 +221,19 @@ inline const char* launch(unsigned grid, unsigned block, const std::function<voi
         int idle_rounds = 0;
         while (m.live > 0) {
             const unsigned long long before = m.progress;
-            for (int t = 0; t < m.n && m.live > 0; ++t) {
+            // the order in which the fibres get their turn this round: different orders give different
+            // interleavings of producers / consumers / pollers, i.e. a cheap search for protocol races
+            m.order.resize((size_t)m.n);
+            for (int t = 0; t < m.n; ++t) m.order[(size_t)t] = m.schedule == 1 ? m.n - 1 - t : t;
+            if (m.schedule == 2) {
+                for (int t = m.n - 1; t > 0; --t) {
+                    m.rng = m.rng * 6364136223846793005ull + 1442695040888963407ull;
+                    const int j = (int)((m.rng >> 33) % (uint64_t)(t + 1));
+                    const int tmp = m.order[(size_t)t]; m.order[(size_t)t] = m.order[(size_t)j]; m.order[(size_t)j] = tmp;
+                }
+            }
+            for (int k = 0; k < m.n && m.live > 0; ++k) {
+                const int t = m.order[(size_t)k];
                 if (m.fibres[t].done) continue;
                 m.cur = t;
                 threadIdx.x = (unsigned)t; threadIdx.y = threadIdx.z = 0;

@@ -21,6 +21,12 @@ extern "C" {
 
 const char* emu_last_error() { return g_error; }
 
+// 0: threads in order (default), 1: reverse order, 2: a fresh pseudo-random order every scheduler round
+void emu_set_schedule(int mode, unsigned long long seed) {
+    emu::M().schedule = mode;
+    emu::M().rng = seed * 0x9E3779B97F4A7C15ull + 1;
+}
+
 // variant 0 = K1f (pileup_tiled_kernel), 1 = K1x (pileup_wide_kernel), 2 = K1f with kLean,
 // 3 = K1w (pileup_ws_kernel, WsCfg1), 4 = K1w2 (WsCfg2).  All pointers are HOST pointers;
 // `counts` is int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.

@@ -64,6 +64,8 @@ def load():
     lib.emu_vote_peers.argtypes = [C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int,
                                    C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
     lib.emu_seq_off_scan.argtypes = [vp, C.c_longlong, vp]
+    lib.emu_set_schedule.argtypes = [C.c_int, C.c_ulonglong]
+    lib.emu_set_schedule.restype = None
     lib.emu_exchange_epoch.argtypes = [C.POINTER(_ffi.KdlExchange), C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
     _lib = lib
     return lib
@@ -201,3 +203,9 @@ def seq_off_scan(l_seq: np.ndarray) -> np.ndarray:
     out = np.full(l_seq.shape[0], 0xDEADBEEF, dtype=np.uint32)
     _check(lib.emu_seq_off_scan(l_seq.ctypes.data, l_seq.shape[0], out.ctypes.data))
     return out
+
+
+def set_schedule(mode: str = "forward", seed: int = 1):
+    """Order in which the emulator runs the threads of a block within a scheduler round: "forward", "reverse" or
+    "random" (a fresh pseudo-random order every round) -- different interleavings of producers and consumers."""
+    load().emu_set_schedule({"forward": 0, "reverse": 1, "random": 2}[mode], seed)

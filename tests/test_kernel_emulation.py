@@ -193,3 +193,19 @@ def test_dense_layout_predicate():
     assert not engine.seq_is_dense(b)
     with pytest.raises(ValueError):
         engine.host_struct(b, derive_seq_off=True)
+
+
+@pytest.mark.parametrize("schedule,seed", [("reverse", 0), ("random", 1), ("random", 2)])
+@pytest.mark.parametrize("variant", [E.K1F, E.K1W, E.K1W2], ids=["K1f", "K1w", "K1w2"])
+def test_other_thread_interleavings(variant, schedule, seed):
+    """The staging protocols (bulk copy + mbarrier in K1f; full/empty mbarrier ring, producer barrier and
+    cp.async prefetch in K1w / K1w2) under other thread orders than the emulator's default."""
+    E.set_schedule(schedule, seed)
+    try:
+        for name in ("shallow", "multi_contig", "long_reads"):
+            batch = CASES[name]()
+            want, _ = coracle.pileup(batch)
+            got = E.run_pileup(batch, variant, fresh=True, grid=4)
+            np.testing.assert_array_equal(got[:5], want[:5], err_msg="%s %s/%d" % (name, schedule, seed))
+    finally:
+        E.set_schedule("forward")

@@ -69,6 +69,8 @@ struct WsSmemT {
     uint64_t empty[C::kStages];     // consumers -> producers: 8 warp arrivals
 };
 using WsSmem = WsSmemT<WsCfg1>;
+static_assert(WsCfg2::kConsumers == W_CONSUMERS && WsCfg2::kProducers == W_PRODUCERS,
+              "the kernel body uses W_CONSUMERS / W_PRODUCERS for both configurations");
 static_assert(sizeof(WsSmemT<WsCfg2>) <= 113 * 1024, "K1w2 must fit two CTAs per SM");
 static_assert(offsetof(WsStageT<WsCfg2>, diff) % 16 == 0 && sizeof(WsStageT<WsCfg2>) % 16 == 0,
               "kLean reads the difference array with 128-bit loads");

@@ -8,8 +8,10 @@ by feeding it records from a small stdlib (gzip + struct) BAM/SAM decoder that p
 attributes the pileup consumes (`.pos`, `.mapped`, `.seq`, `.cigars`; reference
 `kindel/kindel.py:42-48`) plus `.rname` (`kindel/kindel.py:145`).
 
-`/root/reference` does not exist on the GPU box: nothing under `-m gpu`, `smoke()` or `bench.py`
-may import this module. `available()` says whether the reference tree is present.
+`/root/reference` does not exist on the GPU box.  There the only copy is the staged install under
+`baseline/_ref/` (git-ignored; `oracle/stage_reference.py`), used solely by `bench.py`'s CPU legs
+(`--impl reference`, `cpu_baseline`) to time the reference's own functions; the `-m gpu` tests and `smoke()`
+never import this module.  `available()` says whether a reference tree was found.
 
 The decoder here is deliberately independent of the product decoder in `kindel_b200/bamio.py`
 (record-at-a-time `struct.unpack`, no numpy), so the two cross-check each other.
@@ -21,7 +23,21 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("KINDEL_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# search order: explicit override, the reference tree of the build container, the staged install that
+# travels to the GPU box (baseline/_ref/, produced by oracle/stage_reference.py; git-ignored)
+_CANDIDATES = [os.environ.get("KINDEL_REFERENCE_ROOT"), "/root/reference",
+               os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+
+
+def _find_root():
+    for c in _CANDIDATES:
+        if c and os.path.isfile(os.path.join(c, "kindel", "kindel.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 _PKG = "_kindel_reference"  # private package name so it never shadows a user's `kindel`
 
 from .samdecode import Record, read_alignment_file, read_bam, read_sam  # noqa: F401

@@ -36,3 +36,7 @@ for v in lean ws2; do
         > gpurun_out/r02_ncu_$v.log 2>&1
 done
 ls -la gpurun_out | tail -20
+
+# 5. shapes round 1 never timed (K1g on cfg 3, deep piles, multi-contig)
+timeout 400 python tools/r2_baselines.py > gpurun_out/r02_baselines.log 2>&1
+cat gpurun_out/r02_baselines.log | tee -a gpurun_out/r02_summary.txt

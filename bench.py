@@ -40,13 +40,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-K1_LABELS = {  # KDL_K1F -> what the roofline's dominant kernel is called in the JSON line
-    "tiled": "K0 tile index + K1f tiled pileup",
-    "lean": "K0 tile index + K1f tiled pileup (kLean instantiation)",
-    "ws": "K0 tile index + K1w warp-specialised pileup",
-    "ws2": "K0 tile index + K1w2 warp-specialised pileup (2 CTAs/SM, setmaxnreg)",
-    "wide": "K0 tile index + K1x wide-lane pileup",
-}
 METRIC = "aligned bases/sec through pileup+consensus"
 UNIT = "aligned_bases/s"
 
@@ -82,7 +75,7 @@ def make_workload(name, rank=0, world=1, scaling="weak"):
 def algorithmic_bytes(batch):
     """SURVEY.md 8(d): per read ceil(l_seq/2) + 4*n_cigar + 12 read-side bytes (K1);
     per position 28 B read + 1 B written by the vote (K2)."""
-    lseq = (batch.l_seq.astype(np.int64) & 0x7FFFFFFF)
+    lseq = batch.seq_len.astype(np.int64)
     n_cig = np.diff(batch.cig_off.astype(np.int64))
     k1 = int(((lseq + 1) // 2).sum() + 4 * n_cig.sum() + 12 * batch.n_reads)
     k2 = int(batch.n_slots) * 29
@@ -153,10 +146,10 @@ def measured_peak():
 def ncu_traffic(workload, world):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
     `ncu --set full` capture of this same command (profiles/); None for configurations not captured."""
-    if workload != "cfg4_5Mb_200x" or world != 1 or os.environ.get("KDL_K1F", "tiled") != "tiled":
-        return None  # the committed capture is of the default kernel on the default workload
+    if workload != "cfg4_5Mb_200x" or world != 1:
+        return None  # the committed capture is of the default workload
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_k1f_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r02_k1_traffic.json")) as fh:
             d = json.load(fh)
         return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
     except Exception:
@@ -334,9 +327,6 @@ def run_native(args):
             tpin = torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).pin_memory() if a.size else None
             pinned[f] = tpin
         ptr = {f: (int(tp.data_ptr()) if tp is not None else None) for f, tp in pinned.items()}
-        if args.derive_seq_off:  # 4 bytes per read less over PCIe: the device derives the word offsets (scan.cu)
-            assert engine.seq_is_dense(batch)
-            ptr["seq_off"] = None
         struct = engine.make_struct(batch, ptr)
         calls_host = torch.empty(n_slots, dtype=torch.uint8).pin_memory()
         calls_np = calls_host.numpy()
@@ -358,7 +348,7 @@ def run_native(args):
         # every rank copies its own shard in and its calls out; with N > 1 this leg runs the shards
         # concurrently but does not reduce across ranks (the reduction is in `value`'s step)
         e2e = {"value": total_bases / (float(tt[0]) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": batch.input_bytes() - (4 * int(batch.n_reads) if args.derive_seq_off else 0),
+               "h2d_bytes_per_step": batch.input_bytes(),
                "d2h_bytes_per_step": int(n_slots) + 16,
                "ms_per_step": float(tt[0]), "wall_ms_per_step": float(tt[1]),
                "breakdown_ms": {k: statistics.mean(x[2][k] for x in e2e_ms) for k in ("h2d_ms", "kernel_ms", "d2h_ms")},
@@ -386,9 +376,8 @@ def run_native(args):
                                      "K2p: vote over peer tables (NVLink), NCCL barrier + all_gather of call bytes"
                                      if args.exchange == "peer" else
                                      "NCCL all_reduce(int32 sum) of the 7 vote columns, vote replicated"),
-                       "k1_kernel": os.environ.get("KDL_K1F", "tiled"),  # tile-owner kernel variant (default K1f)
                        "l2_policy": "inputs (%.0f MB) larger than L2 (126 MB); no flush" % (batch.input_bytes() / 1e6)},
-            "roofline": {"bound": "hbm", "kernel": K1_LABELS.get(os.environ.get("KDL_K1F", "tiled"), "K0 tile index + K1f tiled pileup"),
+            "roofline": {"bound": "hbm", "kernel": "K0 tile index + K1 tile-owner pileup",
                          "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload, world),
                          "peak_source": peak_src,
@@ -400,7 +389,7 @@ def run_native(args):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_port_sample(batch)
             line["cpu_native_port"] = cpu_native_sample(batch)
-            if len(batch.contig_names) == 1 and len(batch.complex_idx) == 0:
+            if len(batch.contig_names) == 1 and batch.n_complex == 0:
                 line["host"] = host_side_timings(batch)
         print(json.dumps(line))
     if world > 1:
@@ -416,8 +405,6 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg4_5Mb_200x")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--derive-seq-off", action="store_true",
-                    help="e2e leg: leave seq_off on the host and derive it on the device (dense layouts; scan.cu)")
     ap.add_argument("--scaling", choices=["weak", "strong"], default="weak",
                     help="N > 1: weak = the full per-GPU workload on every rank (N x deeper in total); "
                          "strong = the N = 1 data set cut N ways")

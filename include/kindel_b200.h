@@ -23,21 +23,30 @@
  *   reads, in the reference's iteration order (grouped by contig in first-seen order, file order
  *   inside a contig; records failing `mapped and len(seq) > 1`, kindel.py:43-46, already dropped):
  *     ref_start[n]   int32   0-based reference cursor at walk start (= SAM POS - 1; -1 if POS == 0)
- *     seq_off[n]     uint32  offset of the read's packed bases in `seq4`, in 4-byte words
- *     l_seq[n]       int32   low 31 bits: SEQ length.  bit 31 (KDL_COMPLEX) set = needs the general
- *                            CIGAR walk; clear = "simple" read: exactly one M/=/X op whose length
- *                            equals the SEQ length, fully inside the contig (ref_start >= 0,
- *                            ref_start + len <= L), every base one of A,C,G,T,N (nibbles
- *                            1,2,4,8,15).  The flatten step classifies (kindel_b200/bamio.py);
- *                            the fast pileup kernel relies on it and never looks at the CIGAR
- *     cig_off[n_complex+1] uint32  prefix offsets into `cigar`, one entry per COMPLEX read (list order)
- *     cigar[n_ops]   uint32  BAM encoding  len << 4 | op,  op index into "MIDNSHP=X", of the complex
- *                            reads only: a simple read's CIGAR is implied by l_seq and never travels
- *     seq4[n_words]  uint32  BAM nibble codes "=ACMGRSVTWYHKDBN", 8 bases per 32-bit word, FIRST
- *                            base in the MOST significant nibble (base k of a read sits at bits
- *                            [28-4*(k%8), 32-4*(k%8)) of its word k/8); every read starts on a
- *                            word boundary, unused trailing nibbles of its last word are zero,
- *                            and reads are laid out in read order (seq_off non-decreasing)
+ *     seq_off[n]     uint32  offset of the read's block in `seq4`, in 4-byte words (non-decreasing)
+ *     l_seq[n]       int32   bits 0..29: SEQ length.  bit 31 (KDL_COMPLEX) clear = "simple" read: exactly
+ *                            one M/=/X op whose length equals the SEQ length, fully inside the contig
+ *                            (ref_start >= 0, ref_start + len <= L), every base one of A,C,G,T,N (nibbles
+ *                            1,2,4,8,15), at most KDL_FAST_MAXLEN bases.  Its CIGAR is implied and never
+ *                            travels.  bit 31 set = complex read: its CIGAR follows its bases in `seq4`
+ *                            (below).  bit 30 (KDL_HARD) set as well = the general, atomic kernel K1g must
+ *                            walk it (it may wrap a Python negative index, raise like the reference, or is
+ *                            too long for a tile: SURVEY.md A-7..A-10); bit 30 clear = "tile-eligible": every
+ *                            slot it touches lies in [1, L - 1] of its contig, its query span fits its SEQ,
+ *                            it has at most KDL_TILE_MAXOPS ops and reaches at most KDL_TILE_MAXREACH slots
+ *                            to either side of its start, and all its bases are A,C,G,T,N -- the tile
+ *                            kernel K1 walks it without bounds or error logic.  bits 16..22 of a complex
+ *                            read's word: number of M/=/X ops (saturating at 127; exact for tile-eligible
+ *                            reads), so a tile can be sized before its bases are staged.
+ *                            The flatten step classifies (kindel_b200/bamio.py).
+ *     seq4[n_words]  uint32  one block per read, in read order.  Bases: BAM nibble codes
+ *                            "=ACMGRSVTWYHKDBN", 8 per 32-bit word, FIRST base in the MOST significant
+ *                            nibble (base k of a read sits at bits [28-4*(k%8), 32-4*(k%8)) of word k/8),
+ *                            unused trailing nibbles of the last word zero.  A COMPLEX read's block goes on
+ *                            with  [n_ops] [evt_off] [n_ops x CIGAR word]  -- BAM encoding len << 4 | op,
+ *                            op index into "MIDNSHP=X"; evt_off = number of I ops of all reads before this
+ *                            one (row of its first insertion event).  A tile's reads are one contiguous
+ *                            byte range of this array, CIGARs included: one bulk copy stages them.
  *   contigs:
  *     contig_read_off[n_contigs+1] int64  reads of contig c are [off[c], off[c+1])
  *     contig_len[n_contigs]        int32  reference length L_c
@@ -61,12 +70,19 @@
 extern "C" {
 #endif
 
-#define KDL_ABI_VERSION 1
+#define KDL_ABI_VERSION 2
 #define KDL_NCOL 19
 #define KDL_NVOTE_COL 7 /* columns 0..6 are all the vote needs */
 #define KDL_COMPLEX 0x80000000u
+#define KDL_HARD 0x40000000u
+#define KDL_LEN_MASK 0x0000ffffu   /* SEQ length of a complex read lives in bits 0..15 (longer reads are KDL_HARD
+                                      and keep their length in bits 0..29 with the op count field zero) */
+#define KDL_NM_SHIFT 16            /* bits 16..22: M/=/X op count of a complex read */
+#define KDL_NM_MASK 0x7fu
 #define KDL_TILE 512          /* slots per tile of the owner-computes pileup; n_slots % KDL_TILE == 0 */
 #define KDL_FAST_MAXLEN 8192  /* longest read the flatten step may mark simple */
+#define KDL_TILE_MAXOPS 64    /* most CIGAR ops of a tile-eligible complex read */
+#define KDL_TILE_MAXREACH 1024 /* furthest slot, relative to its start, a tile-eligible complex read touches */
 
 enum kdl_col {
     KDL_W_A = 0, KDL_W_C, KDL_W_G, KDL_W_T, KDL_W_N,
@@ -88,30 +104,28 @@ typedef enum kdl_status {
  * pointers for the kdl_ctx_* entry points. */
 typedef struct kdl_batch {
     int64_t n_reads;
-    int64_t n_ops;       /* entries in cigar (complex reads only) */
     int64_t seq4_words;  /* 32-bit words in seq4 */
     const int32_t* ref_start;
     const uint32_t* seq_off;
     const int32_t* l_seq;
-    const uint32_t* cig_off;
-    const uint32_t* cigar;
     const uint32_t* seq4;
     int32_t n_contigs;
-    int32_t reads_sorted;   /* 1 = ref_start is non-decreasing inside every contig */
+    int32_t reads_sorted;   /* 1 = contig_slot + ref_start and seq_off are non-decreasing over all reads */
     int32_t max_simple_len; /* longest simple read (bases); 0 if there is none */
+    int32_t reach_right;    /* max over simple and tile-eligible reads of (last touched slot - start + 1) */
+    int32_t reach_left;     /* max over tile-eligible reads of (start - first touched slot) */
     int32_t reserved0;
     const int64_t* contig_read_off;
     const int32_t* contig_len;
     const int64_t* contig_slot;
-    /* complex reads (bit 31 of l_seq set), ascending read index; may be NULL when n_complex == 0 */
+    /* complex reads: how many there are (tile-eligible + hard; columns 5..18 are only ever written when
+     * this is non-zero) and the ascending indices of the KDL_HARD ones, which K1g walks */
     int64_t n_complex;
-    const uint32_t* complex_idx; /* [n_complex] */
-    const uint32_t* evt_off;     /* [n_complex+1] running count of I ops before each listed read */
-    /* cig_off above is indexed like complex_idx / evt_off: cigar[cig_off[j] .. cig_off[j+1]) is the
-     * CIGAR of read complex_idx[j] */
+    int64_t n_hard;
+    const uint32_t* hard_idx; /* [n_hard]; may be NULL when n_hard == 0 */
     /* scratch for the tile index kdl_pileup builds (K0): uint32[8 * n_slots / KDL_TILE], device
      * memory owned by the caller.  NULL, or reads_sorted == 0, selects the order-independent
-     * atomic kernel instead of the tile-owner kernel. */
+     * atomic kernels instead of the tile-owner kernel. */
     uint32_t* tile_index;
 } kdl_batch;
 

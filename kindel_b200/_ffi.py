@@ -19,6 +19,12 @@ c_u8p = C.POINTER(C.c_uint8)
 KDL_NCOL = 19
 KDL_NVOTE_COL = 7
 KDL_COMPLEX = 0x80000000
+KDL_HARD = 0x40000000
+KDL_LEN_MASK = 0xFFFF
+KDL_NM_SHIFT = 16
+KDL_NM_MASK = 0x7F
+KDL_TILE_MAXOPS = 64
+KDL_TILE_MAXREACH = 1024
 KDL_TILE = 512
 KDL_PILEUP_FRESH_WEIGHTS = 1
 KDL_PILEUP_ZERO_REST = 2
@@ -31,24 +37,23 @@ KDL_ERR_KEY = 11
 class KdlBatch(C.Structure):
     _fields_ = [
         ("n_reads", C.c_int64),
-        ("n_ops", C.c_int64),
         ("seq4_words", C.c_int64),
         ("ref_start", C.c_void_p),
         ("seq_off", C.c_void_p),
         ("l_seq", C.c_void_p),
-        ("cig_off", C.c_void_p),
-        ("cigar", C.c_void_p),
         ("seq4", C.c_void_p),
         ("n_contigs", C.c_int32),
         ("reads_sorted", C.c_int32),
         ("max_simple_len", C.c_int32),
+        ("reach_right", C.c_int32),
+        ("reach_left", C.c_int32),
         ("reserved0", C.c_int32),
         ("contig_read_off", C.c_void_p),
         ("contig_len", C.c_void_p),
         ("contig_slot", C.c_void_p),
         ("n_complex", C.c_int64),
-        ("complex_idx", C.c_void_p),
-        ("evt_off", C.c_void_p),
+        ("n_hard", C.c_int64),
+        ("hard_idx", C.c_void_p),
         ("tile_index", C.c_void_p),
     ]
 
@@ -134,7 +139,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.kdl_abi_version() != 1:
+    if lib.kdl_abi_version() != 2:
         raise RuntimeError("libkindel_b200.so ABI version mismatch")
     _lib = lib
     return lib

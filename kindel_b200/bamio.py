@@ -47,7 +47,9 @@ for _i, _c in enumerate(NIBBLES):
 
 @dataclass
 class ReadBatch:
-    """Flattened reads of one alignment file (host memory).  Field meanings: include/kindel_b200.h."""
+    """Flattened reads of one alignment file (host memory).  Field meanings: include/kindel_b200.h.
+    Host-only companions of the device layout: `seq_len` (plain SEQ lengths), `cig_off` / `cigar` (the CIGARs of
+    ALL reads: what the CPU checker, the sharder and the insertion-string builder read) and `complex_idx`."""
 
     contig_names: list
     contig_len: np.ndarray        # int32 [nc]
@@ -55,20 +57,21 @@ class ReadBatch:
     contig_slot: np.ndarray       # int64 [nc]
     n_slots: int
     ref_start: np.ndarray         # int32 [n]
-    seq_off: np.ndarray           # uint32 [n]  (4-byte words)
-    l_seq: np.ndarray             # int32 [n]   bit 31 = complex
-    cig_off: np.ndarray           # uint32 [n+1]
-    cigar: np.ndarray             # uint32 [n_ops]
-    seq4: np.ndarray              # uint32 [words]: 8 bases per word, first base in the top nibble
-    complex_idx: np.ndarray = field(default=None)   # uint32 [n_complex]
-    evt_off: np.ndarray = field(default=None)       # uint32 [n_complex+1]
-    cx_cig_off: np.ndarray = field(default=None)    # uint32 [n_complex+1]  device view: CIGARs of the
-    cx_cigar: np.ndarray = field(default=None)      # uint32 [ops]          complex reads only
+    seq_off: np.ndarray           # uint32 [n]  (4-byte words) start of the read's block in seq4
+    l_seq: np.ndarray             # int32 [n]   device word: length | op-count field | KDL_COMPLEX | KDL_HARD
+    seq_len: np.ndarray           # int32 [n]   plain SEQ length (host only)
+    cig_off: np.ndarray           # uint32 [n+1]  (host only)
+    cigar: np.ndarray             # uint32 [n_ops] (host only)
+    seq4: np.ndarray              # uint32 [words]: per read its bases, complex reads followed by [n_ops][evt_off][ops]
+    hard_idx: np.ndarray = field(default=None)      # uint32 [n_hard]: KDL_HARD reads (K1g walks them)
+    complex_idx: np.ndarray = field(default=None)   # uint32 [n_complex] (host only)
     n_events: int = 0
     reads_sorted: bool = False
     aligned_bases: int = 0        # sum of M/=/X lengths = sum of the weights table (the metric's unit)
     n_records: int = 0            # records in the file, before filtering
     max_simple_len: int = 0       # longest simple read
+    reach_right: int = 0          # see include/kindel_b200.h
+    reach_left: int = 0
 
     @property
     def n_reads(self) -> int:
@@ -78,11 +81,27 @@ class ReadBatch:
     def n_contigs(self) -> int:
         return len(self.contig_names)
 
+    @property
+    def n_complex(self) -> int:
+        return int(self.complex_idx.shape[0])
+
+    @property
+    def n_hard(self) -> int:
+        return int(self.hard_idx.shape[0])
+
     def input_bytes(self) -> int:
         """Bytes of read data the device consumes (what the e2e path copies host->device)."""
-        arrs = (self.ref_start, self.seq_off, self.l_seq, self.cx_cig_off, self.cx_cigar, self.seq4,
-                self.complex_idx, self.evt_off, self.contig_len, self.contig_read_off, self.contig_slot)
+        arrs = (self.ref_start, self.seq_off, self.l_seq, self.seq4, self.hard_idx, self.contig_len,
+                self.contig_read_off, self.contig_slot)
         return int(sum(a.nbytes for a in arrs if a is not None))
+
+
+def seq_lengths(l_seq: np.ndarray) -> np.ndarray:
+    """SEQ length (int64) of every read from the device word l_seq (include/kindel_b200.h)."""
+    w = np.asarray(l_seq).astype(np.int64) & 0xFFFFFFFF
+    cx = (w & _ffi.KDL_COMPLEX) != 0
+    hard = (w & _ffi.KDL_HARD) != 0
+    return np.where(cx, np.where(hard, w & 0x3FFFFFFF, w & _ffi.KDL_LEN_MASK), w)
 
 
 def _reads_with_exotic_bases(seq4: np.ndarray, seq_off: np.ndarray, lseq: np.ndarray) -> np.ndarray:
@@ -128,27 +147,39 @@ def layout_slots(contig_len: np.ndarray):
     return slot, n_slots
 
 
+def _per_read_sum(values: np.ndarray, cig_off: np.ndarray) -> np.ndarray:
+    """Sum of `values` (one per CIGAR op) over each read's ops."""
+    c = np.concatenate(([0], np.cumsum(values, dtype=np.int64)))
+    return c[cig_off[1:]] - c[cig_off[:-1]]
+
+
 def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_seq, cig_off, cigar, seq4,
              n_records=0, exotic=None) -> ReadBatch:
-    """Classify reads (simple / complex), list the complex ones with their insertion-event offsets,
-    detect coordinate order.  All vectorised numpy; shared by the BAM, SAM and synthetic paths."""
+    """Classify reads (simple / tile-eligible complex / hard), lay the complex reads' CIGARs behind their bases,
+    detect coordinate order.  All vectorised numpy; shared by the BAM, SAM and synthetic paths.
+
+    In: per read its start, SEQ length, CIGAR (cig_off / cigar over ALL reads) and the offset of its packed
+    bases in `seq4` (any layout: gaps and extra words between reads are allowed and dropped)."""
     contig_len = np.ascontiguousarray(contig_len, dtype=np.int32)
     contig_read_off = np.ascontiguousarray(contig_read_off, dtype=np.int64)
     ref_start = np.ascontiguousarray(ref_start, dtype=np.int32)
-    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint32)
-    lseq = np.ascontiguousarray(l_seq).astype(np.int64) & 0x7FFFFFFF  # tolerate already-flagged input
+    seq_off_in = np.ascontiguousarray(seq_off).astype(np.int64)
+    lseq = np.ascontiguousarray(l_seq).astype(np.int64)
     cig_off = np.ascontiguousarray(cig_off, dtype=np.uint32)
     cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
     seq4 = np.ascontiguousarray(seq4, dtype=np.uint32)
     n = ref_start.shape[0]
+    if lseq.size and (lseq.min() < 0 or lseq.max() >= (1 << 30)):
+        raise ValueError("finalize() takes plain SEQ lengths below 2^30 (use ReadBatch.seq_len, not the device word l_seq)")
     slot, n_slots = layout_slots(contig_len)
     per_contig = np.diff(contig_read_off)
     read_L = np.repeat(contig_len.astype(np.int64), per_contig)
+    co = cig_off.astype(np.int64)
 
-    n_cig = np.diff(cig_off.astype(np.int64))
+    n_cig = np.diff(co)
     first = np.zeros(n, dtype=np.uint32)
     has = n_cig > 0
-    first[has] = cigar[cig_off[:-1][has]]
+    first[has] = cigar[co[:-1][has]]
     op = first & 15
     oplen = (first >> 4).astype(np.int64)
     is_m = (op == 0) | (op == 7) | (op == 8)
@@ -156,43 +187,137 @@ def finalize(contig_names, contig_len, contig_read_off, ref_start, seq_off, l_se
     simple = (n_cig == 1) & is_m & (oplen == lseq) & (start >= 0) & (start + oplen <= read_L)
     simple &= oplen <= _ffi.KDL_FAST_MAXLEN
     # reads with a base outside A,C,G,T,N (flagged by the C++ gather for BAM input, else found here)
-    simple &= ~(np.asarray(exotic, dtype=bool) if exotic is not None else _reads_with_exotic_bases(seq4, seq_off, lseq))
-    l_out = np.where(simple, oplen, lseq | _ffi.KDL_COMPLEX).astype(np.uint32).view(np.int32)
+    exo = (np.asarray(exotic, dtype=bool) if exotic is not None
+           else _reads_with_exotic_bases(seq4, seq_off_in.astype(np.uint32), lseq))
+    simple &= ~exo
 
-    complex_idx = np.flatnonzero(~simple).astype(np.uint32)
-    ops_all = cigar & 15
-    is_i = (ops_all == 1).astype(np.int64)
-    csum = np.concatenate(([0], np.cumsum(is_i)))
-    ins_per_read = csum[cig_off[1:].astype(np.int64)] - csum[cig_off[:-1].astype(np.int64)]
-    evt = np.zeros(complex_idx.shape[0] + 1, dtype=np.int64)
-    np.cumsum(ins_per_read[complex_idx], out=evt[1:])
-    n_events = int(evt[-1])
-    # only complex reads need their CIGAR on the device (a simple read's is implied by l_seq)
-    cx_n = n_cig[complex_idx]
-    cx_cig_off = np.concatenate(([0], np.cumsum(cx_n))).astype(np.int64)
-    cx_src = np.repeat(cig_off[:-1].astype(np.int64)[complex_idx], cx_n) + (
-        np.arange(int(cx_cig_off[-1]), dtype=np.int64) - np.repeat(cx_cig_off[:-1], cx_n))
-    cx_cigar = cigar[cx_src]
+    # ---- complex reads: which of them the tile kernel may walk (include/kindel_b200.h: "tile-eligible")
+    ops_all = (cigar & 15).astype(np.int64)
+    len_all = (cigar >> 4).astype(np.int64)
     is_match = (ops_all == 0) | (ops_all == 7) | (ops_all == 8)
-    aligned = int(((cigar >> 4).astype(np.int64) * is_match).sum())
+    is_first = np.zeros(cigar.shape[0], dtype=bool)
+    is_first[co[:-1][has]] = True
+    later_clip = (ops_all == 4) & ~is_first
+    q_span = _per_read_sum(len_all * (is_match | (ops_all == 1) | (ops_all == 4)), co)
+    r_span = _per_read_sum(len_all * (is_match | (ops_all == 2) | later_clip), co)  # a non-first S advances r_pos too
+    n_match = _per_read_sum(is_match.astype(np.int64), co)
+    ins_per_read = _per_read_sum((ops_all == 1).astype(np.int64), co)
+    lead = np.where(has & (op == 4), oplen, 0)
+    tile_ok = (~simple & ~exo & (n_cig <= _ffi.KDL_TILE_MAXOPS) & (lseq <= _ffi.KDL_FAST_MAXLEN) & (q_span <= lseq)
+               & (start - lead - 1 >= 0) & (start + r_span <= read_L - 1)
+               & (r_span + 1 <= _ffi.KDL_TILE_MAXREACH) & (lead + 1 <= _ffi.KDL_TILE_MAXREACH))
+    hard = ~simple & ~tile_ok
+    l_out = np.where(simple, oplen,
+                     np.where(tile_ok, lseq | (n_match << _ffi.KDL_NM_SHIFT) | _ffi.KDL_COMPLEX,
+                              lseq | _ffi.KDL_COMPLEX | _ffi.KDL_HARD)).astype(np.uint32).view(np.int32)
+    complex_idx = np.flatnonzero(~simple).astype(np.uint32)
+    hard_idx = np.flatnonzero(hard).astype(np.uint32)
+    evt = np.concatenate(([0], np.cumsum(ins_per_read)))  # row of each read's first insertion event
+    n_events = int(evt[-1])
+    aligned = int((len_all * is_match).sum())
+    reach_right = int(max(oplen[simple].max() if simple.any() else 0, (r_span[tile_ok] + 1).max() if tile_ok.any() else 0))
+    reach_left = int((lead[tile_ok] + 1).max()) if tile_ok.any() else 0
+
+    # ---- the read stream: bases of every read in read order, complex reads followed by [n_ops][evt_off][ops...]
+    words = (lseq + 7) // 8
+    extra = np.where(simple, 0, 2 + n_cig)
+    new_off = np.concatenate(([0], np.cumsum(words + extra)))
+    dense_in = bool(n == 0 or (seq_off_in[0] == 0 and np.array_equal(seq_off_in[1:], np.cumsum(words[:-1]))
+                               and int(words.sum()) == seq4.shape[0]))
+    if dense_in and not extra.any():
+        stream = seq4  # already the device layout: no copy
+    else:
+        if new_off[-1] >= (1 << 32):
+            raise ValueError("alignment too large for 32-bit word offsets; split it by contig")
+        stream = np.zeros(int(new_off[-1]), dtype=np.uint32)
+        total = int(words.sum())
+        ramp = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(words) - words, words)
+        stream[np.repeat(new_off[:-1], words) + ramp] = seq4[np.repeat(seq_off_in, words) + ramp]
+        cx = np.flatnonzero(~simple)
+        if cx.size:
+            hdr = new_off[:-1][cx] + words[cx]
+            stream[hdr] = n_cig[cx]
+            stream[hdr + 1] = evt[:-1][cx]
+            nc = n_cig[cx]
+            tot = int(nc.sum())
+            ramp2 = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(nc) - nc, nc)
+            stream[np.repeat(hdr + 2, nc) + ramp2] = cigar[np.repeat(co[:-1][cx], nc) + ramp2]
+    seq_off_out = new_off[:-1].astype(np.uint32)
 
     # coordinate order: the global start slot (contig_slot + ref_start) must be non-decreasing over
-    # ALL reads, and the packed bases must be laid out in read order (the tile-owner kernel stages
+    # ALL reads (the blocks of seq4 are in read order by construction: the tile-owner kernel stages
     # the reads of a tile as one contiguous index range and one contiguous byte range)
     sorted_ok = True
     if n > 1:
         gstart = np.repeat(slot, per_contig) + start
-        sorted_ok = bool((np.diff(gstart) >= 0).all()) and bool((np.diff(seq_off.astype(np.int64)) >= 0).all())
+        sorted_ok = bool((np.diff(gstart) >= 0).all())
 
     return ReadBatch(
         contig_names=list(contig_names), contig_len=contig_len, contig_read_off=contig_read_off,
-        contig_slot=slot, n_slots=n_slots, ref_start=ref_start, seq_off=seq_off, l_seq=l_out,
-        cig_off=cig_off, cigar=cigar, seq4=seq4, complex_idx=complex_idx,
-        evt_off=evt.astype(np.uint32), n_events=n_events, reads_sorted=sorted_ok,
-        cx_cig_off=cx_cig_off.astype(np.uint32), cx_cigar=np.ascontiguousarray(cx_cigar, dtype=np.uint32),
-        aligned_bases=aligned, n_records=int(n_records),
-        max_simple_len=int(oplen[simple].max()) if simple.any() else 0,
+        contig_slot=slot, n_slots=n_slots, ref_start=ref_start, seq_off=seq_off_out, l_seq=l_out,
+        seq_len=lseq.astype(np.int32), cig_off=cig_off, cigar=cigar, seq4=stream, hard_idx=hard_idx,
+        complex_idx=complex_idx, n_events=n_events, reads_sorted=sorted_ok, aligned_bases=aligned,
+        n_records=int(n_records), max_simple_len=int(oplen[simple].max()) if simple.any() else 0,
+        reach_right=reach_right, reach_left=reach_left,
     )
+
+
+def select_reads(batch: ReadBatch, idx) -> ReadBatch:
+    """The sub-batch made of reads `idx` (any order; kept grouped by contig, the given order inside a contig),
+    over the same contigs and slot layout."""
+    idx = np.asarray(idx, dtype=np.int64)
+    contig_of = np.searchsorted(batch.contig_read_off, idx, side="right") - 1
+    order = np.argsort(contig_of, kind="stable")
+    idx, contig_of = idx[order], contig_of[order]
+    read_off = np.concatenate(([0], np.cumsum(np.bincount(contig_of, minlength=batch.n_contigs))))
+    n = idx.shape[0]
+    lseq = batch.seq_len[idx].astype(np.int64)
+    co = batch.cig_off.astype(np.int64)
+    n_cig = np.diff(co)[idx]
+    # gather the ragged CIGAR and base ranges of the kept reads
+    cig_off = np.concatenate(([0], np.cumsum(n_cig)))
+    cig_src = np.repeat(co[:-1][idx], n_cig) + (np.arange(int(cig_off[-1])) - np.repeat(cig_off[:-1], n_cig))
+    words = (lseq + 7) // 8
+    seq_off = np.concatenate(([0], np.cumsum(words)))
+    seq_src = np.repeat(batch.seq_off.astype(np.int64)[idx], words) + (
+        np.arange(int(seq_off[-1])) - np.repeat(seq_off[:-1], words))
+    return finalize(batch.contig_names, batch.contig_len, read_off, batch.ref_start[idx], seq_off[:-1], lseq,
+                          cig_off, batch.cigar[cig_src], batch.seq4[seq_src], n_records=n)
+
+
+
+def _ragged_gather(src: np.ndarray, starts: np.ndarray, lens: np.ndarray) -> np.ndarray:
+    """Concatenation of src[starts[i] : starts[i] + lens[i]] over i."""
+    lens = lens.astype(np.int64)
+    total = int(lens.sum())
+    ramp = np.arange(total, dtype=np.int64) - np.repeat(np.cumsum(lens) - lens, lens)
+    return src[np.repeat(starts.astype(np.int64), lens) + ramp]
+
+
+def merge_batches(batches) -> ReadBatch:
+    """All reads of several batches over the SAME contigs as one batch, coordinate-sorted inside every contig
+    (stable: ties keep batch order).  Used to mix synthetic read populations; not a hot path."""
+    first = batches[0]
+    for b in batches[1:]:
+        if list(b.contig_names) != list(first.contig_names) or not np.array_equal(b.contig_len, first.contig_len):
+            raise ValueError("merge_batches needs batches over the same contigs")
+    nc = first.n_contigs
+    contig_of = np.concatenate([np.repeat(np.arange(nc), np.diff(b.contig_read_off)) for b in batches])
+    ref_start = np.concatenate([b.ref_start for b in batches]).astype(np.int64)
+    lseq = np.concatenate([b.seq_len for b in batches]).astype(np.int64)
+    n_cig = np.concatenate([np.diff(b.cig_off.astype(np.int64)) for b in batches])
+    cigar = np.concatenate([b.cigar for b in batches])
+    cig_base = np.concatenate(([0], np.cumsum([b.cigar.shape[0] for b in batches])))
+    cig_at = np.concatenate([b.cig_off[:-1].astype(np.int64) + cig_base[k] for k, b in enumerate(batches)])
+    words = (lseq + 7) // 8
+    bases = np.concatenate([_ragged_gather(b.seq4, b.seq_off, (b.seq_len.astype(np.int64) + 7) // 8) for b in batches])
+    base_at = np.cumsum(words) - words
+    order = np.lexsort((ref_start, contig_of))  # stable
+    read_off = np.concatenate(([0], np.cumsum(np.bincount(contig_of, minlength=nc))))
+    nco = n_cig[order]
+    cig_off = np.concatenate(([0], np.cumsum(nco)))
+    return finalize(first.contig_names, first.contig_len, read_off, ref_start[order], base_at[order], lseq[order],
+                    cig_off, _ragged_gather(cigar, cig_at[order], nco), bases, n_records=int(order.shape[0]))
 
 
 # --------------------------------------------------------------------------------------- BGZF

@@ -54,7 +54,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"),
-           os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "scan.cu"), os.path.join(CSRC, "bam_host.cpp"), "-o", LIB_PATH]
+           os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "bam_host.cpp"), "-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:

@@ -8,17 +8,8 @@
 #include "kdl_common.cuh"
 #include "pileup_general.cu"
 #include "pileup_simple.cu"
-#include "pileup_tiled.cu"
-#include "pileup_ws.cu"
-#include "pileup_wide.cu"
+#include "pileup_tile.cu"
 #include "vote.cu"
-
-namespace kdl {
-// scan.cu is its own translation unit (so that adding it leaves the code generated for the kernels above
-// untouched); its launcher:
-int launch_seq_off_scan(const int32_t* l_seq, long long n, uint32_t* block_sums, uint32_t* seq_off, cudaStream_t st);
-long long seq_off_scan_blocks(long long n);
-}  // namespace kdl
 
 namespace {
 
@@ -51,90 +42,29 @@ inline int sm_count() {
     return n;
 }
 
-// opt-in to > 48 KB dynamic shared memory for K1f, once per device
-inline int ensure_k1f_smem(int smem) {
+// opt-in to > 48 KB dynamic shared memory for the tile kernel's instantiations, once per device
+template <int kFlush, bool kCx>
+inline int ensure_tile_smem() {
     static std::atomic<int> done[kMaxDevices];
     const int dev = current_device();
     if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
-    if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-            cudaSuccess ||
-        cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-            cudaSuccess)
-        return KDL_ERR_CUDA;
-    if (cudaFuncSetAttribute(kdl::pileup_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(kdl::WsSmem)) != cudaSuccess ||
-        cudaFuncSetAttribute(kdl::pileup_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(kdl::WsSmem)) != cudaSuccess)
+    if (cudaFuncSetAttribute(kdl::pileup_tile_kernel<kFlush, kCx>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sizeof(kdl::TileSmem<kdl::TileCfg<kCx>>)) != cudaSuccess)
         return KDL_ERR_CUDA;
     done[dev].store(1, std::memory_order_release);
     return KDL_OK;
 }
 
-// the same opt-in for the experimental K1x, made only when that kernel is selected so that the default
-// path never depends on it
-inline int ensure_k1x_smem() {
-    static std::atomic<int> done[kMaxDevices];
-    const int dev = current_device();
-    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
-    if (cudaFuncSetAttribute(kdl::pileup_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(kdl::WideSmem)) != cudaSuccess ||
-        cudaFuncSetAttribute(kdl::pileup_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)sizeof(kdl::WideSmem)) != cudaSuccess)
-        return KDL_ERR_CUDA;
-    done[dev].store(1, std::memory_order_release);
+template <int kFlush, bool kCx>
+inline int launch_tile(const kdl_batch& b, int32_t* counts, long long n_slots, long long tile_lo, long long n_tiles,
+                       int split, int32_t* ins_events, cudaStream_t st) {
+    int rc = ensure_tile_smem<kFlush, kCx>();
+    if (rc != KDL_OK) return rc;
+    const long long units = n_tiles * split, max_grid = (long long)sm_count() * 2;  // two CTAs per SM, persistent
+    const long long grid = units < max_grid ? units : max_grid;
+    kdl::pileup_tile_kernel<kFlush, kCx><<<(unsigned)grid, kdl::W_THREADS, sizeof(kdl::TileSmem<kdl::TileCfg<kCx>>), st>>>(
+        b, counts, n_slots, b.tile_index, tile_lo, n_tiles, split, ins_events);
     return KDL_OK;
-}
-
-// the same opt-in for the experimental lean instantiation of K1f (KDL_K1F=lean)
-inline int ensure_k1f_lean_smem(int smem) {
-    static std::atomic<int> done[kMaxDevices];
-    const int dev = current_device();
-    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
-    if (cudaFuncSetAttribute(kdl::pileup_tiled_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess ||
-        cudaFuncSetAttribute(kdl::pileup_tiled_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem) != cudaSuccess)
-        return KDL_ERR_CUDA;
-    done[dev].store(1, std::memory_order_release);
-    return KDL_OK;
-}
-
-// K1w2 = pileup_ws_kernel<.., WsCfg2>: two CTAs per SM, setmaxnreg (experimental, KDL_K1F=ws2)
-inline int ensure_k1w2_smem() {
-    static std::atomic<int> done[kMaxDevices];
-    const int dev = current_device();
-    if (done[dev].load(std::memory_order_acquire)) return KDL_OK;
-    const int bytes = (int)sizeof(kdl::WsSmemT<kdl::WsCfg2>);
-    if (cudaFuncSetAttribute(kdl::pileup_ws_kernel<false, kdl::WsCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(kdl::pileup_ws_kernel<true, kdl::WsCfg2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             bytes) != cudaSuccess)
-        return KDL_ERR_CUDA;
-    done[dev].store(1, std::memory_order_release);
-    return KDL_OK;
-}
-
-inline bool use_ws2_kernel() {
-    const char* ev = getenv("KDL_K1F");
-    return ev && !strcmp(ev, "ws2");
-}
-
-inline bool use_lean_kernel() {  // K1f<.., kLean = true>, experimental (not yet validated on a GPU)
-    const char* ev = getenv("KDL_K1F");
-    return ev && !strcmp(ev, "lean");
-}
-
-inline bool use_wide_kernel() {  // K1x, experimental (not yet validated on a GPU)
-    const char* ev = getenv("KDL_K1F");
-    return ev && !strcmp(ev, "wide");
-}
-
-// which tile-owner kernel: "ws" = warp-specialised pipeline (K1w), "tiled" = K1f
-inline bool use_ws_kernel() {
-    const char* ev = getenv("KDL_K1F");
-    if (ev && !strcmp(ev, "tiled")) return false;
-    if (ev && !strcmp(ev, "ws")) return true;
-    return false;
 }
 
 inline int check_launch() {
@@ -143,12 +73,13 @@ inline int check_launch() {
 }
 
 int validate_batch(const kdl_batch* b) {
-    if (!b || b->n_reads < 0 || b->n_contigs < 0) return KDL_ERR_INVALID_ARG;
+    if (!b || b->n_reads < 0 || b->n_contigs < 0 || b->n_hard < 0 || b->n_complex < b->n_hard)
+        return KDL_ERR_INVALID_ARG;
     if (b->n_reads > 0 && (!b->ref_start || !b->seq_off || !b->l_seq || !b->seq4 ||
                            !b->contig_read_off || !b->contig_len || !b->contig_slot))
         return KDL_ERR_INVALID_ARG;
-    if (b->n_complex > 0 && (!b->complex_idx || !b->evt_off || !b->cig_off || (b->n_ops > 0 && !b->cigar)))
-        return KDL_ERR_INVALID_ARG;
+    if (b->n_hard > 0 && !b->hard_idx) return KDL_ERR_INVALID_ARG;
+    if (b->reach_right < b->max_simple_len || b->reach_left < 0) return KDL_ERR_INVALID_ARG;
     return KDL_OK;
 }
 
@@ -187,12 +118,26 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
     if ((slot_lo & 3) || (slot_hi & 3)) return KDL_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int cap = sm_count() * 8;
-    const bool has_simple = batch->n_reads > batch->n_complex;
-    const bool tiled = has_simple && tileable && batch->reads_sorted && batch->tile_index &&
-                       batch->max_simple_len > 0 && batch->max_simple_len <= KDL_FAST_MAXLEN;
+    const bool has_tile_reads = batch->n_reads > batch->n_hard;
+    const bool tiled = has_tile_reads && tileable && batch->reads_sorted && batch->tile_index &&
+                       batch->reach_right > 0 && batch->reach_right <= KDL_FAST_MAXLEN + KDL_TILE_MAXREACH;
     const bool fresh = (flags & KDL_PILEUP_FRESH_WEIGHTS) != 0;
+    const long long tile_lo = slot_lo / KDL_TILE, n_tiles = (slot_hi - slot_lo) / KDL_TILE;
+    // Depth split: a small reference piled deep has fewer tiles than the GPU has CTA slots (30 kb = 59 tiles for
+    // 296 slots); `split` CTAs then share a tile by read range and flush with REDs into a zeroed table.
+    int split = 1;
+    if (tiled && n_tiles > 0) {
+        const long long slots = (long long)sm_count() * 2;
+        if (n_tiles < slots) {
+            long long want = (slots + n_tiles - 1) / n_tiles;
+            const long long deep = batch->n_reads / (n_tiles * 256);  // at least ~256 reads per unit
+            if (want > deep) want = deep;
+            split = (int)(want < 1 ? 1 : (want > 32 ? 32 : want));
+        }
+        if (const char* ev = getenv("KDL_SPLIT")) { const int v = atoi(ev); if (v >= 1 && v <= 64) split = v; }
+    }
     // zeroing that the chosen kernels will not do themselves
-    const int zero_from = (fresh && !tiled) ? 0 : 5;
+    const int zero_from = (fresh && !(tiled && split == 1)) ? 0 : 5;
     const int zero_to = (flags & KDL_PILEUP_ZERO_REST) ? KDL_NCOL : 5;
     if (zero_to > zero_from && slot_hi > slot_lo) {
         kdl::zero_cols_kernel<<<sm_count() * 4, 256, 0, st>>>(counts, n_slots, zero_from, zero_to, slot_lo, slot_hi);
@@ -200,82 +145,45 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
     }
     if (batch->n_reads == 0) return KDL_OK;
     if (tiled) {
-        // K0: read range per tile of the slot range (the linear index of a sorted BAM, built on device)
-        const long long tile_lo = slot_lo / KDL_TILE, n_tiles = (slot_hi - slot_lo) / KDL_TILE;
         if (n_tiles > 0) {
+            // K0: read range per tile of the slot range (the linear index of a sorted BAM, built on device)
             kdl::tile_index_kernel<<<(unsigned)((n_tiles * 32 + 255) / 256), 256, 0, st>>>(*batch, tile_lo, n_tiles,
                                                                                           batch->tile_index);
             if ((rc = check_launch()) != KDL_OK) return rc;
-        }
-        // K1f: one CTA per tile, 2 CTAs per SM (2 x ~90 KB shared memory)
-        const int smem = (int)sizeof(kdl::FastSmem);
-        if ((rc = ensure_k1f_smem(smem)) != KDL_OK) return rc;
-        if (n_tiles > 0 && use_ws_kernel()) {
-            // K1w: one persistent CTA per SM (4 producer + 8 consumer warps, ~200 KB shared memory)
-            long long grid = n_tiles < (long long)sm_count() ? n_tiles : (long long)sm_count();
-            const int wsmem = (int)sizeof(kdl::WsSmem);
-            if (fresh)
-                kdl::pileup_ws_kernel<true><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            else
-                kdl::pileup_ws_kernel<false><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            if ((rc = check_launch()) != KDL_OK) return rc;
-        } else if (n_tiles > 0 && use_ws2_kernel()) {
-            if ((rc = ensure_k1w2_smem()) != KDL_OK) return rc;
-            const long long max_grid = (long long)sm_count() * 2;
-            const long long grid = n_tiles < max_grid ? n_tiles : max_grid;
-            const int wsmem = (int)sizeof(kdl::WsSmemT<kdl::WsCfg2>);
-            if (fresh)
-                kdl::pileup_ws_kernel<true, kdl::WsCfg2><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            else
-                kdl::pileup_ws_kernel<false, kdl::WsCfg2><<<(unsigned)grid, kdl::W_THREADS, wsmem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            if ((rc = check_launch()) != KDL_OK) return rc;
-        } else if (n_tiles > 0 && use_wide_kernel()) {
-            long long grid = n_tiles < (long long)sm_count() * 2 ? n_tiles : (long long)sm_count() * 2;
-            const int xsmem = (int)sizeof(kdl::WideSmem);
-            if ((rc = ensure_k1x_smem()) != KDL_OK) return rc;
-            if (fresh)
-                kdl::pileup_wide_kernel<true><<<(unsigned)grid, kdl::F_THREADS, xsmem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            else
-                kdl::pileup_wide_kernel<false><<<(unsigned)grid, kdl::F_THREADS, xsmem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            if ((rc = check_launch()) != KDL_OK) return rc;
-        } else if (n_tiles > 0) {
-            // CTAs per SM-slot: 2 are resident per SM; each CTA walks its tiles with a software pipeline
-            // (metadata of its next tile streams in while it counts), so a persistent grid is best
-            long long mult = 1;
-            if (const char* ev = getenv("KDL_K1F_GRID_MULT")) { mult = atoll(ev); if (mult < 1) mult = 1; }
-            const long long max_grid = (long long)sm_count() * 2 * mult;
-            long long grid = n_tiles < max_grid ? n_tiles : max_grid;
-            if (use_lean_kernel()) {
-                if ((rc = ensure_k1f_lean_smem(smem)) != KDL_OK) return rc;
-                if (fresh)
-                    kdl::pileup_tiled_kernel<true, true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
-                        *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-                else
-                    kdl::pileup_tiled_kernel<false, true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
-                        *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            } else if (fresh)
-                kdl::pileup_tiled_kernel<true><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
-            else
-                kdl::pileup_tiled_kernel<false><<<(unsigned)grid, kdl::F_THREADS, smem, st>>>(
-                    *batch, counts, n_slots, batch->tile_index, tile_lo, n_tiles);
+            // K1: the tile-owner kernel
+            const bool cx = batch->n_complex > batch->n_hard;  // tile-eligible complex reads present
+            if (split > 1) {
+                rc = cx ? launch_tile<kdl::F_ATOMIC, true>(*batch, counts, n_slots, tile_lo, n_tiles, split, ins_events, st)
+                        : launch_tile<kdl::F_ATOMIC, false>(*batch, counts, n_slots, tile_lo, n_tiles, split, ins_events, st);
+            } else if (fresh) {
+                rc = cx ? launch_tile<kdl::F_STORE, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st)
+                        : launch_tile<kdl::F_STORE, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st);
+            } else {
+                rc = cx ? launch_tile<kdl::F_ADD, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st)
+                        : launch_tile<kdl::F_ADD, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st);
+            }
+            if (rc != KDL_OK) return rc;
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
-    } else if (has_simple) {
-        const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
-        kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
-        if ((rc = check_launch()) != KDL_OK) return rc;
-    }
-    if (batch->n_complex > 0) {
-        const int grid = grid_for(batch->n_complex, 8, cap);
-        kdl::pileup_general_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events, err_flag);
-        if ((rc = check_launch()) != KDL_OK) return rc;
+        if (batch->n_hard > 0) {  // K1g: the reads that may wrap or raise, atomically, after the tile stores
+            const int grid = grid_for(batch->n_hard, 8, cap);
+            kdl::pileup_general_kernel<<<grid, 256, 0, st>>>(*batch, batch->hard_idx, batch->n_hard, counts, n_slots,
+                                                            ins_events, err_flag);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        }
+    } else {
+        // order-independent fallback (unsorted input): K1s for the simple reads, K1g for every complex read
+        if (batch->n_reads > batch->n_complex) {
+            const int grid = grid_for(batch->n_reads, 8, cap);  // 8 warps (reads) per 256-thread CTA
+            kdl::pileup_simple_atomic_kernel<<<grid, 256, 0, st>>>(*batch, counts, n_slots, err_flag);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        }
+        if (batch->n_complex > 0) {
+            const int grid = grid_for(batch->n_reads, 8, cap);
+            kdl::pileup_general_kernel<<<grid, 256, 0, st>>>(*batch, nullptr, batch->n_reads, counts, n_slots,
+                                                            ins_events, err_flag);
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        }
     }
     return KDL_OK;
 }
@@ -287,8 +195,8 @@ int kdl_diagnose(const kdl_batch* batch, kdl_diag* diag_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     kdl::diagnose_init_kernel<<<1, 1, 0, st>>>(diag_dev);
     if ((rc = check_launch()) != KDL_OK) return rc;
-    if (batch->n_complex > 0) {
-        const long long grid = (batch->n_complex + 255) / 256;
+    if (batch->n_hard > 0) {
+        const long long grid = (batch->n_hard + 255) / 256;
         kdl::diagnose_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, diag_dev);
         if ((rc = check_launch()) != KDL_OK) return rc;
     }

@@ -17,8 +17,8 @@ struct kdl_ctx {
         void* p = nullptr;
         size_t cap = 0;
     };
-    enum { B_REF_START, B_SEQ_OFF, B_L_SEQ, B_CIG_OFF, B_CIGAR, B_SEQ4, B_CREAD_OFF, B_CLEN, B_CSLOT,
-           B_CX_IDX, B_EVT_OFF, B_COUNTS, B_EVENTS, B_CALLS, B_FLAG, B_DIAG, B_TILE_IDX, B_SCAN, B_N };
+    enum { B_REF_START, B_SEQ_OFF, B_L_SEQ, B_SEQ4, B_CREAD_OFF, B_CLEN, B_CSLOT, B_HARD_IDX, B_COUNTS, B_EVENTS,
+           B_CALLS, B_FLAG, B_DIAG, B_TILE_IDX, B_N };
     Buf buf[B_N];
 
     int ensure(int which, size_t bytes) {
@@ -75,74 +75,41 @@ void kdl_ctx_destroy(kdl_ctx* c) {
     delete c;
 }
 
-int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t n_events,
-                      int64_t min_depth_ceil, uint8_t* calls_out, int32_t* counts_out,
-                      int32_t* ins_events_out, kdl_diag* diag_out) {
-    if (!c || !diag_out || !hb) return KDL_ERR_INVALID_ARG;
-    // seq_off == NULL: the packed bases are dense and the offsets are derived on the device (scan.cu)
-    const bool derive_seq_off = hb->n_reads > 0 && hb->seq_off == nullptr && hb->l_seq != nullptr;
-    kdl_batch checked = *hb;
-    if (derive_seq_off) checked.seq_off = reinterpret_cast<const uint32_t*>(hb->l_seq);  // any non-null pointer
-    int rc = validate_batch(&checked);
-    if (rc != KDL_OK) return rc;
-    if (n_slots <= 0 || (n_slots & 3) || n_events < 0) return KDL_ERR_INVALID_ARG;
-    if (cudaSetDevice(c->device) != cudaSuccess) return KDL_ERR_CUDA;
-    std::memset(diag_out, 0, sizeof(*diag_out));
-    diag_out->read = -1;
-    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nx = (size_t)hb->n_complex;
-
+// the body of kdl_ctx_consensus after the first enqueue: every exit goes back through the caller, which
+// synchronises the stream (the caller's host buffers may be the source / target of copies still in flight)
+static int ctx_consensus_enqueued(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t n_events,
+                                  int64_t min_depth_ceil, uint8_t* calls_out, int32_t* counts_out,
+                                  int32_t* ins_events_out, kdl_diag* diag_out, int32_t* flag_host) {
+    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nh = (size_t)hb->n_hard;
     struct Copy { int which; const void* src; size_t bytes; };
     const Copy copies[] = {
         {kdl_ctx::B_REF_START, hb->ref_start, n * 4},
         {kdl_ctx::B_SEQ_OFF, hb->seq_off, n * 4},
         {kdl_ctx::B_L_SEQ, hb->l_seq, n * 4},
-        {kdl_ctx::B_CIG_OFF, hb->cig_off, nx ? (nx + 1) * 4 : 0},
-        {kdl_ctx::B_CIGAR, hb->cigar, (size_t)hb->n_ops * 4},
         {kdl_ctx::B_SEQ4, hb->seq4, (size_t)hb->seq4_words * 4},
         {kdl_ctx::B_CREAD_OFF, hb->contig_read_off, (nc + 1) * 8},
         {kdl_ctx::B_CLEN, hb->contig_len, nc * 4},
         {kdl_ctx::B_CSLOT, hb->contig_slot, nc * 8},
-        {kdl_ctx::B_CX_IDX, hb->complex_idx, nx * 4},
-        {kdl_ctx::B_EVT_OFF, hb->evt_off, nx ? (nx + 1) * 4 : 0},
+        {kdl_ctx::B_HARD_IDX, hb->hard_idx, nh * 4},
     };
-    for (const Copy& cp : copies)
-        if ((rc = c->ensure(cp.which, cp.bytes)) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_COUNTS, (size_t)n_slots * KDL_NCOL * 4)) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_EVENTS, (size_t)n_events * 16)) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_CALLS, (size_t)n_slots)) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_FLAG, 16)) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_DIAG, sizeof(kdl_diag))) != KDL_OK) return rc;
-    if ((rc = c->ensure(kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 32)) != KDL_OK) return rc;
-    const long long scan_blocks = kdl::seq_off_scan_blocks((long long)n);
-    if (derive_seq_off && (rc = c->ensure(kdl_ctx::B_SCAN, (size_t)scan_blocks * 4)) != KDL_OK) return rc;
-
     cudaStream_t st = c->stream;
-    cudaEventRecord(c->ev[0], st);
+    int rc;
+    if (cudaEventRecord(c->ev[0], st) != cudaSuccess) return KDL_ERR_CUDA;
     for (const Copy& cp : copies)
         if (cp.bytes && cp.src &&
             cudaMemcpyAsync(c->buf[cp.which].p, cp.src, cp.bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
             return KDL_ERR_CUDA;
-    cudaEventRecord(c->ev[1], st);
-    if (derive_seq_off) {  // K-1: seq_off = exclusive prefix sum of ceil(l_seq / 8)
-        if (kdl::launch_seq_off_scan((const int32_t*)c->buf[kdl_ctx::B_L_SEQ].p, (long long)n,
-                                     (uint32_t*)c->buf[kdl_ctx::B_SCAN].p, (uint32_t*)c->buf[kdl_ctx::B_SEQ_OFF].p,
-                                     st) != 0)
-            return KDL_ERR_CUDA;
-        g_launches.fetch_add(3, std::memory_order_relaxed);
-    }
+    if (cudaEventRecord(c->ev[1], st) != cudaSuccess) return KDL_ERR_CUDA;
 
     kdl_batch db = *hb;
     db.ref_start = (const int32_t*)c->buf[kdl_ctx::B_REF_START].p;
     db.seq_off = (const uint32_t*)c->buf[kdl_ctx::B_SEQ_OFF].p;
     db.l_seq = (const int32_t*)c->buf[kdl_ctx::B_L_SEQ].p;
-    db.cig_off = (const uint32_t*)c->buf[kdl_ctx::B_CIG_OFF].p;
-    db.cigar = (const uint32_t*)c->buf[kdl_ctx::B_CIGAR].p;
     db.seq4 = (const uint32_t*)c->buf[kdl_ctx::B_SEQ4].p;
     db.contig_read_off = (const int64_t*)c->buf[kdl_ctx::B_CREAD_OFF].p;
     db.contig_len = (const int32_t*)c->buf[kdl_ctx::B_CLEN].p;
     db.contig_slot = (const int64_t*)c->buf[kdl_ctx::B_CSLOT].p;
-    db.complex_idx = nx ? (const uint32_t*)c->buf[kdl_ctx::B_CX_IDX].p : nullptr;
-    db.evt_off = nx ? (const uint32_t*)c->buf[kdl_ctx::B_EVT_OFF].p : nullptr;
+    db.hard_idx = nh ? (const uint32_t*)c->buf[kdl_ctx::B_HARD_IDX].p : nullptr;
     db.tile_index = (n_slots % KDL_TILE) == 0 ? (uint32_t*)c->buf[kdl_ctx::B_TILE_IDX].p : nullptr;
 
     int32_t* d_counts = (int32_t*)c->buf[kdl_ctx::B_COUNTS].p;
@@ -162,13 +129,10 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     if ((rc = kdl_pileup_range(&db, d_counts, n_slots, 0, n_slots, pflags, n_events ? d_events : nullptr, d_flag,
                                st)) != KDL_OK)
         return rc;
-    c->table_slots = n_slots;
-    c->table_dirty_rest = hb->n_complex > 0;
     if ((rc = kdl_vote(d_counts, n_slots, min_depth_ceil, d_calls, st)) != KDL_OK) return rc;
-    cudaEventRecord(c->ev[2], st);
+    if (cudaEventRecord(c->ev[2], st) != cudaSuccess) return KDL_ERR_CUDA;
 
-    int32_t flag[4] = {0, 0, 0, 0};
-    if (cudaMemcpyAsync(flag, d_flag, 16, cudaMemcpyDeviceToHost, st) != cudaSuccess) return KDL_ERR_CUDA;
+    if (cudaMemcpyAsync(flag_host, d_flag, 16, cudaMemcpyDeviceToHost, st) != cudaSuccess) return KDL_ERR_CUDA;
     if (calls_out && cudaMemcpyAsync(calls_out, d_calls, (size_t)n_slots, cudaMemcpyDeviceToHost, st) != cudaSuccess)
         return KDL_ERR_CUDA;
     if (counts_out && cudaMemcpyAsync(counts_out, d_counts, (size_t)n_slots * KDL_NCOL * 4,
@@ -177,11 +141,14 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     if (ins_events_out && n_events &&
         cudaMemcpyAsync(ins_events_out, d_events, (size_t)n_events * 16, cudaMemcpyDeviceToHost, st) != cudaSuccess)
         return KDL_ERR_CUDA;
-    cudaEventRecord(c->ev[3], st);
+    if (cudaEventRecord(c->ev[3], st) != cudaSuccess) return KDL_ERR_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess) return KDL_ERR_CUDA;
-    for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&c->ms[k], c->ev[k], c->ev[k + 1]);
+    c->table_slots = n_slots;
+    c->table_dirty_rest = hb->n_complex > 0;
+    for (int k = 0; k < 3; ++k)
+        if (cudaEventElapsedTime(&c->ms[k], c->ev[k], c->ev[k + 1]) != cudaSuccess) c->ms[k] = 0.f;
 
-    if (flag[0]) {  // some read raised: find the first one in reference iteration order
+    if (flag_host[0]) {  // some read raised: find the first one in reference iteration order
         kdl_diag* d_diag = (kdl_diag*)c->buf[kdl_ctx::B_DIAG].p;
         if ((rc = kdl_diagnose(&db, d_diag, st)) != KDL_OK) return rc;
         if (cudaMemcpyAsync(diag_out, d_diag, sizeof(kdl_diag), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
@@ -190,6 +157,42 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
         return diag_out->status ? diag_out->status : KDL_ERR_CUDA;
     }
     return KDL_OK;
+}
+
+int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t n_events,
+                      int64_t min_depth_ceil, uint8_t* calls_out, int32_t* counts_out,
+                      int32_t* ins_events_out, kdl_diag* diag_out) {
+    if (!c || !diag_out || !hb) return KDL_ERR_INVALID_ARG;
+    int rc = validate_batch(hb);
+    if (rc != KDL_OK) return rc;
+    if (n_slots <= 0 || (n_slots & 3) || n_events < 0) return KDL_ERR_INVALID_ARG;
+    if (cudaSetDevice(c->device) != cudaSuccess) return KDL_ERR_CUDA;
+    std::memset(diag_out, 0, sizeof(*diag_out));
+    diag_out->read = -1;
+    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nh = (size_t)hb->n_hard;
+    const struct { int which; size_t bytes; } sizes[] = {
+        {kdl_ctx::B_REF_START, n * 4}, {kdl_ctx::B_SEQ_OFF, n * 4}, {kdl_ctx::B_L_SEQ, n * 4},
+        {kdl_ctx::B_SEQ4, (size_t)hb->seq4_words * 4 + 16}, {kdl_ctx::B_CREAD_OFF, (nc + 1) * 8},
+        {kdl_ctx::B_CLEN, nc * 4}, {kdl_ctx::B_CSLOT, nc * 8}, {kdl_ctx::B_HARD_IDX, nh * 4},
+        {kdl_ctx::B_COUNTS, (size_t)n_slots * KDL_NCOL * 4}, {kdl_ctx::B_EVENTS, (size_t)n_events * 16},
+        {kdl_ctx::B_CALLS, (size_t)n_slots}, {kdl_ctx::B_FLAG, 16}, {kdl_ctx::B_DIAG, sizeof(kdl_diag)},
+        {kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 32},
+    };
+    for (const auto& z : sizes)
+        if ((rc = c->ensure(z.which, z.bytes)) != KDL_OK) return rc;
+    // from here on work is enqueued on the context's stream against the caller's host buffers: whatever
+    // happens, do not return before the stream has drained
+    int32_t flag[4] = {0, 0, 0, 0};
+    rc = ctx_consensus_enqueued(c, hb, n_slots, n_events, min_depth_ceil, calls_out, counts_out, ins_events_out,
+                                diag_out, flag);
+    if (rc != KDL_OK) {
+        cudaStreamSynchronize(c->stream);
+        if (rc != KDL_ERR_INDEX && rc != KDL_ERR_KEY) {
+            c->table_slots = -1;  // the table's contents are unknown after a failed call
+            c->ms[0] = c->ms[1] = c->ms[2] = 0.f;
+        }
+    }
+    return rc;
 }
 
 int kdl_ctx_last_timing(kdl_ctx* c, float* h2d_ms, float* kernel_ms, float* d2h_ms) {

@@ -31,6 +31,12 @@ __device__ __forceinline__ int nibble_at(const uint32_t* __restrict__ seq, long 
     return (int)((seq[q >> 3] >> (28 - 4 * (int)(q & 7))) & 0xFu);
 }
 
+// SEQ length of a complex read's l_seq word: tile-eligible reads keep it in bits 0..15 (bits 16..22 hold their
+// M-op count), KDL_HARD reads in bits 0..29
+__device__ __forceinline__ long long complex_len(uint32_t lraw) {
+    return (lraw & KDL_HARD) ? (long long)(lraw & 0x3fffffffu) : (long long)(lraw & KDL_LEN_MASK);
+}
+
 // Python list indexing (list length n): negative indices wrap once, otherwise IndexError (-1).
 __device__ __forceinline__ long long pyindex(long long i, long long n) {
     if (i < 0) i += n;

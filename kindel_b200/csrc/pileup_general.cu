@@ -1,4 +1,9 @@
-// pileup_general.cu -- K1g: the general CIGAR walk (any op mix), one warp per read.
+// pileup_general.cu -- K1g: the general CIGAR walk (any op mix), one warp per read, global atomics.
+//
+// Walks the reads the tile kernel leaves out: the KDL_HARD ones of a coordinate-sorted batch (they may wrap a
+// Python index or raise, or are too long for a tile) -- listed in batch.hard_idx -- or, for batches the tile
+// kernel cannot take at all (unsorted input), every complex read (list == NULL: all reads are scanned and the
+// simple ones skipped).  A complex read's CIGAR sits behind its bases in seq4: [n_ops][evt_off][ops...].
 //
 // Restates the per-read loop of the reference, kindel/kindel.py:40-81 (M/=/X :49-54, I :55-58,
 // D :59-62, left clip :64-73, right clip :74-81; N/H/P fall through), including its edge
@@ -15,28 +20,31 @@
 namespace kdl {
 
 __global__ void __launch_bounds__(256)
-pileup_general_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
-                      int32_t* __restrict__ ins_events, int32_t* __restrict__ err_flag) {
+pileup_general_kernel(kdl_batch b, const uint32_t* __restrict__ list, long long n_list, int32_t* __restrict__ counts,
+                      long long n_slots, int32_t* __restrict__ ins_events, int32_t* __restrict__ err_flag) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long n_list = b.n_complex;
     bool bad = false;
 
     for (long long j = warp0; j < n_list; j += n_warps) {
-        const long long r = (long long)b.complex_idx[j];
+        const long long r = list ? (long long)list[j] : j;
+        const uint32_t lraw = (uint32_t)b.l_seq[r];
+        if (!(lraw & KDL_COMPLEX)) continue;  // simple read: K1 / K1s count it
         const int c = find_contig(b.contig_read_off, b.n_contigs, r);
         const long long L = b.contig_len[c];
         const long long base = b.contig_slot[c];
-        const long long lseq = (long long)(b.l_seq[r] & 0x7fffffff);
+        const long long lseq = complex_len(lraw);
         const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
-        const uint32_t c0 = b.cig_off[j], c1 = b.cig_off[j + 1];  // CIGARs travel for complex reads only
+        const uint32_t* __restrict__ blk = seq + ((lseq + 7) >> 3);  // [n_ops][evt_off][ops...]
+        const uint32_t c0 = 0, c1 = blk[0];
+        const uint32_t* __restrict__ cig = blk + 2;
         long long r_pos = b.ref_start[r];
         long long q_pos = 0;
-        uint32_t evt = b.evt_off[j];
+        uint32_t evt = blk[1];
 
         for (uint32_t i = c0; i < c1; ++i) {
-            const uint32_t cg = b.cigar[i];
+            const uint32_t cg = cig[i];
             const long long len = cg >> 4;
             const int op = cg & 0xF;
             if (op == 0 || op == 7 || op == 8) {  // M = X
@@ -123,19 +131,20 @@ pileup_general_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slo
 // raise; the minimum over reads of (read << 24 | kind << 20 | nibble << 16 | op) is the error of
 // the first offending record.
 __device__ unsigned long long diagnose_read(const kdl_batch& b, long long j) {
-    const long long r = (long long)b.complex_idx[j];  // only complex reads can raise (flatten contract)
+    const long long r = (long long)b.hard_idx[j];  // only KDL_HARD reads can raise (flatten contract)
     const int c = find_contig(b.contig_read_off, b.n_contigs, r);
     const long long L = b.contig_len[c];
-    const int32_t lraw = b.l_seq[r];
-    const long long lseq = (long long)(lraw & 0x7fffffff);
+    const long long lseq = complex_len((uint32_t)b.l_seq[r]);
     const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
-    const uint32_t c0 = b.cig_off[j], c1 = b.cig_off[j + 1];
+    const uint32_t* __restrict__ blk = seq + ((lseq + 7) >> 3);
+    const uint32_t c0 = 0, c1 = blk[0];
+    const uint32_t* __restrict__ cig = blk + 2;
     long long r_pos = b.ref_start[r], q_pos = 0;
 #define KDL_FAIL(kind, nib)                                                                     \
     return ((unsigned long long)r << 24) | ((unsigned long long)(kind) << 20) |                 \
            ((unsigned long long)(nib) << 16) | (unsigned long long)((i - c0) > 0xFFFF ? 0xFFFF : (i - c0))
     for (uint32_t i = c0; i < c1; ++i) {
-        const uint32_t cg = b.cigar[i];
+        const uint32_t cg = cig[i];
         const long long len = cg >> 4;
         const int op = cg & 0xF;
         if (op == 0 || op == 7 || op == 8) {
@@ -191,7 +200,7 @@ __global__ void diagnose_init_kernel(kdl_diag* d) {
 
 __global__ void __launch_bounds__(256) diagnose_kernel(kdl_batch b, kdl_diag* d) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= b.n_complex) return;
+    if (j >= b.n_hard) return;
     const unsigned long long key = diagnose_read(b, j);
     if (key != ~0ull) atomicMin(reinterpret_cast<unsigned long long*>(&d->read), key);
 }

@@ -1,0 +1,648 @@
+// pileup_tile.cu -- K1: the owner-computes pileup of coordinate-sorted reads, a warp-specialised pipeline.
+//
+// What it computes is the per-read loop of the reference, kindel/kindel.py:40-81, for every read that is not
+// KDL_HARD: `weights[pos][base] += 1` for the bases of M/=/X ops (kindel.py:49-54) as a positional population
+// count (tile_common.cuh), and -- for complex reads -- the insertion / deletion / clip updates (kindel.py:55-81).
+//
+//   * The slot space is cut into tiles of KDL_TILE = 512 slots.  Because the reads are coordinate-sorted, the
+//     reads that can touch a tile are ONE index range and ONE byte range of seq4 (K0, tile_common.cuh); a tile
+//     is owned by one CTA (or, for small references piled deep, by `split` CTAs that share it by read range and
+//     flush with REDs), so the weight columns are written with plain 128-bit stores: no atomics, no memset.
+//   * Two CTAs per SM, each 4 PRODUCER + 8 CONSUMER warps over a two-stage shared-memory ring, the register
+//     file re-balanced with setmaxnreg.  An ITEM is (tile, up to kRmax reads).  Producers: wait for a free stage,
+//     ONE 1-D bulk copy (TMA) of the item's bytes, per-read metadata, the +1/-1 coverage array and its prefix
+//     sums; they run one item ahead with the next item's metadata words in flight (cp.async).  Consumers: each
+//     warp owns a 64-slot window, each quarter-warp walks a different read (one funnel shift of two staged
+//     words per lane and read, 7 full adders per 8 reads), and flushes at the end of a tile.  Consumers never
+//     touch global memory except for the table stores and never meet a CTA-wide barrier.
+//   * Complex reads (indels, clips; include/kindel_b200.h) carry their CIGAR behind their bases in seq4, so it
+//     arrives with the bulk copy.  A producer thread walks it ONCE per (read, tile): every M/=/X segment that
+//     overlaps the tile becomes a PIECE (virtual start = slot of the read's base 0, clipped slot range), which
+//     the consumers count with the same bit-sliced adders plus a nibble mask; I / D / clip updates that fall
+//     into the tile are sparse REDs issued by the producer (exactly once: slots are owned by tiles), insertion
+//     events are written to their deterministic rows.  Reads that could wrap a Python index or raise
+//     (KDL_HARD) are left to K1g.
+//
+// Preconditions (checked by the host side of the ABI): reads_sorted, classification as in include/kindel_b200.h.
+#include "tile_common.cuh"
+
+namespace kdl {
+
+constexpr int W_CONSUMERS = 8;   // consumer warps (one 64-slot window each)
+constexpr int W_PRODUCERS = 4;   // producer warps
+constexpr int W_STAGES = 2;
+constexpr int W_THREADS = 32 * (W_CONSUMERS + W_PRODUCERS);
+constexpr int W_PT = 32 * W_PRODUCERS;  // producer threads
+template <bool kCx> struct TileRegs { static constexpr int kProducer = kCx ? 56 : 40, kConsumer = kCx ? 88 : 96; };  // 128 p + 256 c <= 384 * 80
+
+// kCx = false: batches without tile-eligible complex reads (no piece list, larger stages)
+template <bool kCx> struct TileCfg;
+template <> struct TileCfg<false> {
+    static constexpr int kRmax = 512;    // reads per item
+    static constexpr int kCapW = 9216;   // words of seq4 per item (36 KB: ~485 reads of 150 bases)
+    static constexpr int kPcap = 0;      // pieces of complex reads per item
+};
+template <> struct TileCfg<true> {
+    static constexpr int kRmax = 384;
+    static constexpr int kCapW = 7168;   // 28 KB
+    static constexpr int kPcap = 768;
+};
+
+enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
+
+template <class C>
+struct TileStage {
+    uint32_t seq[C::kCapW];
+    // per staged read (32 sentinels follow the last one); entry of read i at i + i/8 (one pad per 8: the four
+    // quarter-warps' entries then sit 144 B = 4 banks apart):
+    //   .x  4 * ceil(start / 8): byte offset, relative to the tile, of the first 8-slot group the read can serve
+    //   .y  shared-memory address (u32) of the read's first word
+    //   .z  bytes of packed bases (0 = not a simple read: adds nothing in the simple loop)
+    //   .w  funnel-shift amount 4 * ((-start) & 7)
+    int4 meta[C::kRmax + 40 + (C::kRmax + 40) / 8];
+    // pieces of complex reads: .x/.y/.z as above with start = the slot of the read's base 0 (virtual start);
+    // .w = shift | s0 << 8 | s1 << 20, [s0, s1) the piece's slots clipped to the tile.  px[kPcap] = a piece that
+    // covers nothing (what idle lanes of a block read).
+    int4 px[C::kPcap + 1];
+    int gs[C::kRmax + 32];       // start slot relative to the tile (all reads: the array stays sorted)
+    int cov[KDL_TILE];           // reads / pieces of THIS item covering each slot
+    int diff[KDL_TILE + 32];     // producers only: +1 at a piece's first slot, -1 behind its last
+    long long tile_slot;
+    int n_sub;
+    int flags;
+    int n_px;
+    int pad;
+};
+
+template <class C>
+struct TileSmem {
+    TileStage<C> st[W_STAGES];
+    int raw[3][C::kRmax];          // producers: l_seq / ref_start / seq_off of the NEXT unit's first reads (cp.async)
+    unsigned short queue[W_CONSUMERS][64];  // consumers (kCx): indices of the pieces that overlap the warp's window
+    int scan[W_PRODUCERS * 4 + 4];  // producers (kCx): per-group piece totals, cut counter
+    uint64_t full[W_STAGES];       // producers -> consumers: 4 warp arrivals (metadata, pieces, coverage written)
+    uint64_t landed[W_STAGES];     // the bulk copy's bytes (1 arrival + tx): consumers, and producers that explode
+    uint64_t empty[W_STAGES];      // consumers -> producers: 8 warp arrivals
+};
+static_assert(sizeof(TileSmem<TileCfg<false>>) <= 113 * 1024 && sizeof(TileSmem<TileCfg<true>>) <= 113 * 1024,
+              "K1 must fit two CTAs per SM");
+static_assert(offsetof(TileStage<TileCfg<false>>, diff) % 16 == 0 && sizeof(TileStage<TileCfg<false>>) % 16 == 0 &&
+              offsetof(TileStage<TileCfg<true>>, diff) % 16 == 0 && sizeof(TileStage<TileCfg<true>>) % 16 == 0 &&
+              offsetof(TileStage<TileCfg<true>>, px) % 16 == 0 && offsetof(TileStage<TileCfg<true>>, meta) % 16 == 0,
+              "128-bit shared loads of the difference array, the metadata and the pieces");
+
+// kFlush: F_STORE = the weight columns hold stale data (first flush of a window stores, untouched tiles are stored
+// as zeros); F_ADD = add to what is there; F_ATOMIC = `split` CTAs share a tile, the table was zeroed, flush with REDs.
+template <int kFlush, bool kCx>
+__global__ void __launch_bounds__(W_THREADS, 2)
+pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
+                   const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles, int split,
+                   int32_t* __restrict__ ins_events) {
+    KDL_DYNAMIC_SMEM(smem_raw);
+    using C = TileCfg<kCx>;
+    using Smem = TileSmem<C>;
+    using Stage = TileStage<C>;
+    constexpr int W_RMAX = C::kRmax, W_CAPW = C::kCapW, W_PCAP = C::kPcap;
+    constexpr bool kFresh = kFlush == F_STORE;
+    constexpr int kAdd = kFlush == F_ATOMIC ? F_ATOMIC : F_ADD;
+    Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int maxlen = b.max_simple_len;
+    const long long n_units = n_tiles * split;
+
+    if (tid == 0) {
+        for (int s = 0; s < W_STAGES; ++s) {
+            mbar_init(&sm.full[s], W_PRODUCERS);
+            mbar_init(&sm.landed[s], 1);
+            mbar_init(&sm.empty[s], W_CONSUMERS);
+        }
+    }
+    for (int s = 0; s < W_STAGES; ++s) {
+        for (int k = tid; k < KDL_TILE + 32; k += W_THREADS) sm.st[s].diff[k] = 0;
+        if (tid == 0) sm.st[s].px[W_PCAP] = make_int4(0x10000000, (int)smem_u32(sm.st[s].seq), 0, 0);
+    }
+    if (tid < W_PRODUCERS * 4 + 4) sm.scan[tid] = 0;
+    __syncthreads();
+
+    if (warp >= W_CONSUMERS) {
+        // =========================== PRODUCERS ====================================================
+        reg_dealloc<TileRegs<kCx>::kProducer>();
+        const int pw = warp - W_CONSUMERS;          // 0..3
+        const int ptid = tid - 32 * W_CONSUMERS;    // 0..127
+        long long item = 0;
+        auto acquire_stage = [&](long long it) -> Stage& {
+            const int s = (int)(it % W_STAGES);
+            const uint32_t round = (uint32_t)(it / W_STAGES);
+            if (round > 0) mbar_wait(&sm.empty[s], (round - 1) & 1u);  // consumers released its last use
+            return sm.st[s];
+        };
+        auto publish = [&](long long it) {  // this warp's part of the item is written
+            const int s = (int)(it % W_STAGES);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.full[s]);
+        };
+
+        // The producers run a software pipeline of their own: the index entry of the next unit's tile and the
+        // three metadata words of its first reads are in flight (cp.async into sm.raw, each thread fetching
+        // exactly the elements it will consume) while the current item is being prepared.
+        constexpr int PER = W_RMAX / W_PT;  // reads per producer thread and item
+        struct Unit { long long lo, hi, plo, phi; uint32_t wa, wend; uint2 ic; long long cs; };
+        auto load_unit = [&](long long w, Unit& u) {
+            if (w >= n_units) { u.lo = u.hi = u.plo = u.phi = 0; u.wa = u.wend = 0; u.ic = make_uint2(0, 0); u.cs = 0; return; }
+            const long long t = tile_lo + w / split;
+            const int part = (int)(w % split);
+            const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * t));
+            u.ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * t + 4));
+            u.lo = ix.x;
+            u.hi = ix.y;
+            u.wa = ix.z;
+            u.wend = ix.w;
+            const long long n = u.hi - u.lo;
+            u.plo = u.lo + n * part / split;
+            u.phi = u.lo + n * (part + 1) / split;
+            u.cs = b.contig_slot[u.ic.x];
+        };
+        auto prefetch_raw = [&](const Unit& u) {
+            const long long n = u.phi - u.plo;
+            const int cnt = (int)(n < W_RMAX ? n : W_RMAX);
+            for (int i = ptid; i < cnt; i += W_PT) {
+                cp_async4(&sm.raw[0][i], b.l_seq + u.plo + i);
+                cp_async4(&sm.raw[1][i], b.ref_start + u.plo + i);
+                cp_async4(&sm.raw[2][i], b.seq_off + u.plo + i);
+            }
+        };
+        Unit u, nu;
+        load_unit(blockIdx.x, u);
+        prefetch_raw(u);
+
+        for (long long w = blockIdx.x; w < n_units; w += gridDim.x) {
+            load_unit(w + gridDim.x, nu);  // consumed at the end of this iteration
+            const long long tile_slot = (tile_lo + w / split) * KDL_TILE;
+            if (u.plo >= u.phi) {
+                if (kFresh) {  // consumers must store zeros: a header-only item
+                    Stage& st = acquire_stage(item);
+                    if (ptid == 0) {
+                        st.tile_slot = tile_slot; st.n_sub = 0; st.n_px = 0; st.flags = ITEM_FIRST | ITEM_LAST | ITEM_EMPTY;
+                        mbar_expect_tx(&sm.landed[(int)(item % W_STAGES)], 0);
+                    }
+                    publish(item);
+                    ++item;
+                }
+                prefetch_raw(nu);  // nothing was in flight for an empty unit
+                u = nu;
+                continue;
+            }
+            const bool one_contig = u.ic.x == u.ic.y;
+            const long long slot_base = one_contig ? u.cs - tile_slot : 0;
+            long long c0 = u.plo;
+            bool first = true;
+            bool raw_pending = true;
+            while (c0 < u.phi) {
+                long long c1 = c0 + W_RMAX < u.phi ? c0 + W_RMAX : u.phi;
+                const long long wa = c0 == u.lo ? (long long)u.wa : (long long)(b.seq_off[c0] & ~3u);
+                long long wend = c1 == u.hi ? (long long)u.wend : (long long)b.seq_off[c1];
+                bool skip = false;
+                while (wend - wa > W_CAPW) {
+                    if (c1 - c0 == 1) { skip = true; break; }  // one read too long to stage: never tile-eligible
+                    const long long n = c1 - c0;               // cut where the capacity ends
+                    long long n2 = n * W_CAPW / (wend - wa);
+                    n2 = n2 >= n ? n - 1 : (n2 < 1 ? 1 : n2);
+                    c1 = c0 + n2;
+                    wend = (long long)b.seq_off[c1];
+                }
+                int n_sub = skip ? 0 : (int)(c1 - c0);
+                // this thread's reads of the item: from the prefetched words (first item of the unit) or directly
+                int l[PER], rs[PER];
+                uint32_t so[PER];
+                if (c0 == u.plo && raw_pending) {
+                    cp_async_wait_all();
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        const int i = ptid + k * W_PT;
+                        const int ii = i < n_sub ? i : ptid;
+                        l[k] = sm.raw[0][ii];
+                        rs[k] = sm.raw[1][ii];
+                        so[k] = (uint32_t)sm.raw[2][ii];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        const int i = ptid + k * W_PT;
+                        const long long r = c0 + (i < n_sub ? i : 0);
+                        l[k] = b.l_seq[r];
+                        rs[k] = b.ref_start[r];
+                        so[k] = b.seq_off[r];
+                    }
+                }
+                if (raw_pending) {  // own elements are in registers: refill them for the next unit
+                    prefetch_raw(nu);
+                    raw_pending = false;
+                }
+                // ---- complex reads: where each one's pieces go (exclusive prefix of the M-op counts in read order),
+                // and a cut of the item if they do not fit the piece list
+                int pre[PER];
+                int n_px = 0, n_cx = 0;  // pieces / tile-eligible complex reads of the item
+                if constexpr (kCx) {
+                    int ub[PER];
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) {
+                        const int i = ptid + k * W_PT;
+                        const uint32_t lw = (uint32_t)l[k];
+                        // low 16 bits: pieces (M-op count), bit 16 up: one per tile-eligible complex read
+                        ub[k] = (i < n_sub && (lw & (KDL_COMPLEX | KDL_HARD)) == KDL_COMPLEX)
+                                    ? (int)((lw >> KDL_NM_SHIFT) & KDL_NM_MASK) | 0x10000 : 0;
+                        int incl = ub[k];  // reads ptid + k * 128: group g = 4 k + pw holds 32 consecutive reads
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                            if (lane >= d) incl += o;
+                        }
+                        pre[k] = incl - ub[k];
+                        if (lane == 31) sm.scan[4 * k + pw] = incl;
+                    }
+                    producer_sync();
+                    int run = 0;
+#pragma unroll
+                    for (int g = 0; g < 4 * PER; ++g) {
+                        const int t = sm.scan[g];
+#pragma unroll
+                        for (int k = 0; k < PER; ++k)
+                            if (g == 4 * k + pw) pre[k] += run;
+                        run += t;
+                    }
+                    n_px = run & 0xFFFF;
+                    n_cx = run >> 16;
+#pragma unroll
+                    for (int k = 0; k < PER; ++k) { pre[k] &= 0xFFFF; ub[k] &= 0xFFFF; }
+                    if (n_px > W_PCAP) {  // rare: cut the item behind the last read whose pieces still fit
+                        int fits = 0;
+#pragma unroll
+                        for (int k = 0; k < PER; ++k) {
+                            const int i = ptid + k * W_PT;
+                            fits += __popc(__ballot_sync(0xffffffffu, i < n_sub && pre[k] + ub[k] <= W_PCAP));
+                        }
+                        if (lane == 0) atomicAdd(&sm.scan[4 * W_PRODUCERS], fits);
+                        producer_sync();
+                        n_sub = sm.scan[4 * W_PRODUCERS];  // >= 1: one read has at most KDL_TILE_MAXOPS <= kPcap pieces
+                        c1 = c0 + n_sub;
+                        wend = (long long)b.seq_off[c1];   // c1 < u.phi <= n_reads here
+                        n_px = 0;
+#pragma unroll
+                        for (int k = 0; k < PER; ++k) {
+                            const int i = ptid + k * W_PT;
+                            if (i >= n_sub) ub[k] = 0;
+                            if (i == n_sub - 1) sm.scan[4 * W_PRODUCERS + 1] = pre[k] + ub[k];  // (n_cx stays > 0)
+                        }
+                        producer_sync();
+                        n_px = sm.scan[4 * W_PRODUCERS + 1];
+                        if (ptid == 0) sm.scan[4 * W_PRODUCERS] = 0;
+                    }
+                    // (the next item's first write to sm.scan[g] comes after its acquire/metadata work and at least
+                    // one producer_sync of this item: no thread still reads the totals then)
+                }
+                const bool last = c1 >= u.phi;
+                Stage& st = acquire_stage(item);
+                const int stage_id = (int)(item % W_STAGES);
+                const uint32_t seq_base = smem_u32(st.seq);
+                {
+                    const long long n_words = skip ? 0 : wend - wa;
+                    const long long avail = b.seq4_words - wa;
+                    const long long want = (n_words + 3) & ~3ll;
+                    const long long bulk_words = want <= avail ? want : (avail & ~3ll);
+                    const uint32_t tx = (uint32_t)(bulk_words * 4);
+                    if (ptid == 0) {  // announce the bytes (one arrival), then let the TMA engine copy them
+                        mbar_expect_tx(&sm.landed[stage_id], tx);
+                        if (bulk_words) bulk_g2s(st.seq, b.seq4 + wa, tx, &sm.landed[stage_id]);
+                    }
+                    if (bulk_words < n_words) {  // the (at most one) partial granule at the array's end, by hand
+                        if (ptid < 4) {
+                            const long long wq = bulk_words + ptid;
+                            st.seq[wq] = wq < avail ? b.seq4[wa + wq] : 0u;
+                        }
+                        if constexpr (kCx) producer_sync();  // a CIGAR may sit in those words (uniform branch)
+                    }
+                }
+                int gsv[PER];
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const int i = ptid + k * W_PT;
+                    gsv[k] = 0;
+                    if (i < n_sub) {
+                        long long g;
+                        if (one_contig) {
+                            g = slot_base + rs[k];
+                        } else {
+                            const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
+                            g = b.contig_slot[c] + rs[k] - tile_slot;
+                        }
+                        const int gs = (int)g;  // inside (-reach_right, 512 + reach_left) by construction of the index
+                        gsv[k] = gs;
+                        int nb = 0;
+                        if (l[k] > 0) {  // simple read (bit 31 clear)
+                            nb = ((l[k] + 7) >> 3) << 2;
+                            const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
+                            if (cs < ce) {
+                                atomicAdd(st.diff + cs, 1);
+                                atomicAdd(st.diff + ce, -1);
+                            }
+                        }
+                        st.gs[i] = gs;
+                        st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
+                                                          (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
+                                                          ((-gs) & 7) << 2);
+                    }
+                }
+                if (ptid < 40) {  // sentinels behind the last read
+                    const int i = n_sub + ptid;
+                    if (ptid < 32) st.gs[i] = 0x10000000;
+                    st.meta[i + (i >> 3)] = make_int4(0x10000000, (int)seq_base, 0, 0);
+                }
+                if (ptid == 0) {
+                    st.tile_slot = tile_slot;
+                    st.n_sub = n_sub;
+                    st.n_px = n_px;
+                    st.flags = (first ? ITEM_FIRST : 0) | (last ? ITEM_LAST : 0);
+                }
+                if constexpr (kCx) {
+                    if (n_cx > 0) {
+                        // ---- explode the complex reads: their CIGARs came with the bulk copy
+                        mbar_wait(&sm.landed[stage_id], (uint32_t)((item / W_STAGES) & 1));
+#pragma unroll
+                        for (int k = 0; k < PER; ++k) {
+                            const int i = ptid + k * W_PT;
+                            const uint32_t lw = (uint32_t)l[k];
+                            if (i >= n_sub || (lw & (KDL_COMPLEX | KDL_HARD)) != KDL_COMPLEX) continue;
+                            const int lseq = (int)(lw & KDL_LEN_MASK);
+                            const int nbw = (lseq + 7) >> 3;
+                            const uint32_t* rw = st.seq + ((long long)so[k] - wa);  // the read's block in shared memory
+                            const uint32_t raddr = seq_base + (uint32_t)(((long long)so[k] - wa) << 2);
+                            const int n_ops = (int)rw[nbw];
+                            uint32_t evt = rw[nbw + 1];
+                            const uint32_t* ops = rw + nbw + 2;
+                            int pos = pre[k];
+                            const int pend = pos + (int)((lw >> KDL_NM_SHIFT) & KDL_NM_MASK);
+                            int r = gsv[k], q = 0;
+                            auto nib = [&](int qq) { return (int)((rw[qq >> 3] >> (28 - 4 * (qq & 7))) & 0xFu); };
+                            auto red = [&](int col, int rel) {  // only slots of THIS tile: every slot has one owner
+                                if ((unsigned)rel < (unsigned)KDL_TILE)
+                                    atomicAdd(counts + (long long)col * n_slots + tile_slot + rel, 1);
+                            };
+                            for (int o = 0; o < n_ops; ++o) {
+                                const uint32_t cg = ops[o];
+                                const int len = (int)(cg >> 4);
+                                const int op = (int)(cg & 0xF);
+                                if (op == 0 || op == 7 || op == 8) {  // M = X (kindel.py:49-54): a piece
+                                    const int s0 = r < 0 ? 0 : r, s1 = r + len > KDL_TILE ? KDL_TILE : r + len;
+                                    if (s0 < s1) {
+                                        const int v = r - q;  // slot of the read's base 0
+                                        atomicAdd(st.diff + s0, 1);
+                                        atomicAdd(st.diff + s1, -1);
+                                        st.px[pos++] = make_int4(((v + 7) >> 3) << 2, (int)raddr, nbw << 2,
+                                                                 (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
+                                    }
+                                    r += len;
+                                    q += len;
+                                } else if (op == 1) {  // I (kindel.py:55-58)
+                                    if ((unsigned)r < (unsigned)KDL_TILE) {
+                                        atomicAdd(counts + (long long)KDL_INS * n_slots + tile_slot + r, 1);
+                                        if (ins_events)
+                                            reinterpret_cast<int4*>(ins_events)[evt] =
+                                                make_int4((int)(tile_slot + r), (int)(c0 + i), q, len);
+                                    }
+                                    evt += 1;
+                                    q += len;
+                                } else if (op == 2) {  // D (kindel.py:59-62)
+                                    for (int d = 0; d < len; ++d) red(KDL_DEL, r + d);
+                                    r += len;
+                                } else if (op == 4) {  // S
+                                    if (o == 0) {      // left clip (kindel.py:64-73)
+                                        red(KDL_CLIP_ENDS, r);
+                                        for (int g = 0; g < len; ++g) {
+                                            const int rel = r - len + g;
+                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CEW_A + nib2col(nib(g)), rel);
+                                        }
+                                        q += len;
+                                    } else {           // right clip (kindel.py:74-81); never reaches the contig end here
+                                        red(KDL_CLIP_STARTS, r - 1);
+                                        for (int d = 0; d < len; ++d) {
+                                            const int rel = r + d;
+                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CSW_A + nib2col(nib(q + d)), rel);
+                                        }
+                                        r += len;
+                                        q += len;
+                                    }
+                                }
+                                // N, H, P: no-op (kindel.py:49-63 has no branch for them)
+                            }
+                            while (pos < pend) st.px[pos++] = make_int4(0x10000000, (int)seq_base, 0, 0);  // covers nothing
+                        }
+                    }
+                }
+                producer_sync();  // difference array complete
+                {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
+                    const int w0 = (KDL_TILE / W_PRODUCERS) * pw;
+                    int pre_sum = 0;
+                    for (int k = 4 * lane; k < w0; k += 128) {  // w0 is a multiple of 128, diff is 16-byte aligned
+                        const int4 v4 = *reinterpret_cast<const int4*>(st.diff + k);
+                        pre_sum += (v4.x + v4.y) + (v4.z + v4.w);
+                    }
+#pragma unroll
+                    for (int d = 16; d; d >>= 1) pre_sum += __shfl_xor_sync(0xffffffffu, pre_sum, d);
+                    constexpr int E = KDL_TILE / W_PRODUCERS / 32;  // entries per lane
+                    int v[E];
+                    int run = 0;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) { v[k] = st.diff[w0 + E * lane + k]; run += v[k]; }
+                    int incl = run;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    int acc = pre_sum + incl - run;
+#pragma unroll
+                    for (int k = 0; k < E; ++k) { acc += v[k]; st.cov[w0 + E * lane + k] = acc; }
+                }
+                producer_sync();  // everybody has read diff: clean it for the stage's next use
+                for (int k = ptid; k < (KDL_TILE + 32) / 4; k += W_PT)
+                    reinterpret_cast<int4*>(st.diff)[k] = make_int4(0, 0, 0, 0);
+                publish(item);
+                ++item;
+                first = false;
+                c0 = c1;
+            }
+            u = nu;
+        }
+        {   // END item
+            Stage& st = acquire_stage(item);
+            if (ptid == 0) {
+                st.tile_slot = 0; st.n_sub = 0; st.n_px = 0; st.flags = ITEM_END;
+                mbar_expect_tx(&sm.landed[(int)(item % W_STAGES)], 0);
+            }
+            publish(item);
+        }
+        return;
+    }
+
+    // =============================== CONSUMERS ===================================================
+    reg_alloc<TileRegs<kCx>::kConsumer>();
+    const int quarter = lane >> 3;
+    const int wlo = warp * F_WIN;
+    const int p8b = (wlo >> 1) + 4 * (lane & 7);  // 4 * (lane's first slot / 8): byte offset of its word
+    Planes acc;
+    acc.clear();
+    int rawacc[8], covacc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { rawacc[k] = 0; covacc[k] = 0; }
+    int blocks_since_flush = 0;
+    uint32_t pend8 = 0;  // weight-8 carry of an odd block, waiting for its partner
+    bool stored = false;
+    long long tile_slot = 0;
+
+    // one block = 8 words per lane (the quarter's 8 reads / pieces) into the counters; two blocks share one ripple
+    auto add_block = [&](const uint32_t (&x)[8]) {
+        const uint32_t e8 = acc.add8_carry(x);
+        if (blocks_since_flush & 1) {  // second block of a pair: eights + eights -> sixteens, one ripple
+            uint32_t c16;
+            csa(c16, acc.p[3], acc.p[3], pend8, e8);
+            acc.template ripple<4>(c16);
+        } else {
+            pend8 = e8;
+        }
+        if (++blocks_since_flush == F_FLUSH_BLOCKS) {
+            acc.template ripple<3>(pend8);  // F_FLUSH_BLOCKS is odd: one carry is pending
+            if (kFresh && !stored)
+                flush_window<F_STORE, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            else
+                flush_window<kAdd, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            stored = true;
+            blocks_since_flush = 0;
+        }
+    };
+    // the two staged words of entry `mt` that cover the lane's 8 slots, funnel-shifted into place; words outside
+    // the read are predicated off and read as zero
+    auto extract = [&](const int4& mt) -> uint32_t {
+        const uint32_t jb = (uint32_t)(p8b - mt.x);  // byte offset of the read's word
+        const uint32_t addr = (uint32_t)mt.y + jb;
+        uint32_t hw, lw;
+#ifndef KDL_HOST_EMU
+        asm("{\n"
+            ".reg .pred p, q;\n"
+            "setp.lt.u32 p, %2, %3;\n"
+            "setp.lt.u32 q, %4, %3;\n"
+            "mov.u32 %0, 0;\n"
+            "mov.u32 %1, 0;\n"
+            "@p ld.shared.u32 %0, [%5];\n"
+            "@q ld.shared.u32 %1, [%5+4];\n"
+            "}\n"
+            : "=&r"(hw), "=&r"(lw)
+            : "r"(jb), "r"((uint32_t)mt.z), "r"(jb + 4u), "r"(addr));
+#else
+        hw = jb < (uint32_t)mt.z ? lds_u32(addr) : 0u;
+        lw = jb + 4u < (uint32_t)mt.z ? lds_u32(addr + 4u) : 0u;
+#endif
+        return __funnelshift_l(lw, hw, (uint32_t)mt.w);
+    };
+
+    for (long long item = 0;; ++item) {
+        const int s = (int)(item % W_STAGES);
+        const uint32_t parity = (uint32_t)((item / W_STAGES) & 1);
+        mbar_wait(&sm.full[s], parity);
+        mbar_wait(&sm.landed[s], parity);
+        Stage& st = sm.st[s];
+        const int flags = st.flags;
+        const int n_sub = st.n_sub;
+        if (flags & ITEM_END) break;
+        if (flags & ITEM_FIRST) {
+            tile_slot = st.tile_slot;
+            stored = false;
+            blocks_since_flush = 0;  // (already 0 after the previous tile's final flush)
+        }
+        if (n_sub > 0) {
+            {
+                const int4 ca = *reinterpret_cast<const int4*>(st.cov + wlo + 8 * (lane & 7));
+                const int4 cb = *reinterpret_cast<const int4*>(st.cov + wlo + 8 * (lane & 7) + 4);
+                covacc[0] += ca.x; covacc[1] += ca.y; covacc[2] += ca.z; covacc[3] += ca.w;
+                covacc[4] += cb.x; covacc[5] += cb.y; covacc[6] += cb.z; covacc[7] += cb.w;
+            }
+            // ---- simple reads: those with start in (wlo - maxlen, wlo + 64), two lower bounds over the sorted starts
+            int a, e;
+            lower_bound_warp2(st.gs, n_sub, wlo - maxlen + 1, wlo + F_WIN, lane, a, e);
+            for (int base = a & ~7; base < e; base += 32) {
+                // 8 reads per lane and block: quarter q takes the 8 CONSECUTIVE reads base + 8q .. + 7.  No bounds
+                // logic: a read that does not reach the lane's 8 slots (the up to 7 reads before a, reads [e, ...)
+                // right of the window, complex reads, the sentinels) fails both range tests and contributes zero.
+                uint32_t x[8];
+                int4 mt[8];
+                const int i0 = base + 8 * quarter;
+                const int4* mp = st.meta + i0 + (i0 >> 3);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mt[k] = mp[k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = extract(mt[k]);
+                add_block(x);
+            }
+            // ---- pieces of complex reads: unsorted, so the warp first collects the ones that overlap its window
+            if constexpr (kCx) {
+                const int n_px = st.n_px;
+                if (n_px > 0) {
+                    unsigned short* qu = sm.queue[warp];
+                    int qn = 0, qh = 0;  // pending entries, ring head
+                    const int p0 = wlo + 8 * (lane & 7);  // the lane's first slot
+                    auto run_block = [&](int n_valid) {
+                        uint32_t x[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int en = 8 * quarter + k;
+                            const int idx = en < n_valid ? (int)qu[(qh + en) & 63] : W_PCAP;
+                            const int4 pv = st.px[idx];
+                            const int s0 = (pv.w >> 8) & 0xFFF, s1 = (pv.w >> 20) & 0xFFF;
+                            int lead = s0 - p0, trail = p0 + 8 - s1;
+                            lead = lead < 0 ? 0 : (lead > 8 ? 8 : lead);
+                            trail = trail < 0 ? 0 : (trail > 8 ? 8 : trail);
+                            uint32_t mask = lead >= 8 ? 0u : (0xFFFFFFFFu >> (4 * lead));
+                            mask &= trail >= 8 ? 0u : (0xFFFFFFFFu << (4 * trail));
+                            int4 mt = pv;
+                            mt.w = pv.w & 31;
+                            x[k] = extract(mt) & mask;
+                        }
+                        add_block(x);
+                    };
+                    for (int base = 0; base < n_px; base += 32) {
+                        const int i = base + lane;
+                        const int w3 = i < n_px ? st.px[i].w : 0;
+                        const int s0 = (w3 >> 8) & 0xFFF, s1 = (w3 >> 20) & 0xFFF;
+                        const bool hit = s0 < wlo + F_WIN && s1 > wlo;
+                        const unsigned m = __ballot_sync(0xffffffffu, hit);
+                        if (hit) qu[(qh + qn + __popc(m & ((1u << lane) - 1u))) & 63] = (unsigned short)i;
+                        qn += __popc(m);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            run_block(32);
+                            qh = (qh + 32) & 63;
+                            qn -= 32;
+                            __syncwarp();
+                        }
+                    }
+                    if (qn > 0) {
+                        run_block(qn);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        // this warp is done reading the stage: hand it back before the (global-memory) flush
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+        if (flags & ITEM_LAST) {
+            if (blocks_since_flush & 1) acc.template ripple<3>(pend8);
+            if (kFresh && !stored) flush_window<F_STORE, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            else flush_window<kAdd, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            blocks_since_flush = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) covacc[k] = 0;
+        }
+    }
+}
+
+}  // namespace kdl

@@ -30,33 +30,44 @@ import numpy as np
 from . import _ffi, bamio
 
 
+select_reads = bamio.select_reads
+
+
 def shard_batch(batch: bamio.ReadBatch, rank: int, world: int) -> bamio.ReadBatch:
     """Rank's contiguous block of the reads of every contig (order and layout preserved)."""
     if world == 1:
         return batch
-    keep = np.zeros(batch.n_reads, dtype=bool)
-    read_off = [0]
+    parts = []
     for c in range(batch.n_contigs):
         lo, hi = int(batch.contig_read_off[c]), int(batch.contig_read_off[c + 1])
-        a = lo + (hi - lo) * rank // world
-        b = lo + (hi - lo) * (rank + 1) // world
-        keep[a:b] = True
-        read_off.append(read_off[-1] + (b - a))
-    idx = np.flatnonzero(keep)
-    n = idx.shape[0]
-    lseq = batch.l_seq[idx].astype(np.int64) & 0x7FFFFFFF
-    n_cig = np.diff(batch.cig_off.astype(np.int64))[idx]
-    # gather the ragged CIGAR and base ranges of the kept reads
-    cig_off = np.concatenate(([0], np.cumsum(n_cig)))
-    cig_src = np.repeat(batch.cig_off[:-1].astype(np.int64)[idx], n_cig) + (
-        np.arange(int(cig_off[-1])) - np.repeat(cig_off[:-1], n_cig))
-    words = (lseq + 7) // 8
-    # a simple read stores its op length in l_seq: its SEQ length is the same (flatten contract)
-    seq_off = np.concatenate(([0], np.cumsum(words)))
-    seq_src = np.repeat(batch.seq_off.astype(np.int64)[idx], words) + (
-        np.arange(int(seq_off[-1])) - np.repeat(seq_off[:-1], words))
-    return bamio.finalize(batch.contig_names, batch.contig_len, np.array(read_off), batch.ref_start[idx],
-                          seq_off[:-1], lseq, cig_off, batch.cigar[cig_src], batch.seq4[seq_src], n_records=n)
+        parts.append(np.arange(lo + (hi - lo) * rank // world, lo + (hi - lo) * (rank + 1) // world, dtype=np.int64))
+    return select_reads(batch, np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64))
+
+
+def partition_contigs(batch: bamio.ReadBatch, world: int):
+    """Contigs are independent units in the reference (kindel/kindel.py:143-151): give every rank a contiguous run
+    of whole contigs with about 1/world of the reads (64 contigs -> 8 per rank).  Returns
+    [(c_lo, c_hi)] per rank; a rank may get nothing when there are fewer contigs than ranks."""
+    reads = np.diff(batch.contig_read_off).astype(np.int64)
+    cum = np.concatenate(([0], np.cumsum(reads)))
+    total = int(cum[-1])
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        c = int(np.searchsorted(cum, target, side="left"))
+        if c > 0 and abs(cum[c - 1] - target) <= abs(cum[min(c, len(cum) - 1)] - target):
+            c -= 1
+        cuts.append(min(max(c, cuts[-1]), batch.n_contigs))
+    cuts.append(batch.n_contigs)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def shard_by_contig(batch: bamio.ReadBatch, rank: int, world: int) -> bamio.ReadBatch:
+    """Rank's whole contigs (partition_contigs), as a batch over the SAME slot layout: its table is non-zero only
+    on the slots of its own contigs, nobody else touches them, no count reduction is needed at all."""
+    c_lo, c_hi = partition_contigs(batch, world)[rank]
+    lo, hi = int(batch.contig_read_off[c_lo]), int(batch.contig_read_off[c_hi])
+    return select_reads(batch, np.arange(lo, hi, dtype=np.int64))
 
 
 def footprint(batch: bamio.ReadBatch, align: int = 4):
@@ -67,16 +78,20 @@ def footprint(batch: bamio.ReadBatch, align: int = 4):
         return 0, 0
     per_contig = np.diff(batch.contig_read_off)
     gstart = np.repeat(batch.contig_slot, per_contig) + batch.ref_start.astype(np.int64)
-    lseq = batch.l_seq.astype(np.int64) & 0x7FFFFFFF
+    lseq = batch.seq_len.astype(np.int64)
     oplen = (batch.cigar >> 4).astype(np.int64)
     csum = np.concatenate(([0], np.cumsum(oplen)))
     span = csum[batch.cig_off[1:].astype(np.int64)] - csum[batch.cig_off[:-1].astype(np.int64)]
     reach = np.maximum(lseq, span) + 2
     lo = int((gstart - reach).min())
     hi = int((gstart + reach).max()) + 1
-    # POS == 0 wraps to the END of the contig: such shards claim everything
-    if (batch.ref_start < 0).any():
-        return 0, int(batch.n_slots)
+    # Python negative indices wrap to the END of the contig (POS == 0, or clip_starts[r_pos - 1]
+    # of a non-first S at r_pos == 0): only KDL_HARD reads can do that, and their exact reach is not modelled
+    # here -- a shard holding any hard read that starts within `reach` of its contig's start claims everything
+    if batch.n_hard:
+        h = batch.hard_idx.astype(np.int64)
+        if (batch.ref_start[h].astype(np.int64) - reach[h] < 0).any():
+            return 0, int(batch.n_slots)
     lo = max(0, lo) // align * align
     hi = min(int(batch.n_slots), (hi + align - 1) // align * align)
     return lo, hi

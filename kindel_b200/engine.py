@@ -52,49 +52,33 @@ class DeviceBatch:
 def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     s = _ffi.KdlBatch()
     s.n_reads = host.n_reads
-    s.n_ops = int(host.cx_cigar.shape[0])
     s.seq4_words = int(host.seq4.shape[0])
     s.ref_start = ptr["ref_start"]
     s.seq_off = ptr["seq_off"]
     s.l_seq = ptr["l_seq"]
-    s.cig_off = ptr["cx_cig_off"]
-    s.cigar = ptr["cx_cigar"]
     s.seq4 = ptr["seq4"]
     s.n_contigs = host.n_contigs
     s.reads_sorted = 1 if host.reads_sorted else 0
     s.max_simple_len = int(host.max_simple_len)
+    s.reach_right = int(host.reach_right)
+    s.reach_left = int(host.reach_left)
     s.contig_read_off = ptr["contig_read_off"]
     s.contig_len = ptr["contig_len"]
     s.contig_slot = ptr["contig_slot"]
-    n_cx = int(host.complex_idx.shape[0])
-    s.n_complex = n_cx
-    s.complex_idx = ptr["complex_idx"] if n_cx else None
-    s.evt_off = ptr["evt_off"] if n_cx else None
+    s.n_complex = host.n_complex
+    s.n_hard = host.n_hard
+    s.hard_idx = ptr["hard_idx"] if host.n_hard else None
     s.tile_index = ptr.get("tile_index")
     return s
 
 
-_FIELDS = ("ref_start", "seq_off", "l_seq", "cx_cig_off", "cx_cigar", "seq4", "contig_read_off", "contig_len",
-           "contig_slot", "complex_idx", "evt_off")
+_FIELDS = ("ref_start", "seq_off", "l_seq", "seq4", "contig_read_off", "contig_len", "contig_slot", "hard_idx")
 
 
-def seq_is_dense(host: ReadBatch) -> bool:
-    """True if the packed bases are laid out back to back: seq_off[i] == sum of ceil(l_seq[j] / 8) over j < i.
-    Then kdl_ctx_consensus can derive seq_off on the device (batch->seq_off == NULL) instead of copying it."""
-    words = ((np.asarray(host.l_seq).astype(np.int64) & 0x7FFFFFFF) + 7) >> 3
-    off = np.asarray(host.seq_off).astype(np.int64)
-    return bool(off.size == 0 or (off[0] == 0 and np.array_equal(off[1:], np.cumsum(words[:-1]))))
-
-
-def host_struct(host: ReadBatch, derive_seq_off: bool = False):
-    """kdl_batch over HOST pointers (for the kdl_ctx_* entry points).  Returns (struct, keepalive).
-    derive_seq_off=True leaves seq_off NULL (the device derives it; requires seq_is_dense(host))."""
+def host_struct(host: ReadBatch):
+    """kdl_batch over HOST pointers (for the kdl_ctx_* entry points).  Returns (struct, keepalive)."""
     keep = {f: np.ascontiguousarray(getattr(host, f)) for f in _FIELDS}
     ptr = {f: (a.ctypes.data if a.size else None) for f, a in keep.items()}
-    if derive_seq_off:
-        if not seq_is_dense(host):
-            raise ValueError("derive_seq_off needs densely packed bases (seq_off == running sum of the reads' words)")
-        ptr["seq_off"] = None
     return make_struct(host, ptr), keep
 
 
@@ -175,7 +159,7 @@ def pileup(dbatch: DeviceBatch, counts: torch.Tensor = None, check: bool = True,
             rc = lib.kdl_pileup_range(C.byref(dbatch.struct), counts.data_ptr(), n_slots, lo, hi, flags,
                                       events.data_ptr(), flag.data_ptr(), _stream_ptr(dev))
             table.dirty = (lo, hi)
-            table.dirty_rest = len(dbatch.host.complex_idx) > 0
+            table.dirty_rest = dbatch.host.n_complex > 0
         else:
             if counts is None:
                 counts = torch.zeros((_ffi.KDL_NCOL, n_slots), dtype=torch.int32, device=dev)
@@ -248,11 +232,10 @@ class HostContext:
             pass
 
     def consensus(self, host: ReadBatch, min_depth=1, calls_out=None, counts_out=None, events_out=None,
-                  struct=None, derive_seq_off: bool = False):
-        """Runs H2D + K1 + K2 + D2H.  Returns calls (numpy uint8[n_slots]).
-        derive_seq_off: do not copy seq_off to the device, derive it there (dense layouts only)."""
+                  struct=None):
+        """Runs H2D + K1 + K2 + D2H.  Returns calls (numpy uint8[n_slots])."""
         if struct is None:
-            struct, keep = host_struct(host, derive_seq_off)
+            struct, keep = host_struct(host)
         if calls_out is None:
             calls_out = np.empty(host.n_slots, dtype=np.uint8)
         diag = _ffi.KdlDiag()

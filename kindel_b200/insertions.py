@@ -24,7 +24,7 @@ def decode_events(batch: ReadBatch, rows: np.ndarray) -> list:
         return []
     read = rows[:, 1].astype(np.int64)
     q0 = rows[:, 2].astype(np.int64)
-    lseq = (batch.l_seq[read].astype(np.int64)) & 0x7FFFFFFF
+    lseq = batch.seq_len[read].astype(np.int64)
     # simple reads store the op length in l_seq, but simple reads have no I ops, so lseq is SEQ's
     q1 = np.minimum(q0 + rows[:, 3].astype(np.int64), lseq)
     ln = np.maximum(q1 - q0, 0)

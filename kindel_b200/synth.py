@@ -75,11 +75,12 @@ def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_
 
 
 def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150, sub_rate: float = 0.01,
-                  edge_tail: bool = True) -> bamio.ReadBatch:
+                  edge_tail: bool = True, unsorted_tail: bool = False) -> bamio.ReadBatch:
     """Config-3 shape: per read p=0.5 leading soft clip (1-29), p=0.5 trailing soft clip (1-29),
     0-3 indel events (I or D, length 1-4) between M segments; query length is always `read_len`.
     With edge_tail a few hundred reads using N / = / X / H / P ops, H-then-S, clips overhanging
-    both contig ends and POS == 0 are appended (all legal for the reference, no exceptions)."""
+    both contig ends and POS == 0 are added (all legal for the reference, no exceptions); unsorted_tail leaves them
+    at the end of the batch (an unsorted file: the order-independent kernels take it)."""
     rng = np.random.default_rng(seed)
     L = int(contig_len)
     n = int(round(depth * L / read_len))
@@ -179,8 +180,34 @@ def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150,
     cig_off = np.concatenate([[0], np.cumsum(counts)])
     seq4 = np.concatenate(seq_rows).reshape(-1)
     seq_off = np.arange(n_all, dtype=np.int64) * words
-    return bamio.finalize(["ctg0"], np.array([L]), np.array([0, n_all]), ref_start, seq_off, l_seq, cig_off,
-                          np.concatenate(cig_parts), seq4, n_records=n_all)
+    batch = bamio.finalize(["ctg0"], np.array([L]), np.array([0, n_all]), ref_start, seq_off, l_seq, cig_off,
+                           np.concatenate(cig_parts), seq4, n_records=n_all)
+    if edge_tail and not unsorted_tail:  # the tail goes where a coordinate-sorted file would have it
+        batch = bamio.select_reads(batch, np.argsort(ref_start, kind="stable"))
+    return batch
+
+
+def on_contig(batch: bamio.ReadBatch, names, contig_lens, c: int) -> bamio.ReadBatch:
+    """A single-contig batch re-homed as contig `c` of a multi-contig layout (same length required)."""
+    assert batch.n_contigs == 1 and int(batch.contig_len[0]) == int(contig_lens[c])
+    read_off = np.zeros(len(names) + 1, dtype=np.int64)
+    read_off[c + 1:] = batch.n_reads
+    words = (batch.seq_len.astype(np.int64) + 7) // 8
+    bases = bamio._ragged_gather(batch.seq4, batch.seq_off, words)
+    return bamio.finalize(names, np.asarray(contig_lens), read_off, batch.ref_start, np.cumsum(words) - words,
+                          batch.seq_len, batch.cig_off, batch.cigar, bases, n_records=batch.n_reads)
+
+
+def mixed_reads(seed: int, contig_lens, depth: float, complex_frac: float, read_len: int = 150) -> bamio.ReadBatch:
+    """What a real short-read alignment looks like: coordinate-sorted `read_len`M reads with a fraction of clipped /
+    indel reads (the config-3 generator without its edge-case tail) mixed in at the same depth profile."""
+    contig_lens = [int(x) for x in contig_lens]
+    names = ["ctg%d" % i for i in range(len(contig_lens))]
+    parts = [simple_reads(seed, contig_lens, depth * (1.0 - complex_frac), read_len=read_len)]
+    for c, L in enumerate(contig_lens):
+        cx = complex_reads(seed * 131 + c, L, depth * complex_frac, read_len=read_len, edge_tail=False)
+        parts.append(on_contig(cx, names, contig_lens, c))
+    return bamio.merge_batches(parts)
 
 
 def to_records(batch: bamio.ReadBatch):
@@ -189,9 +216,8 @@ def to_records(batch: bamio.ReadBatch):
     recs = []
     for c in range(batch.n_contigs):
         for r in range(int(batch.contig_read_off[c]), int(batch.contig_read_off[c + 1])):
-            lraw = int(batch.l_seq[r])
             words = batch.cigar[int(batch.cig_off[r]):int(batch.cig_off[r + 1])].tolist()
-            lseq = lraw & 0x7FFFFFFF if lraw < 0 else sum(w >> 4 for w in words if (w & 15) in (0, 1, 4, 7, 8))
+            lseq = int(batch.seq_len[r])
             base = int(batch.seq_off[r])
             nib = bamio.unpack_nibbles(batch.seq4[base:base + (lseq + 7) // 8])[:lseq]
             recs.append((c, int(batch.ref_start[r]), 0, words, "".join(bamio.NIBBLES[x] for x in nib.tolist())))
@@ -206,7 +232,7 @@ def write_simple_bam(path, batch: bamio.ReadBatch, level: int = 1, threads: int 
 
     n = batch.n_reads
     lens = np.unique(batch.l_seq)
-    if len(batch.complex_idx) or lens.shape[0] != 1:
+    if batch.n_complex or lens.shape[0] != 1:
         raise ValueError("write_simple_bam needs simple reads of one length")
     L = int(lens[0])
     words = (L + 7) // 8

@@ -79,7 +79,8 @@ def _struct(batch, keep):
     b.seq4_words = int(batch.seq4.shape[0])
     b.ref_start = ptr(batch.ref_start, np.int32)
     b.seq_off = ptr(batch.seq_off, np.uint32)
-    b.l_seq = ptr(batch.l_seq, np.int32)
+    # plain SEQ lengths: the checker does not depend on the device word's flag bits
+    b.l_seq = ptr(batch.seq_len if getattr(batch, "seq_len", None) is not None else batch.l_seq, np.int32)
     b.cig_off = ptr(batch.cig_off, np.uint32)
     b.cigar = ptr(batch.cigar, np.uint32)
     b.seq4 = ptr(batch.seq4, np.uint32)

@@ -124,9 +124,8 @@ def records_of(batch, lo=0, hi=None):
     lut = np.frombuffer(_NIB.encode(), dtype=np.uint8)
     out = []
     for r in range(lo, hi):
-        lraw = int(batch.l_seq[r])
         words = batch.cigar[int(batch.cig_off[r]):int(batch.cig_off[r + 1])].tolist()
-        lseq = (lraw & 0x7FFFFFFF) if lraw < 0 else (words[0] >> 4)
+        lseq = int(batch.seq_len[r])
         base = int(batch.seq_off[r])
         w = batch.seq4[base:base + (lseq + 7) // 8].astype(np.uint32)
         nib = ((w[:, None] >> np.arange(28, -4, -4, dtype=np.uint32)[None, :]) & 15).reshape(-1)

@@ -1,4 +1,4 @@
-// emu_pileup.cpp -- TEST INFRASTRUCTURE: K0 + the tile-owner kernels (K1f, K1x) compiled for the host and run
+// emu_pileup.cpp -- TEST INFRASTRUCTURE: K0 + the tile-owner kernel K1 (and every other kernel) compiled for the host and run
 // under tests/emu/cuda_emu.h.  The kernel sources are included as they are (KDL_HOST_EMU only swaps the inline
 // PTX for functional stand-ins); nothing here is part of the product.
 #define KDL_HOST_EMU 1
@@ -7,13 +7,10 @@
 #include <vector>
 
 #include "../../kindel_b200/csrc/kdl_common.cuh"
-#include "../../kindel_b200/csrc/pileup_tiled.cu"
-#include "../../kindel_b200/csrc/pileup_wide.cu"
-#include "../../kindel_b200/csrc/pileup_ws.cu"
+#include "../../kindel_b200/csrc/pileup_tile.cu"
 #include "../../kindel_b200/csrc/pileup_general.cu"
 #include "../../kindel_b200/csrc/pileup_simple.cu"
 #include "../../kindel_b200/csrc/vote.cu"
-#include "../../kindel_b200/csrc/scan.cu"
 
 static char g_error[512];
 
@@ -27,36 +24,25 @@ void emu_set_schedule(int mode, unsigned long long seed) {
     emu::M().rng = seed * 0x9E3779B97F4A7C15ull + 1;
 }
 
-// variant 0 = K1f (pileup_tiled_kernel), 1 = K1x (pileup_wide_kernel), 2 = K1f with kLean,
-// 3 = K1w (pileup_ws_kernel, WsCfg1), 4 = K1w2 (WsCfg2).  All pointers are HOST pointers;
-// `counts` is int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.
+// K0 + K1 as kdl_pileup_range launches them.  mode: 0 = F_STORE (weight columns hold garbage), 1 = F_ADD,
+// 2 = F_ATOMIC (`split` CTAs share a tile; the table must be zero or hold counts to add to).  cx: the kCx
+// instantiation (piece lists for tile-eligible complex reads).  All pointers are HOST pointers; `counts` is
+// int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.
 // Returns 0, or 1 with emu_last_error() set.
 int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint32_t* tile_index, long long tile_lo,
-               long long n_tiles, int variant, int fresh, int grid) {
+               long long n_tiles, int mode, int cx, int split, int32_t* ins_events, int grid) {
     g_error[0] = 0;
     if (n_tiles <= 0) return 0;
     const kdl_batch b = *batch;
     const unsigned idx_grid = (unsigned)((n_tiles * 32 + 255) / 256);
     const char* err = emu::launch(idx_grid, 256, [&] { kdl::tile_index_kernel(b, tile_lo, n_tiles, tile_index); });
     if (!err) {
-        const unsigned threads = variant >= 3 ? (unsigned)kdl::W_THREADS : (unsigned)kdl::F_THREADS;
-        err = emu::launch((unsigned)grid, threads, [&] {
-            if (variant == 3) {
-                if (fresh) kdl::pileup_ws_kernel<true, kdl::WsCfg1>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-                else kdl::pileup_ws_kernel<false, kdl::WsCfg1>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-            } else if (variant == 4) {
-                if (fresh) kdl::pileup_ws_kernel<true, kdl::WsCfg2>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-                else kdl::pileup_ws_kernel<false, kdl::WsCfg2>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-            } else if (variant == 0) {
-                if (fresh) kdl::pileup_tiled_kernel<true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-                else kdl::pileup_tiled_kernel<false>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-            } else if (variant == 2) {
-                if (fresh) kdl::pileup_tiled_kernel<true, true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-                else kdl::pileup_tiled_kernel<false, true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-            } else {
-                if (fresh) kdl::pileup_wide_kernel<true>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-                else kdl::pileup_wide_kernel<false>(b, counts, n_slots, tile_index, tile_lo, n_tiles);
-            }
+        err = emu::launch((unsigned)grid, (unsigned)kdl::W_THREADS, [&] {
+#define KDL_EMU_TILE(M, X) kdl::pileup_tile_kernel<M, X>(b, counts, n_slots, tile_index, tile_lo, n_tiles, split, ins_events)
+            if (mode == 0) { if (cx) KDL_EMU_TILE(kdl::F_STORE, true); else KDL_EMU_TILE(kdl::F_STORE, false); }
+            else if (mode == 1) { if (cx) KDL_EMU_TILE(kdl::F_ADD, true); else KDL_EMU_TILE(kdl::F_ADD, false); }
+            else { if (cx) KDL_EMU_TILE(kdl::F_ATOMIC, true); else KDL_EMU_TILE(kdl::F_ATOMIC, false); }
+#undef KDL_EMU_TILE
         });
     }
     if (err) {
@@ -80,18 +66,23 @@ int emu_pileup_simple(const kdl_batch* batch, int32_t* counts, long long n_slots
     EMU_RUN(grid, 256, kdl::pileup_simple_atomic_kernel(b, counts, n_slots, err_flag));
     return 0;
 }
+// K1g: all = 0 walks the KDL_HARD reads (batch.hard_idx), all = 1 every complex read (the unsorted fallback)
 int emu_pileup_general(const kdl_batch* batch, int32_t* counts, long long n_slots, int32_t* ins_events,
-                       int32_t* err_flag, int grid) {
+                       int32_t* err_flag, int all, int grid) {
     g_error[0] = 0;
     const kdl_batch b = *batch;
-    if (b.n_complex > 0) EMU_RUN(grid, 256, kdl::pileup_general_kernel(b, counts, n_slots, ins_events, err_flag));
+    if (all) {
+        if (b.n_complex > 0) EMU_RUN(grid, 256, kdl::pileup_general_kernel(b, nullptr, b.n_reads, counts, n_slots, ins_events, err_flag));
+    } else if (b.n_hard > 0) {
+        EMU_RUN(grid, 256, kdl::pileup_general_kernel(b, b.hard_idx, b.n_hard, counts, n_slots, ins_events, err_flag));
+    }
     return 0;
 }
 int emu_diagnose(const kdl_batch* batch, kdl_diag* diag) {
     g_error[0] = 0;
     const kdl_batch b = *batch;
     EMU_RUN(1, 1, kdl::diagnose_init_kernel(diag));
-    if (b.n_complex > 0) EMU_RUN((b.n_complex + 255) / 256, 256, kdl::diagnose_kernel(b, diag));
+    if (b.n_hard > 0) EMU_RUN((b.n_hard + 255) / 256, 256, kdl::diagnose_kernel(b, diag));
     EMU_RUN(1, 1, kdl::diagnose_final_kernel(diag));
     return 0;
 }
@@ -160,18 +151,6 @@ int emu_exchange_epoch(const kdl_exchange* xs, int n_ranks, long long n_slots, l
             if (e_) { snprintf(g_error, sizeof g_error, "%s", e_); return 1; }
         }
     }
-    return 0;
-}
-
-// K-1: seq_off = exclusive prefix sum of ceil(l_seq / 8), the three launches of launch_seq_off_scan
-int emu_seq_off_scan(const int32_t* l_seq, long long n, uint32_t* seq_off) {
-    g_error[0] = 0;
-    if (n <= 0) return 0;
-    const long long blocks = (n + kdl::S_BLOCK - 1) / kdl::S_BLOCK;
-    std::vector<uint32_t> sums((size_t)blocks);
-    EMU_RUN(blocks, kdl::S_THREADS, kdl::seq_off_block_sums_kernel(l_seq, n, sums.data()));
-    EMU_RUN(1, kdl::S_THREADS, kdl::seq_off_scan_sums_kernel(sums.data(), (int)blocks));
-    EMU_RUN(blocks, kdl::S_THREADS, kdl::seq_off_write_kernel(l_seq, n, sums.data(), seq_off));
     return 0;
 }
 

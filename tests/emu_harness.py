@@ -1,6 +1,6 @@
 """Builds and drives the kernel emulator (tests/emu/): test infrastructure.
 
-`tests/emu/emu_pileup.cpp` compiles the SOURCE of K0 + the tile-owner kernels (K1f, K1x) for the host on top
+`tests/emu/emu_pileup.cpp` compiles the SOURCE of K0, the tile-owner kernel K1 and every other kernel for the host on top
 of `tests/emu/cuda_emu.h`, a functional model of the CUDA execution model (fibres per thread, warp
 collectives, shared memory, mbarrier / bulk copy / cp.async with late completion).  `run_pileup` runs one
 kernel over a batch held in numpy arrays and returns the count table."""
@@ -18,7 +18,7 @@ EMU_DIR = os.path.join(ROOT, "tests", "emu")
 OUT_DIR = os.path.join(EMU_DIR, "_build")
 LIB = os.path.join(OUT_DIR, "libkdl_emu.so")
 CUDA_INCLUDE = os.environ.get("CUDA_INCLUDE", "/usr/local/cuda/include")
-K1F, K1X, K1F_LEAN, K1W, K1W2 = 0, 1, 2, 3, 4
+F_STORE, F_ADD, F_ATOMIC = 0, 1, 2  # flush modes of the tile kernel (tile_common.cuh)
 
 _lib = None
 
@@ -30,8 +30,7 @@ def available() -> bool:
 def _sources():
     csrc = os.path.join(ROOT, "kindel_b200", "csrc")
     return [os.path.join(EMU_DIR, "cuda_emu.h"), os.path.join(EMU_DIR, "emu_pileup.cpp"),
-            os.path.join(csrc, "kdl_common.cuh"), os.path.join(csrc, "pileup_tiled.cu"),
-            os.path.join(csrc, "pileup_wide.cu"), os.path.join(csrc, "pileup_ws.cu"), os.path.join(csrc, "scan.cu"),
+            os.path.join(csrc, "kdl_common.cuh"), os.path.join(csrc, "tile_common.cuh"), os.path.join(csrc, "pileup_tile.cu"),
             os.path.join(csrc, "pileup_general.cu"), os.path.join(csrc, "pileup_simple.cu"), os.path.join(csrc, "vote.cu"),
             os.path.join(ROOT, "include", "kindel_b200.h")]
 
@@ -54,16 +53,15 @@ def load():
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_pileup.restype = C.c_int
     lib.emu_pileup.argtypes = [C.POINTER(_ffi.KdlBatch), C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
-                               C.c_longlong, C.c_int, C.c_int, C.c_int]
+                               C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     vp = C.c_void_p
     lib.emu_pileup_simple.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, C.c_int]
-    lib.emu_pileup_general.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, vp, C.c_int]
+    lib.emu_pileup_general.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, vp, C.c_int, C.c_int]
     lib.emu_diagnose.argtypes = [C.POINTER(_ffi.KdlBatch), C.POINTER(_ffi.KdlDiag)]
     lib.emu_vote.argtypes = [vp, C.c_longlong, C.c_longlong, vp]
     lib.emu_derive.argtypes = [vp, C.c_longlong, vp]
     lib.emu_vote_peers.argtypes = [C.POINTER(vp), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int,
                                    C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, vp, vp]
-    lib.emu_seq_off_scan.argtypes = [vp, C.c_longlong, vp]
     lib.emu_set_schedule.argtypes = [C.c_int, C.c_ulonglong]
     lib.emu_set_schedule.restype = None
     lib.emu_exchange_epoch.argtypes = [C.POINTER(_ffi.KdlExchange), C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_int]
@@ -76,12 +74,22 @@ def _check(rc):
         raise RuntimeError(_lib.emu_last_error().decode())
 
 
-def run_pileup(batch, variant: int, fresh: bool, grid: int = 5, tile_lo: int = 0, n_tiles: int = None,
-               counts: np.ndarray = None) -> np.ndarray:
-    """K0 + one tile-owner kernel over tiles [tile_lo, tile_lo + n_tiles) of `batch` (a bamio.ReadBatch).
+def tileable(batch) -> bool:
+    """kdl_pileup_range's test for the tile-owner path."""
+    from kindel_b200 import _ffi
 
-    fresh=True: the weight columns of `counts` hold garbage on entry (the kernel must overwrite them);
-    fresh=False: the kernel adds to what is there.  Returns int32 [19, n_slots]."""
+    return (batch.n_reads > batch.n_hard and int(batch.n_slots) % 512 == 0 and bool(batch.reads_sorted)
+            and 0 < int(batch.reach_right) <= _ffi.KDL_FAST_MAXLEN + _ffi.KDL_TILE_MAXREACH)
+
+
+def run_pileup(batch, mode: int = F_STORE, grid: int = 5, tile_lo: int = 0, n_tiles: int = None,
+               counts: np.ndarray = None, split: int = 1, cx: bool = None, want_events: bool = False):
+    """K0 + K1 over tiles [tile_lo, tile_lo + n_tiles) of `batch` (a bamio.ReadBatch): everything but the KDL_HARD
+    reads.
+
+    mode F_STORE: the weight columns of `counts` hold garbage on entry (the kernel must overwrite them);
+    F_ADD / F_ATOMIC: the kernel adds to what is there (F_ATOMIC with `split` CTAs per tile).  cx: which
+    instantiation (default: what kdl_pileup_range picks).  Returns int32 [19, n_slots] (and the event rows)."""
     from kindel_b200 import engine
 
     lib = load()
@@ -89,31 +97,34 @@ def run_pileup(batch, variant: int, fresh: bool, grid: int = 5, tile_lo: int = 0
     n_slots = int(batch.n_slots)
     if n_tiles is None:
         n_tiles = n_slots // 512 - tile_lo
+    if cx is None:
+        cx = batch.n_complex > batch.n_hard
     # the table sits between two canary zones: a kernel writing outside [19, n_slots] is caught
     guard = 4096
     arena = np.full(19 * n_slots + 2 * guard, 0x7A7A7A7A, dtype=np.int32)
     table = arena[guard:guard + 19 * n_slots].reshape(19, n_slots)
     if counts is None:
         table[:] = 0
-        if fresh:
-            table[0:5] = 0x5A5A5A5A
+        if mode == F_STORE:
+            table[0:5, tile_lo * 512:(tile_lo + n_tiles) * 512] = 0x5A5A5A5A
     else:
         table[:] = counts
     index = np.zeros(8 * (n_slots // 512), dtype=np.uint32)
-    rc = lib.emu_pileup(C.byref(st), table.ctypes.data, n_slots, index.ctypes.data, tile_lo, n_tiles, variant,
-                        1 if fresh else 0, grid)
+    events = np.full((max(int(batch.n_events), 1), 4), -1, dtype=np.int32)
+    rc = lib.emu_pileup(C.byref(st), table.ctypes.data, n_slots, index.ctypes.data, tile_lo, n_tiles, mode,
+                        1 if cx else 0, split, events.ctypes.data, grid)
     del keep
     if rc:
         raise RuntimeError(lib.emu_last_error().decode())
     assert (arena[:guard] == 0x7A7A7A7A).all() and (arena[-guard:] == 0x7A7A7A7A).all(), "write outside the count table"
-    return table.copy()
+    return (table.copy(), events[: int(batch.n_events)]) if want_events else table.copy()
 
 
-def pileup_pipeline(batch, variant: int = K1F, grid: int = 3):
-    """What kdl_pileup does, kernel by kernel, under the emulator: K0 + tile-owner kernel (sorted, tileable
-    batches) or K1s (anything else) for the simple reads, K1g for the complex ones; on a raised error flag,
-    the diagnose kernels.  Returns (counts [19, n_slots], events [n_events, 4]) or raises IndexError /
-    KeyError(base) exactly like kindel_b200.engine.pileup."""
+def pileup_pipeline(batch, grid: int = 3, split: int = 1):
+    """What kdl_pileup does, kernel by kernel, under the emulator: K0 + K1 (sorted, tileable batches) plus K1g for
+    the hard reads, or K1s + K1g over every complex read (anything else); on a raised error flag, the diagnose
+    kernels.  Returns (counts [19, n_slots], events [n_events, 4]) or raises IndexError / KeyError(base)
+    exactly like kindel_b200.engine.pileup."""
     from kindel_b200 import _ffi, engine
 
     lib = load()
@@ -122,17 +133,19 @@ def pileup_pipeline(batch, variant: int = K1F, grid: int = 3):
     counts = np.zeros((19, n_slots), dtype=np.int32)
     events = np.zeros((max(int(batch.n_events), 1), 4), dtype=np.int32)
     flag = np.zeros(4, dtype=np.int32)
-    n_cx = len(batch.complex_idx)
-    has_simple = batch.n_reads > n_cx
-    tiled = (has_simple and n_slots % 512 == 0 and bool(batch.reads_sorted) and 0 < int(batch.max_simple_len) <= _ffi.KDL_FAST_MAXLEN)
     if batch.n_reads:
-        if tiled:
+        if tileable(batch):
             index = np.zeros(8 * (n_slots // 512), dtype=np.uint32)
+            cx = batch.n_complex > batch.n_hard
             _check(lib.emu_pileup(C.byref(st), counts.ctypes.data, n_slots, index.ctypes.data, 0, n_slots // 512,
-                                  variant, 0, grid))
-        elif has_simple:
-            _check(lib.emu_pileup_simple(C.byref(st), counts.ctypes.data, n_slots, flag.ctypes.data, grid))
-        _check(lib.emu_pileup_general(C.byref(st), counts.ctypes.data, n_slots, events.ctypes.data, flag.ctypes.data, grid))
+                                  F_ATOMIC if split > 1 else F_ADD, 1 if cx else 0, split, events.ctypes.data, grid))
+            _check(lib.emu_pileup_general(C.byref(st), counts.ctypes.data, n_slots, events.ctypes.data,
+                                          flag.ctypes.data, 0, grid))
+        else:
+            if batch.n_reads > batch.n_complex:
+                _check(lib.emu_pileup_simple(C.byref(st), counts.ctypes.data, n_slots, flag.ctypes.data, grid))
+            _check(lib.emu_pileup_general(C.byref(st), counts.ctypes.data, n_slots, events.ctypes.data,
+                                          flag.ctypes.data, 1, grid))
     if flag[0]:
         diag = _ffi.KdlDiag()
         _check(lib.emu_diagnose(C.byref(st), C.byref(diag)))
@@ -201,15 +214,6 @@ def exchange_epoch(tables, feet, slices, calls, flags, epoch, min_depth=1, grid=
             x.slice_lo[p], x.slice_hi[p] = slices[p]
         x.counter = flags["counter"][r].ctypes.data
     _check(lib.emu_exchange_epoch(xs, n, n_slots, int(math.ceil(min_depth)), epoch, grid))
-
-
-def seq_off_scan(l_seq: np.ndarray) -> np.ndarray:
-    """K-1 (scan.cu): word offsets of densely packed reads from their lengths."""
-    lib = load()
-    l_seq = np.ascontiguousarray(l_seq, dtype=np.int32)
-    out = np.full(l_seq.shape[0], 0xDEADBEEF, dtype=np.uint32)
-    _check(lib.emu_seq_off_scan(l_seq.ctypes.data, l_seq.shape[0], out.ctypes.data))
-    return out
 
 
 def set_schedule(mode: str = "forward", seed: int = 1):

@@ -34,7 +34,7 @@ def reference_alignment_to_table(aln):
 
 def event_string(batch, read, q_off, length):
     """Upper-case inserted string of one event, straight from the packed bases."""
-    lseq = int(batch.l_seq[read]) & 0x7FFFFFFF
+    lseq = int(batch.seq_len[read])
     base = int(batch.seq_off[read])
     out = []
     for q in range(q_off, min(q_off + length, lseq)):

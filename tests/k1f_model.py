@@ -148,90 +148,3 @@ def pileup_model(batch):
 
 
 # ---- wide lanes: 16 slots per lane, groups of 4 lanes, 8 read streams per warp ------------------------------
-def pileup_model_wide(batch):
-    """The same pileup with the round-2 lane layout: a lane owns 16 consecutive slots
-    (two words X0, X1 from THREE words of the read and two funnel shifts), a group of 4 lanes owns the
-    64-slot window, the 8 groups of a warp walk 8 different reads; 8 streams are summed bit-sliced in
-    three butterfly stages."""
-    n_slots = int(batch.n_slots)
-    out = np.zeros((5, n_slots), dtype=np.int64)
-    per_contig = np.diff(batch.contig_read_off)
-    gstart = (np.repeat(batch.contig_slot, per_contig) + batch.ref_start.astype(np.int64))
-    lens = batch.l_seq.astype(np.int64)
-    maxlen = int(batch.max_simple_len)
-
-    def add_planes(a, b):
-        o, carry = [], 0
-        for k in range(max(len(a), len(b))):
-            carry, s = csa(a[k] if k < len(a) else 0, b[k] if k < len(b) else 0, carry)
-            o.append(s)
-        o.append(carry)
-        return o
-
-    for tile in range(n_slots // TILE):
-        t0 = tile * TILE
-        lo = int(np.searchsorted(gstart, t0 - maxlen + 1, side="left"))
-        hi = int(np.searchsorted(gstart, t0 + TILE, side="left"))
-        if lo >= hi:
-            continue
-        gs = gstart[lo:hi] - t0
-        ln = lens[lo:hi]
-        diff = np.zeros(TILE + 1, dtype=np.int64)
-        cs, ce = np.clip(gs, 0, TILE), np.clip(gs + ln, 0, TILE)
-        np.add.at(diff, cs[cs < ce], 1)
-        np.add.at(diff, ce[cs < ce], -1)
-        cov = np.cumsum(diff)[:TILE]
-        for warp in range(TILE // WIN):
-            wlo = warp * WIN
-            a = int(np.searchsorted(gs, wlo - maxlen + 1, side="left"))
-            e = int(np.searchsorted(gs, wlo + WIN, side="left"))
-            if a >= e:
-                continue
-            for lane4 in range(4):                       # lane of a group: slots wlo + 16 lane4 .. + 15
-                p8b = (wlo >> 1) + 8 * lane4             # byte offset of the lane's first word (2 words per lane)
-                streams = [[Planes(), Planes()] for _ in range(8)]
-                base = a & ~7
-                while base < e:
-                    for g8 in range(8):                  # group g8: reads base + 8 g8 .. + 7
-                        x0, x1 = [], []
-                        for u in range(8):
-                            i = base + 8 * g8 + u
-                            if i >= hi - lo:
-                                x0.append(0)
-                                x1.append(0)
-                                continue
-                            g = int(gs[i])
-                            nb = ((int(ln[i]) + 7) >> 3) << 2
-                            words = batch.seq4[int(batch.seq_off[lo + i]):int(batch.seq_off[lo + i]) + nb // 4]
-                            jb = (p8b - (((g + 7) >> 3) << 2)) & M32
-
-                            def w(off):
-                                j = (jb + off) & M32
-                                return int(words[j >> 2]) if j < nb else 0
-
-                            sh = ((-g) & 7) << 2
-                            w0, w1, w2 = w(0), w(4), w(8)
-                            x0.append(funnelshift_l(w1, w0, sh))
-                            x1.append(funnelshift_l(w2, w1, sh))
-                        streams[g8][0].add8(x0)
-                        streams[g8][1].add8(x1)
-                    base += 64
-                for word in range(2):
-                    tot = streams[0][word].p
-                    # three butterfly stages == a reduction tree over the 8 streams
-                    s = [st[word].p for st in streams]
-                    s = [add_planes(s[0], s[1]), add_planes(s[2], s[3]), add_planes(s[4], s[5]), add_planes(s[6], s[7])]
-                    s = [add_planes(s[0], s[1]), add_planes(s[2], s[3])]
-                    tot = add_planes(s[0], s[1])
-                    assert len(tot) == F_P + 3
-                    cols = [extract8(tot, bit) for bit in range(4)]
-                    for b in range(8):
-                        slot = wlo + 16 * lane4 + 8 * word + b
-                        raw = [cols[bit][b] for bit in range(4)]
-                        n3 = sum(raw) - int(cov[slot])
-                        assert n3 % 3 == 0 and n3 >= 0
-                        n = n3 // 3
-                        for bit in range(4):
-                            out[bit, t0 + slot] += raw[bit] - n
-                        out[4, t0 + slot] += n
-    return out

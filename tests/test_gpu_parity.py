@@ -192,7 +192,7 @@ def test_unsorted_input_is_legal():
     perm = np.concatenate(parts)
     n = b.n_reads
     shuffled = bamio.finalize(b.contig_names, b.contig_len, b.contig_read_off, b.ref_start[perm], b.seq_off[perm],
-                              b.l_seq[perm], np.arange(n + 1), b.cigar[perm], b.seq4)
+                              b.seq_len[perm], np.arange(n + 1), b.cigar[perm], b.seq4)
     assert not shuffled.reads_sorted
     _, c0, _ = engine_tables(b)
     _, c1, _ = engine_tables(shuffled)
@@ -219,7 +219,7 @@ def test_host_buffer_entry_point():
     bad = synth.simple_reads(23, [5000], 20)
     bad.seq4[7] = (int(bad.seq4[7]) & 0x0FFFFFFF) | 0x30000000  # nibble 3 = 'M' (IUPAC): KeyError('M')
     bad = bamio.finalize(bad.contig_names, bad.contig_len, bad.contig_read_off, bad.ref_start, bad.seq_off,
-                         bad.l_seq & 0x7FFFFFFF, bad.cig_off, bad.cigar, bad.seq4)  # re-classify: that read is now complex
+                         bad.seq_len, bad.cig_off, bad.cigar, bad.seq4)  # re-classify: that read is now hard
     with pytest.raises(KeyError) as exc:
         ctx.consensus(bad, 1)
     assert exc.value.args == ("M",)
@@ -383,17 +383,42 @@ def test_very_long_complex_read_among_short_reads(tmp_path):
     assert aln.insertions[long_pos + 100_000] == {long_seq[100_000:100_010]: 1}
 
 
-def test_warp_specialised_variant_matches(monkeypatch):
-    """K1w (KDL_K1F=ws): the producer/consumer pipeline variant of the tile-owner kernel gives the same
-    tables as the oracle on sorted simple, mixed, deep, sparse and multi-contig inputs."""
-    from kindel_b200 import synth
+def test_tile_kernel_shapes():
+    """K1 on the shapes that stress its paths: deep piles (several items per tile, mid-window flushes), long reads
+    (staging capacity cuts items), sparse and multi-contig tiles, complex-heavy reads at several depths (piece
+    lists, item cuts by piece capacity, sparse REDs, insertion events), mixed simple / complex."""
+    from kindel_b200 import bamio, synth
 
-    monkeypatch.setenv("KDL_K1F", "ws")
     _against_oracle(synth.simple_reads(71, [300_000], 150))
-    _against_oracle(synth.complex_reads(72, 30_000, 400))
     _against_oracle(synth.simple_reads(73, [4000], 6000))
     _against_oracle(synth.simple_reads(74, [500_000], 0.5))
     _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
+    _against_oracle(synth.simple_reads(76, [60_000], 40, read_len=1203))
+    _against_oracle(synth.simple_reads(83, [9000], 600, read_len=6000))
+    _against_oracle(synth.complex_reads(72, 30_000, 400))
+    _against_oracle(synth.complex_reads(77, 3000, 4000, edge_tail=False))
+    _against_oracle(synth.complex_reads(78, 200_000, 60, read_len=900))
+    _against_oracle(mixed_reads(79, 400_000, 150, 0.05))
+
+
+def mixed_reads(seed, L, depth, complex_frac):
+    """A coordinate-sorted batch of simple reads with a fraction of clip / indel reads mixed in (what a real
+    short-read BAM looks like; SURVEY.md 8d config 4: "mostly 150M with ~1 % indel/clip reads")."""
+    from kindel_b200 import synth
+
+    return synth.mixed_reads(seed, [L], depth, complex_frac)
+
+
+@pytest.mark.parametrize("split", [2, 7])
+def test_depth_split_of_small_references(monkeypatch, split):
+    """Fewer tiles than CTA slots: `split` CTAs share a tile by read range and flush with REDs (kdl_pileup_range
+    picks the split from the batch; KDL_SPLIT forces it)."""
+    from kindel_b200 import synth
+
+    monkeypatch.setenv("KDL_SPLIT", str(split))
+    _against_oracle(synth.simple_reads(1, [30000], 500))
+    _against_oracle(synth.complex_reads(3, 30000, 300))
+    _against_oracle(synth.simple_reads(75, [151, 200, 9000, 333], 300))
 
 
 def test_big_bam_file_end_to_end(tmp_path):
@@ -466,7 +491,7 @@ def test_exchange_protocol_emulated_on_one_gpu():
             for r in range(world):
                 tab = engine.CountTable(S, dev, tensor=tables[r])
                 if epoch == 2:
-                    tab.dirty, tab.dirty_rest = feet[r], len(shards[r].complex_idx) > 0
+                    tab.dirty, tab.dirty_rest = feet[r], shards[r].n_complex > 0
                     tab.dirty = engine._tile_align(*feet[r], S)
                 engine.pileup(engine.upload(shards[r], dev), check=False, table=tab, slot_range=feet[r])
             for r in range(world):
@@ -511,73 +536,6 @@ def test_megabase_fixture_digest(manifest):
             nz = np.flatnonzero(aln.table[6])
             assert {int(i): list(aln.insertions[int(i)].items()) for i in nz} == want_ins
             _digest_check(aln.table, res.consensuses[c].sequence, res.refs_changes[ctg], meta)
-
-
-@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="K1x (wide lanes) has not been validated on a "
-                    "GPU yet: opt in with KDL_TEST_EXPERIMENTAL=1")
-def test_wide_lane_variant_matches(monkeypatch):
-    """K1x (KDL_K1F=wide): 16-slot lanes, 8 read streams per warp."""
-    from kindel_b200 import synth
-
-    monkeypatch.setenv("KDL_K1F", "wide")
-    _against_oracle(synth.simple_reads(71, [300_000], 150))
-    _against_oracle(synth.complex_reads(72, 30_000, 400))
-    _against_oracle(synth.simple_reads(73, [4000], 6000))
-    _against_oracle(synth.simple_reads(74, [500_000], 0.5))
-    _against_oracle(synth.simple_reads(75, [151, 200, 90_000, 333], 40))
-    _against_oracle(synth.simple_reads(76, [60_000], 40, read_len=1203))
-
-
-@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="K1f<kLean> has not been validated on a GPU "
-                    "yet: opt in with KDL_TEST_EXPERIMENTAL=1")
-def test_lean_variant_matches(monkeypatch):
-    """K1f with kLean (KDL_K1F=lean): next tile's index a tile ahead in registers, 128-bit prefix loads."""
-    from kindel_b200 import synth
-
-    monkeypatch.setenv("KDL_K1F", "lean")
-    _against_oracle(synth.simple_reads(81, [300_000], 150))
-    _against_oracle(synth.complex_reads(82, 30_000, 400))
-    _against_oracle(synth.simple_reads(83, [9000], 600, read_len=6000))
-    _against_oracle(synth.simple_reads(84, [500_000], 0.5))
-    _against_oracle(synth.simple_reads(85, [151, 200, 90_000, 333], 40))
-
-
-@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="K1w2 has not been validated on a GPU yet: "
-                    "opt in with KDL_TEST_EXPERIMENTAL=1")
-def test_ws2_variant_matches(monkeypatch):
-    """K1w2 (KDL_K1F=ws2): the warp-specialised pipeline as two CTAs per SM with setmaxnreg and half-size stages."""
-    from kindel_b200 import synth
-
-    monkeypatch.setenv("KDL_K1F", "ws2")
-    _against_oracle(synth.simple_reads(91, [300_000], 150))
-    _against_oracle(synth.complex_reads(92, 30_000, 400))
-    _against_oracle(synth.simple_reads(93, [9000], 600, read_len=6000))
-    _against_oracle(synth.simple_reads(94, [500_000], 0.5))
-    _against_oracle(synth.simple_reads(95, [151, 200, 90_000, 333], 40))
-    _against_oracle(synth.simple_reads(96, [2000], 3000))
-
-
-@pytest.mark.skipif(not os.environ.get("KDL_TEST_EXPERIMENTAL"), reason="the device-side seq_off scan has not been "
-                    "validated on a GPU yet: opt in with KDL_TEST_EXPERIMENTAL=1")
-def test_host_buffer_entry_point_derives_seq_off():
-    """kdl_ctx_consensus with batch->seq_off == NULL: offsets derived on the device (scan.cu)."""
-    from kindel_b200 import engine, synth
-    from oracle import coracle
-
-    ctx = engine.HostContext(0)
-    from kindel_b200 import distributed as D
-
-    for b in (D.shard_batch(synth.complex_reads(31, 20000, 200), 1, 2), synth.simple_reads(32, [300_000], 100),
-              synth.simple_reads(33, [40_000], 30, read_len=1203)):
-        assert engine.seq_is_dense(b)
-        counts = np.empty((19, b.n_slots), dtype=np.int32)
-        events = np.empty((max(b.n_events, 1), 4), dtype=np.int32)
-        calls = ctx.consensus(b, 2, counts_out=counts, events_out=events, derive_seq_off=True)
-        oc, oe = coracle.pileup(b)
-        np.testing.assert_array_equal(counts, oc)
-        np.testing.assert_array_equal(events[: b.n_events], oe)
-        np.testing.assert_array_equal(calls, coracle.vote(oc, 2))
-    ctx.close()
 
 
 def test_clip_heavy_cases_through_the_engine(clip_golden, tmp_path):

@@ -195,7 +195,7 @@ def test_bam_writer_reader_roundtrip(tmp_path):
     bamio.write_bam(path, contigs, recs)
     back = bamio.read_alignment(path)
     assert back.n_records == len(recs) and back.n_reads == batch.n_reads
-    for f in ("ref_start", "cig_off", "cigar", "contig_len", "contig_read_off", "contig_slot", "complex_idx", "evt_off"):
+    for f in ("ref_start", "cig_off", "cigar", "contig_len", "contig_read_off", "contig_slot", "complex_idx", "hard_idx", "l_seq", "seq_len", "seq_off", "seq4"):
         np.testing.assert_array_equal(getattr(back, f), getattr(batch, f), err_msg=f)
     c0, e0 = coracle.pileup(batch)
     c1, e1 = coracle.pileup(back)

@@ -46,14 +46,3 @@ def test_model_equals_oracle_on_sorted_simple_reads():
         got = pileup_model(b)
         np.testing.assert_array_equal(got, want[:5])
         assert int(got[4].sum()) > 0  # N really occurs and is recovered from coverage
-
-
-def test_wide_lane_model_equals_oracle():
-    """The round-2 lane layout (16 slots per lane, 4-lane groups, 8 read streams; kernel K1x in
-    kindel_b200/csrc/pileup_wide.cu) modelled in numpy: same tables as the oracle."""
-    from k1f_model import pileup_model_wide
-
-    for b in (synth.simple_reads(111, [3000], 60), synth.simple_reads(112, [700, 1500, 151], 25, sub_rate=0.2),
-              synth.simple_reads(113, [2000], 30, read_len=37, sub_rate=0.3), synth.simple_reads(114, [2500], 12, read_len=301)):
-        want, _ = coracle.pileup(b)
-        np.testing.assert_array_equal(pileup_model_wide(b), want[:5])

@@ -1,9 +1,10 @@
-"""K0 + the tile-owner kernels (K1f, K1w and the experimental K1f-lean, K1x, K1w2), SOURCE-level, on the CPU.
+"""K0 + the tile-owner kernel K1 (and every other kernel), SOURCE-level, on the CPU.
 
-tests/emu/ compiles kindel_b200/csrc/pileup_tiled.cu and pileup_wide.cu for the host and runs them under a
-functional model of the CUDA execution model (tests/emu/cuda_emu.h); the tables must equal the C oracle's.
-This checks what a numpy model of the arithmetic (tests/k1f_model.py) cannot: the kernels' own indexing,
-sentinels, sub-chunk splitting, flush conditions, coverage scan, fresh/accumulate modes and staging protocol.
+tests/emu/ compiles kindel_b200/csrc/*.cu for the host and runs the kernels under a functional model of the CUDA
+execution model (tests/emu/cuda_emu.h); the tables must equal the C oracle's.  This checks what a numpy model of
+the arithmetic (tests/k1f_model.py) cannot: the kernel's own indexing, sentinels, item splitting, flush conditions,
+coverage scan, store / add / atomic modes, the depth split, the explosion of complex reads into pieces and sparse
+updates, and the staging protocol (full / landed / empty mbarriers, producer barrier, cp.async prefetch).
 It does not model timing or the memory model; the `-m gpu` parity tests remain the proof on the device."""
 import numpy as np
 import pytest
@@ -26,32 +27,70 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN, E.K1W, E.K1W2], ids=["K1f", "K1x", "K1f-lean", "K1w", "K1w2"])
+@pytest.mark.parametrize("cx", [False, True], ids=["lean", "cx"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_tile_owner_kernel_source_equals_oracle(name, variant):
+def test_tile_owner_kernel_source_equals_oracle(name, cx):
+    """Simple reads through both instantiations of K1 (the kCx one has smaller stages and the piece machinery)."""
     batch = CASES[name]()
     want, _ = coracle.pileup(batch)
-    for fresh in (False, True):
-        got = E.run_pileup(batch, variant, fresh)
-        np.testing.assert_array_equal(got[:5], want[:5], err_msg="%s fresh=%s" % (name, fresh))
+    for mode in (E.F_ADD, E.F_STORE):
+        got = E.run_pileup(batch, mode, cx=cx)
+        np.testing.assert_array_equal(got[:5], want[:5], err_msg="%s mode=%s" % (name, mode))
         assert not got[5:].any()
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1X, E.K1F_LEAN, E.K1W, E.K1W2], ids=["K1f", "K1x", "K1f-lean", "K1w", "K1w2"])
-def test_accumulate_and_slot_ranges(variant):
+@pytest.mark.parametrize("split", [2, 5])
+@pytest.mark.parametrize("name", ["deep", "cfg4_like", "multi_contig", "sparse"])
+def test_depth_split_units_share_a_tile(name, split):
+    """`split` CTAs per tile, each a contiguous part of the tile's reads, flushing with REDs into a zeroed table."""
+    batch = CASES[name]()
+    want, _ = coracle.pileup(batch)
+    got = E.run_pileup(batch, E.F_ATOMIC, split=split, grid=7)
+    np.testing.assert_array_equal(got[:5], want[:5])
+    assert not got[5:].any()
+
+
+CX_CASES = {
+    "cfg3_like":    lambda: synth.complex_reads(72, 6000, 60),                  # clips + indels + edge tail (hard reads)
+    "cfg3_deep":    lambda: synth.complex_reads(91, 1500, 900, edge_tail=False),  # piece list overflows: items are cut
+    "long_complex": lambda: synth.complex_reads(92, 9000, 30, read_len=900, edge_tail=False),
+}
+
+
+@pytest.mark.parametrize("split", [1, 3])
+@pytest.mark.parametrize("name", list(CX_CASES))
+def test_complex_reads_in_the_tile_kernel(name, split):
+    """Tile-eligible complex reads: M segments as masked pieces through the bit-sliced counters, I / D / clip
+    updates and insertion events from the producers; hard reads (K1g) on top."""
+    batch = CX_CASES[name]()
+    assert batch.n_complex > batch.n_hard
+    want_c, want_e = coracle.pileup(batch)
+    got_c, got_e = E.pileup_pipeline(batch, split=split)
+    np.testing.assert_array_equal(got_c, want_c)
+    np.testing.assert_array_equal(got_e, want_e)
+    if split == 1:  # stale weight columns are overwritten, K1 alone = everything but the hard reads
+        got2, ev2 = E.run_pileup(batch, E.F_STORE, want_events=True)
+        hard = __import__("kindel_b200.distributed", fromlist=["x"]).select_reads(batch, batch.hard_idx)
+        wh, _ = coracle.pileup(hard)
+        np.testing.assert_array_equal(got2, want_c - wh)
+
+
+@pytest.mark.parametrize("mode", [E.F_ADD, E.F_STORE], ids=["add", "store"])
+def test_accumulate_and_slot_ranges(mode):
     """Two batches added into one table (accumulate mode), then a fresh pass over a tile sub-range only."""
     a = synth.simple_reads(81, [20_000], 30)
     b = synth.simple_reads(81, [20_000], 50, read_seed=9)
     wa, _ = coracle.pileup(a)
     wb, _ = coracle.pileup(b)
-    t = E.run_pileup(a, variant, False)
-    t = E.run_pileup(b, variant, False, counts=t)
+    t = E.run_pileup(a, E.F_ADD)
+    t = E.run_pileup(b, E.F_ADD, counts=t)
     np.testing.assert_array_equal(t[:5], (wa + wb)[:5])
-    # fresh overwrite of tiles [7, 19) with batch a: inside the range a's counts, outside untouched
+    # overwrite (F_STORE) / add (F_ADD) on tiles [7, 19) with batch a: outside the range untouched
     lo, n = 7, 12
-    t2 = E.run_pileup(a, variant, True, tile_lo=lo, n_tiles=n, counts=t.copy())
+    t2 = E.run_pileup(a, mode, tile_lo=lo, n_tiles=n, counts=t.copy())
     s0, s1 = lo * 512, (lo + n) * 512
-    np.testing.assert_array_equal(t2[:5, s0:s1], wa[:5, s0:s1])
+    inside = wa[:5, s0:s1] if mode == E.F_STORE else (t + wa)[:5, s0:s1]
+    np.testing.assert_array_equal(t2[:5, s0:s1], inside)
     np.testing.assert_array_equal(t2[:5, :s0], t[:5, :s0])
     np.testing.assert_array_equal(t2[:5, s1:], t[:5, s1:])
 
@@ -108,18 +147,30 @@ def test_whole_pipeline_on_the_fuzz_cases(tmp_path):
     assert raised > 20 and done > 20
 
 
-@pytest.mark.parametrize("variant", [E.K1F, E.K1F_LEAN, E.K1W2], ids=["K1f", "K1f-lean", "K1w2"])
-def test_mixed_batch_pipeline(variant):
-    """Config-3 shape (clips, indels, edge-case tail; most reads complex, some simple): the tile-owner kernel takes
-    the simple reads, K1g the rest, into one table."""
+def test_mixed_batch_pipeline():
+    """Config-3 shape (clips, indels, edge-case tail; most reads complex, some simple) end to end: K1 + K1g into one
+    table, then the vote and the derived columns."""
     batch = synth.complex_reads(72, 6000, 60)
     want_c, want_e = coracle.pileup(batch)
-    got_c, got_e = E.pileup_pipeline(batch, variant)
+    got_c, got_e = E.pileup_pipeline(batch)
     np.testing.assert_array_equal(got_c, want_c)
     np.testing.assert_array_equal(got_e, want_e)
     np.testing.assert_array_equal(E.vote(got_c, 1), coracle.vote(want_c, 1))
     np.testing.assert_array_equal(E.vote(got_c, 7), coracle.vote(want_c, 7))
     np.testing.assert_array_equal(E.derive(got_c), coracle.derive(want_c))
+
+
+def test_unsorted_batches_take_the_atomic_kernels():
+    batch = synth.complex_reads(72, 6000, 20)
+    from kindel_b200 import distributed as D
+
+    perm = np.random.default_rng(3).permutation(batch.n_reads)
+    shuffled = D.select_reads(batch, perm)
+    assert not shuffled.reads_sorted and not E.tileable(shuffled)
+    want_c, want_e = coracle.pileup(shuffled)
+    got_c, got_e = E.pileup_pipeline(shuffled)
+    np.testing.assert_array_equal(got_c, want_c)
+    np.testing.assert_array_equal(got_e, want_e)
 
 
 def test_peer_vote_over_footprints():
@@ -166,46 +217,21 @@ def test_fused_exchange_epochs(world):
             assert (flags["ready"][r][:world] == epoch).all() and (flags["done"][r][:world] == epoch).all()
 
 
-@pytest.mark.parametrize("n", [1, 3, 4, 1023, 1024, 1025, 5000, 262_145, 300_001])
-def test_seq_off_scan(n):
-    """K-1: exclusive prefix sum of ceil(l_seq / 8) with the complex flag (bit 31) ignored."""
-    rng = np.random.default_rng(n)
-    l = rng.integers(0, 400, size=n).astype(np.int64)
-    flagged = np.where(rng.random(n) < 0.3, l | 0x80000000, l).astype(np.uint32).view(np.int32)
-    words = (l + 7) >> 3
-    want = np.concatenate(([0], np.cumsum(words)[:-1])).astype(np.uint32)
-    np.testing.assert_array_equal(E.seq_off_scan(flagged), want)
-
-
-def test_dense_layout_predicate():
-    from kindel_b200 import engine
-
-    from kindel_b200 import distributed as D
-
-    strided = synth.complex_reads(5, 3000, 30)      # fixed stride per read, shorter reads leave gaps
-    assert not engine.seq_is_dense(strided)
-    b = D.shard_batch(strided, 1, 2)                 # a shard is re-packed back to back
-    assert engine.seq_is_dense(b) and engine.seq_is_dense(synth.simple_reads(6, [2000], 20))
-    np.testing.assert_array_equal(E.seq_off_scan(b.l_seq), b.seq_off)
-    st, keep = engine.host_struct(b, derive_seq_off=True)
-    assert st.seq_off is None and st.l_seq
-    b.seq_off[5] += 1
-    assert not engine.seq_is_dense(b)
-    with pytest.raises(ValueError):
-        engine.host_struct(b, derive_seq_off=True)
-
-
 @pytest.mark.parametrize("schedule,seed", [("reverse", 0), ("random", 1), ("random", 2)])
-@pytest.mark.parametrize("variant", [E.K1F, E.K1W, E.K1W2], ids=["K1f", "K1w", "K1w2"])
-def test_other_thread_interleavings(variant, schedule, seed):
-    """The staging protocols (bulk copy + mbarrier in K1f; full/empty mbarrier ring, producer barrier and
-    cp.async prefetch in K1w / K1w2) under other thread orders than the emulator's default."""
+def test_other_thread_interleavings(schedule, seed):
+    """The staging protocol (full / landed / empty mbarrier ring, producer barrier, cp.async prefetch, the piece
+    queue of the consumers) under other thread orders than the emulator's default."""
     E.set_schedule(schedule, seed)
     try:
         for name in ("shallow", "multi_contig", "long_reads"):
             batch = CASES[name]()
             want, _ = coracle.pileup(batch)
-            got = E.run_pileup(batch, variant, fresh=True, grid=4)
+            got = E.run_pileup(batch, E.F_STORE, grid=4)
             np.testing.assert_array_equal(got[:5], want[:5], err_msg="%s %s/%d" % (name, schedule, seed))
+        batch = CX_CASES["cfg3_like"]()
+        want_c, want_e = coracle.pileup(batch)
+        got_c, got_e = E.pileup_pipeline(batch)
+        np.testing.assert_array_equal(got_c, want_c)
+        np.testing.assert_array_equal(got_e, want_e)
     finally:
         E.set_schedule("forward")

@@ -33,7 +33,7 @@ def timeit(name, b, reps=10):
         k1 += ev[0].elapsed_time(ev[1]) / reps
         k2 += ev[1].elapsed_time(ev[2]) / reps
     print("%-34s reads %9d complex %8d bases %.3e  K1 %.4f ms  K2 %.4f ms  -> %.3e bases/s" % (
-        name, b.n_reads, len(b.complex_idx), b.aligned_bases, k1, k2, b.aligned_bases / ((k1 + k2) * 1e-3)), flush=True)
+        name, b.n_reads, b.n_complex, b.aligned_bases, k1, k2, b.aligned_bases / ((k1 + k2) * 1e-3)), flush=True)
 
 
 t0 = time.time()
@@ -41,6 +41,9 @@ timeit("cfg2 30kb x2000 simple", synth.simple_reads(2, [30_000], 2000))
 timeit("cfg3 30kb x5000 complex", synth.complex_reads(3, 30_000, 5000))
 timeit("cfg3-like 30kb x5000 simple", synth.simple_reads(3, [30_000], 5000))
 timeit("cfg5 64x100kb x500 simple", synth.simple_reads(5, [100_000] * 64, 500))
+timeit("cfg4 5Mb x200 simple", synth.simple_reads(4, [5_000_000], 200))
+timeit("cfg4 5Mb x200, 1% complex", synth.mixed_reads(4, [5_000_000], 200, 0.01))
+timeit("cfg4 5Mb x200, 20% complex", synth.mixed_reads(4, [5_000_000], 200, 0.20))
 timeit("weak shard 1/8 of 5Mb, 1600x", synth.simple_reads(4, [5_000_000], 200, start_frac=(0.0, 0.125), read_seed=[4, 0]))
 timeit("weak shard 1/2 of 5Mb, 400x", synth.simple_reads(4, [5_000_000], 200, start_frac=(0.0, 0.5), read_seed=[4, 0]))
 print("total %.1f s" % (time.time() - t0))

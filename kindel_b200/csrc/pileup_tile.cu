@@ -45,7 +45,7 @@ template <> struct TileCfg<false> {
 template <> struct TileCfg<true> {
     static constexpr int kRmax = 384;
     static constexpr int kCapW = 7168;   // 28 KB
-    static constexpr int kPcap = 768;
+    static constexpr int kPcap = 704;
 };
 
 enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
@@ -64,6 +64,7 @@ struct TileStage {
     // .w = shift | s0 << 8 | s1 << 20, [s0, s1) the piece's slots clipped to the tile.  px[kPcap] = a piece that
     // covers nothing (what idle lanes of a block read).
     int4 px[C::kPcap + 1];
+    unsigned short cxl[C::kPcap ? C::kRmax : 8];  // kCx: the item's tile-eligible complex reads (indices into the item)
     int gs[C::kRmax + 32];       // start slot relative to the tile (all reads: the array stays sorted)
     int cov[KDL_TILE];           // reads / pieces of THIS item covering each slot
     int diff[KDL_TILE + 32];     // producers only: +1 at a piece's first slot, -1 behind its last
@@ -238,67 +239,73 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     prefetch_raw(nu);
                     raw_pending = false;
                 }
-                // ---- complex reads: where each one's pieces go (exclusive prefix of the M-op counts in read order),
-                // and a cut of the item if they do not fit the piece list
+                // ---- complex reads: where each one's pieces go and its rank among the item's complex reads (exclusive
+                // prefix in read order of: M-op count in the low 16 bits, 1 per tile-eligible complex read above),
+                // and a cut of the item if the pieces do not fit the list
                 int pre[PER];
                 int n_px = 0, n_cx = 0;  // pieces / tile-eligible complex reads of the item
                 if constexpr (kCx) {
                     int ub[PER];
+                    bool mine = false;
 #pragma unroll
                     for (int k = 0; k < PER; ++k) {
                         const int i = ptid + k * W_PT;
                         const uint32_t lw = (uint32_t)l[k];
-                        // low 16 bits: pieces (M-op count), bit 16 up: one per tile-eligible complex read
                         ub[k] = (i < n_sub && (lw & (KDL_COMPLEX | KDL_HARD)) == KDL_COMPLEX)
                                     ? (int)((lw >> KDL_NM_SHIFT) & KDL_NM_MASK) | 0x10000 : 0;
-                        int incl = ub[k];  // reads ptid + k * 128: group g = 4 k + pw holds 32 consecutive reads
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) {
-                            const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                            if (lane >= d) incl += o;
-                        }
-                        pre[k] = incl - ub[k];
-                        if (lane == 31) sm.scan[4 * k + pw] = incl;
+                        pre[k] = 0;
+                        mine |= ub[k] != 0;
                     }
-                    producer_sync();
-                    int run = 0;
-#pragma unroll
-                    for (int g = 0; g < 4 * PER; ++g) {
-                        const int t = sm.scan[g];
-#pragma unroll
-                        for (int k = 0; k < PER; ++k)
-                            if (g == 4 * k + pw) pre[k] += run;
-                        run += t;
-                    }
-                    n_px = run & 0xFFFF;
-                    n_cx = run >> 16;
-#pragma unroll
-                    for (int k = 0; k < PER; ++k) { pre[k] &= 0xFFFF; ub[k] &= 0xFFFF; }
-                    if (n_px > W_PCAP) {  // rare: cut the item behind the last read whose pieces still fit
-                        int fits = 0;
+                    if (producer_sync_or(mine)) {  // (items without complex reads pay one barrier, nothing else)
 #pragma unroll
                         for (int k = 0; k < PER; ++k) {
-                            const int i = ptid + k * W_PT;
-                            fits += __popc(__ballot_sync(0xffffffffu, i < n_sub && pre[k] + ub[k] <= W_PCAP));
-                        }
-                        if (lane == 0) atomicAdd(&sm.scan[4 * W_PRODUCERS], fits);
-                        producer_sync();
-                        n_sub = sm.scan[4 * W_PRODUCERS];  // >= 1: one read has at most KDL_TILE_MAXOPS <= kPcap pieces
-                        c1 = c0 + n_sub;
-                        wend = (long long)b.seq_off[c1];   // c1 < u.phi <= n_reads here
-                        n_px = 0;
+                            int incl = ub[k];  // reads ptid + k * 128: group g = 4 k + pw holds 32 consecutive reads
 #pragma unroll
-                        for (int k = 0; k < PER; ++k) {
-                            const int i = ptid + k * W_PT;
-                            if (i >= n_sub) ub[k] = 0;
-                            if (i == n_sub - 1) sm.scan[4 * W_PRODUCERS + 1] = pre[k] + ub[k];  // (n_cx stays > 0)
+                            for (int d = 1; d < 32; d <<= 1) {
+                                const int o = __shfl_up_sync(0xffffffffu, incl, d);
+                                if (lane >= d) incl += o;
+                            }
+                            pre[k] = incl - ub[k];
+                            if (lane == 31) sm.scan[4 * k + pw] = incl;
                         }
                         producer_sync();
-                        n_px = sm.scan[4 * W_PRODUCERS + 1];
-                        if (ptid == 0) sm.scan[4 * W_PRODUCERS] = 0;
+                        int run = 0;
+#pragma unroll
+                        for (int g = 0; g < 4 * PER; ++g) {
+                            const int t = sm.scan[g];
+#pragma unroll
+                            for (int k = 0; k < PER; ++k)
+                                if (g == 4 * k + pw) pre[k] += run;
+                            run += t;
+                        }
+                        n_px = run & 0xFFFF;
+                        n_cx = run >> 16;
+                        if (n_px > W_PCAP) {  // rare: cut the item behind the last read whose pieces still fit
+                            int fits = 0;
+#pragma unroll
+                            for (int k = 0; k < PER; ++k) {
+                                const int i = ptid + k * W_PT;
+                                fits += __popc(__ballot_sync(0xffffffffu, i < n_sub && (pre[k] & 0xFFFF) + (ub[k] & 0xFFFF) <= W_PCAP));
+                            }
+                            if (lane == 0) atomicAdd(&sm.scan[4 * W_PRODUCERS], fits);
+                            producer_sync();
+                            n_sub = sm.scan[4 * W_PRODUCERS];  // >= 1: one read has at most KDL_TILE_MAXOPS <= kPcap pieces
+                            c1 = c0 + n_sub;
+                            wend = (long long)b.seq_off[c1];   // c1 < u.phi <= n_reads here
+#pragma unroll
+                            for (int k = 0; k < PER; ++k) {
+                                const int i = ptid + k * W_PT;
+                                if (i >= n_sub) ub[k] = 0;
+                                if (i == n_sub - 1) sm.scan[4 * W_PRODUCERS + 1] = pre[k] + ub[k];
+                            }
+                            producer_sync();
+                            n_px = sm.scan[4 * W_PRODUCERS + 1] & 0xFFFF;
+                            n_cx = sm.scan[4 * W_PRODUCERS + 1] >> 16;
+                            if (ptid == 0) sm.scan[4 * W_PRODUCERS] = 0;
+                        }
+                        // (the next item's first write to sm.scan[g] comes after at least one more producer barrier of
+                        // this item: no thread still reads the totals then)
                     }
-                    // (the next item's first write to sm.scan[g] comes after its acquire/metadata work and at least
-                    // one producer_sync of this item: no thread still reads the totals then)
                 }
                 const bool last = c1 >= u.phi;
                 Stage& st = acquire_stage(item);
@@ -347,9 +354,19 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             }
                         }
                         st.gs[i] = gs;
-                        st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
-                                                          (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
-                                                          ((-gs) & 7) << 2);
+                        const int raddr = (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2));
+                        bool listed = false;
+                        if constexpr (kCx) {
+                            const uint32_t lw = (uint32_t)l[k];
+                            if ((lw & (KDL_COMPLEX | KDL_HARD)) == KDL_COMPLEX) {
+                                // .z = 0 keeps the entry inert in the simple loop; .x / .w carry the read's start, the
+                                // first slot of its pieces, its SEQ length and its M-op count to the exploding warp
+                                st.meta[i + (i >> 3)] = make_int4(gs, raddr, 0, (pre[k] & 0x3FF) | ((int)(lw & KDL_LEN_MASK) << 10));
+                                st.cxl[pre[k] >> 16] = (unsigned short)i;
+                                listed = true;
+                            }
+                        }
+                        if (!listed) st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2, raddr, nb, ((-gs) & 7) << 2);
                     }
                 }
                 if (ptid < 40) {  // sentinels behind the last read
@@ -365,76 +382,91 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 }
                 if constexpr (kCx) {
                     if (n_cx > 0) {
-                        // ---- explode the complex reads: their CIGARs came with the bulk copy
+                        // ---- explode the complex reads (their CIGARs came with the bulk copy): one WARP per read, one
+                        // LANE per CIGAR op.  The cursors at every op come from two warp scans; M/=/X ops become
+                        // pieces, I / D ops and clip counts are single REDs by their lane, the bases of a clip are
+                        // spread over the lanes.
+                        producer_sync();  // entries and list written
                         mbar_wait(&sm.landed[stage_id], (uint32_t)((item / W_STAGES) & 1));
-#pragma unroll
-                        for (int k = 0; k < PER; ++k) {
-                            const int i = ptid + k * W_PT;
-                            const uint32_t lw = (uint32_t)l[k];
-                            if (i >= n_sub || (lw & (KDL_COMPLEX | KDL_HARD)) != KDL_COMPLEX) continue;
-                            const int lseq = (int)(lw & KDL_LEN_MASK);
+                        for (int j = pw; j < n_cx; j += W_PRODUCERS) {
+                            const int i = (int)st.cxl[j];
+                            const int4 en = st.meta[i + (i >> 3)];
+                            const int lseq = (en.w >> 10) & (int)KDL_LEN_MASK;
                             const int nbw = (lseq + 7) >> 3;
-                            const uint32_t* rw = st.seq + ((long long)so[k] - wa);  // the read's block in shared memory
-                            const uint32_t raddr = seq_base + (uint32_t)(((long long)so[k] - wa) << 2);
+                            const uint32_t* rw = st.seq + (((uint32_t)en.y - seq_base) >> 2);  // the read's block
                             const int n_ops = (int)rw[nbw];
                             uint32_t evt = rw[nbw + 1];
                             const uint32_t* ops = rw + nbw + 2;
-                            int pos = pre[k];
-                            const int pend = pos + (int)((lw >> KDL_NM_SHIFT) & KDL_NM_MASK);
-                            int r = gsv[k], q = 0;
+                            int pos = en.w & 0x3FF;
+                            int r0 = en.x, q0 = 0;
                             auto nib = [&](int qq) { return (int)((rw[qq >> 3] >> (28 - 4 * (qq & 7))) & 0xFu); };
                             auto red = [&](int col, int rel) {  // only slots of THIS tile: every slot has one owner
                                 if ((unsigned)rel < (unsigned)KDL_TILE)
                                     atomicAdd(counts + (long long)col * n_slots + tile_slot + rel, 1);
                             };
-                            for (int o = 0; o < n_ops; ++o) {
-                                const uint32_t cg = ops[o];
+                            for (int o0 = 0; o0 < n_ops; o0 += 32) {
+                                const int o = o0 + lane;
+                                const uint32_t cg = o < n_ops ? ops[o] : 0xFu;  // 0xF: a zero-length no-op
                                 const int len = (int)(cg >> 4);
                                 const int op = (int)(cg & 0xF);
-                                if (op == 0 || op == 7 || op == 8) {  // M = X (kindel.py:49-54): a piece
+                                const bool is_m = op == 0 || op == 7 || op == 8;
+                                const int radv = (is_m || op == 2 || (op == 4 && o > 0)) ? len : 0;
+                                const int qadv = (is_m || op == 1 || op == 4) ? len : 0;
+                                int ir = radv, iq = qadv;
+#pragma unroll
+                                for (int d = 1; d < 32; d <<= 1) {
+                                    const int a1 = __shfl_up_sync(0xffffffffu, ir, d), a2 = __shfl_up_sync(0xffffffffu, iq, d);
+                                    if (lane >= d) { ir += a1; iq += a2; }
+                                }
+                                const int r = r0 + ir - radv, q = q0 + iq - qadv;  // cursors when this lane's op starts
+                                const unsigned m_mask = __ballot_sync(0xffffffffu, is_m);
+                                const unsigned i_mask = __ballot_sync(0xffffffffu, op == 1);
+                                const unsigned s_mask = __ballot_sync(0xffffffffu, op == 4);
+                                const unsigned lt = (1u << lane) - 1u;
+                                if (is_m) {  // M = X (kindel.py:49-54): a piece, or a slot that covers nothing
                                     const int s0 = r < 0 ? 0 : r, s1 = r + len > KDL_TILE ? KDL_TILE : r + len;
+                                    int4 pc = make_int4(0x10000000, (int)seq_base, 0, 0);
                                     if (s0 < s1) {
                                         const int v = r - q;  // slot of the read's base 0
                                         atomicAdd(st.diff + s0, 1);
                                         atomicAdd(st.diff + s1, -1);
-                                        st.px[pos++] = make_int4(((v + 7) >> 3) << 2, (int)raddr, nbw << 2,
-                                                                 (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
+                                        pc = make_int4(((v + 7) >> 3) << 2, en.y, nbw << 2, (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
                                     }
-                                    r += len;
-                                    q += len;
+                                    st.px[pos + __popc(m_mask & lt)] = pc;
                                 } else if (op == 1) {  // I (kindel.py:55-58)
                                     if ((unsigned)r < (unsigned)KDL_TILE) {
                                         atomicAdd(counts + (long long)KDL_INS * n_slots + tile_slot + r, 1);
                                         if (ins_events)
-                                            reinterpret_cast<int4*>(ins_events)[evt] =
+                                            reinterpret_cast<int4*>(ins_events)[evt + __popc(i_mask & lt)] =
                                                 make_int4((int)(tile_slot + r), (int)(c0 + i), q, len);
                                     }
-                                    evt += 1;
-                                    q += len;
                                 } else if (op == 2) {  // D (kindel.py:59-62)
                                     for (int d = 0; d < len; ++d) red(KDL_DEL, r + d);
-                                    r += len;
-                                } else if (op == 4) {  // S
-                                    if (o == 0) {      // left clip (kindel.py:64-73)
-                                        red(KDL_CLIP_ENDS, r);
-                                        for (int g = 0; g < len; ++g) {
-                                            const int rel = r - len + g;
-                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CEW_A + nib2col(nib(g)), rel);
-                                        }
-                                        q += len;
-                                    } else {           // right clip (kindel.py:74-81); never reaches the contig end here
-                                        red(KDL_CLIP_STARTS, r - 1);
-                                        for (int d = 0; d < len; ++d) {
-                                            const int rel = r + d;
-                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CSW_A + nib2col(nib(q + d)), rel);
-                                        }
-                                        r += len;
-                                        q += len;
-                                    }
+                                } else if (op == 4) {  // S: the count of the clip; its bases below
+                                    if (o == 0) red(KDL_CLIP_ENDS, r); else red(KDL_CLIP_STARTS, r - 1);
                                 }
                                 // N, H, P: no-op (kindel.py:49-63 has no branch for them)
+                                for (unsigned sm_ = s_mask; sm_; sm_ &= sm_ - 1) {  // clip bases, all lanes on one clip
+                                    const int src = __ffs(sm_) - 1;
+                                    const int sr = __shfl_sync(0xffffffffu, r, src), sq = __shfl_sync(0xffffffffu, q, src);
+                                    const int sl = __shfl_sync(0xffffffffu, len, src);
+                                    if (o0 + src == 0) {  // left clip (kindel.py:64-73): bases end where the read starts
+                                        for (int g = lane; g < sl; g += 32) {
+                                            const int rel = sr - sl + g;
+                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CEW_A + nib2col(nib(g)), rel);
+                                        }
+                                    } else {              // right clip (kindel.py:74-81); never reaches the contig end here
+                                        for (int d = lane; d < sl; d += 32) {
+                                            const int rel = sr + d;
+                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CSW_A + nib2col(nib(sq + d)), rel);
+                                        }
+                                    }
+                                }
+                                pos += __popc(m_mask);
+                                evt += (uint32_t)__popc(i_mask);
+                                r0 += __shfl_sync(0xffffffffu, ir, 31);
+                                q0 += __shfl_sync(0xffffffffu, iq, 31);
                             }
-                            while (pos < pend) st.px[pos++] = make_int4(0x10000000, (int)seq_base, 0, 0);  // covers nothing
                         }
                     }
                 }

@@ -152,6 +152,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // named barrier 1: the 128 producer threads only
 __device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// the same barrier with an OR-reduction of a predicate over the 128 threads
+__device__ __forceinline__ bool producer_sync_or(bool pred) {
+    uint32_t r;
+    asm volatile("{\n"
+                 ".reg .pred p, q;\n"
+                 "setp.ne.u32 p, %1, 0;\n"
+                 "bar.red.or.pred q, 1, 128, p;\n"
+                 "selp.u32 %0, 1, 0, q;\n"
+                 "}\n"
+                 : "=r"(r) : "r"((uint32_t)pred) : "memory");
+    return r != 0;
+}
 template <int kRegs> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 #endif  // KDL_HOST_EMU

@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(Exchange x, int ep
         for (long long s = tail0 + threadIdx.x; s < x.slice_hi[p]; s += blockDim.x) x.calls[x.rank][s] = x.calls[p][s];
 }
 
+// K2x.  Every CTA takes ONE contiguous chunk of the rank's slot slice and waits only for the peers whose
+// footprint reaches into that chunk: with coordinate-block shards and slices cut along the footprints that is
+// nobody for the core of the slice (those CTAs run at the speed of the plain vote, straight after the rank's own
+// pileup) and one neighbour for the halo chunks.
 __global__ void __launch_bounds__(256)
 vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, int epoch) {
     // this kernel runs after the rank's pileup kernels in stream order, so its own table is complete:
@@ -153,15 +157,31 @@ vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, in
         __threadfence_system();
         st_release_sys(x.ready[threadIdx.x] + x.rank, epoch);
     }
-    // ... and every table this CTA may read must be complete: ready[rank][p] >= epoch for all p
-    if (threadIdx.x < x.peers.n)
-        while (ld_acquire_sys(x.ready_local + threadIdx.x) < epoch) __nanosleep(32);
-    __syncthreads();
     const Peers& peers = x.peers;
     const long long slot_lo = x.slice_lo[x.rank], slot_hi = x.slice_hi[x.rank];
+    const long long quads = (slot_hi - slot_lo + 3) >> 2;
+    const long long per_cta = (((quads + gridDim.x - 1) / gridDim.x) + 31) & ~31ll;  // whole warps iterate together
+    const long long q0 = (long long)blockIdx.x * per_cta;
+    long long q1 = q0 + per_cta;
+    if (q1 > ((quads + 31) & ~31ll)) q1 = (quads + 31) & ~31ll;
+    // ... and every table this CTA reads must be complete: ready[rank][p] >= epoch for the peers p whose footprint
+    // overlaps the chunk (the look-ahead depth reads up to 4 slots past it)
+    __shared__ unsigned overlap_mask;
+    if (threadIdx.x == 0) overlap_mask = 0u;
+    __syncthreads();
+    if (threadIdx.x < peers.n && q0 < q1) {
+        const int p = threadIdx.x;
+        const long long c_lo = slot_lo + q0 * 4, c_hi = slot_lo + q1 * 4 + 4;
+        if (peers.lo[p] < c_hi && peers.hi[p] > c_lo) {
+            atomicOr(&overlap_mask, 1u << p);
+            if (p != x.rank)
+                while (ld_acquire_sys(x.ready_local + p) < epoch) __nanosleep(32);
+        }
+    }
+    __syncthreads();
+    const unsigned mask = overlap_mask;
     uint8_t* __restrict__ calls = x.calls[x.rank];
-    for (long long quad = (long long)blockIdx.x * blockDim.x + threadIdx.x; quad * 4 < ((slot_hi - slot_lo + 127) & ~127ll);
-         quad += (long long)gridDim.x * blockDim.x) {  // whole warps iterate together (shuffle below)
+    for (long long quad = q0 + threadIdx.x; quad < q1; quad += blockDim.x) {
         const long long s = slot_lo + quad * 4;
         const bool active = s < slot_hi;
         int4 v[KDL_NVOTE_COL];
@@ -169,7 +189,8 @@ vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, in
         if (active) {
 #pragma unroll
             for (int k = 0; k < KDL_NVOTE_COL; ++k) v[k] = make_int4(0, 0, 0, 0);
-            for (int p = 0; p < peers.n; ++p) {
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int p = __ffs(m) - 1;
                 if (s + 4 <= peers.lo[p] || s >= peers.hi[p]) continue;  // nothing of table p here
                 int4 t[KDL_NVOTE_COL];  // seven independent 128-bit loads in flight per table
 #pragma unroll
@@ -186,8 +207,13 @@ vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, in
         if ((threadIdx.x & 31) == 31 || !active || s + 4 >= slot_hi) {
             dn = 0;
             if (active && s + 4 < n_slots) {
+                for (unsigned m = mask; m; m &= m - 1) {
+                    const int p = __ffs(m) - 1;
+                    if (s + 4 >= peers.lo[p] && s + 4 < peers.hi[p]) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dn += load1<true>(nullptr, peers, k, n_slots, s + 4);
+                        for (int k = 0; k < 4; ++k) dn += peers.tab[p][(long long)k * n_slots + s + 4];
+                    }
+                }
             }
         }
         if (active) {

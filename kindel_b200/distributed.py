@@ -104,8 +104,35 @@ def owner_slices(n_slots: int, world: int, align: int = 512):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def footprint_slices(feet, n_slots: int, align: int = 64):
+    """Slot ownership cut ALONG the shards' footprints: rank r votes on (roughly) the slots only its own table
+    covers, the overlap with a neighbour (a halo of at most one read's reach) is cut in the middle.  Then the
+    core of every slice needs no peer table at all.  Needs footprints that are ordered like the ranks (coordinate
+    blocks, contig runs); anything else falls back to the equal split.  Empty shards own nothing."""
+    world = len(feet)
+    live = [r for r in range(world) if feet[r][1] > feet[r][0]]
+    ordered = all(feet[a][0] <= feet[b][0] and feet[a][1] <= feet[b][1] for a, b in zip(live, live[1:]))
+    if not ordered or not live:
+        return owner_slices(n_slots, world, 512)
+    bounds = [0]  # bounds[k] .. bounds[k + 1] = slice of the k-th live shard
+    for a, b in zip(live, live[1:]):
+        mid = (feet[a][1] + feet[b][0]) // 2 // align * align
+        bounds.append(min(max(mid, bounds[-1]), n_slots))
+    bounds.append(n_slots)
+    out, k = [], 0
+    for r in range(world):
+        if k < len(live) and r == live[k]:
+            out.append((bounds[k], bounds[k + 1]))
+            k += 1
+        else:  # empty shard: zero width, where the next live slice starts
+            at = bounds[k] if k < len(live) else n_slots
+            out.append((at, at))
+    return out
+
+
 class PeerTables:
-    """This rank's IPC-exportable count table plus mappings of every peer's table."""
+    """This rank's IPC block -- TWO count tables and TWO call buffers (epoch parity) plus the flag words -- and
+    mappings of every peer's block."""
 
     def __init__(self, n_slots: int, device, group=None):
         import torch
@@ -117,10 +144,10 @@ class PeerTables:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        # one IPC block per rank: [count table][call bytes][flags: ready[16], done[16], counter]
+        # [table 0][table 1][calls 0][calls 1][flags: ready[16], done[16], counter]
         self.table_bytes = _ffi.KDL_NCOL * n_slots * 4
-        self.calls_off = self.table_bytes
-        self.flags_off = self.table_bytes + n_slots
+        self.calls_off = 2 * self.table_bytes
+        self.flags_off = self.calls_off + 2 * n_slots
         nbytes = self.flags_off + 256
         ptr = C.c_void_p()
         with torch.cuda.device(device):
@@ -141,15 +168,17 @@ class PeerTables:
                 _ffi.check(self.lib.kdl_ipc_open(h, C.byref(p)), "kdl_ipc_open")
                 self.peer_ptrs.append(p.value)
                 self._opened.append(p.value)
-        self.counts = _wrap_device_memory(self.ptr, (_ffi.KDL_NCOL, n_slots), device)
-        self.calls = _wrap_device_memory(self.ptr + self.calls_off, (n_slots,), device, "|u1")
+        self.counts = [_wrap_device_memory(self.ptr + k * self.table_bytes, (_ffi.KDL_NCOL, n_slots), device)
+                       for k in range(2)]
+        self.calls = [_wrap_device_memory(self.ptr + self.calls_off + k * n_slots, (n_slots,), device, "|u1")
+                      for k in range(2)]
 
-    def exchange_struct(self, feet, slices) -> _ffi.KdlExchange:
+    def exchange_struct(self, feet, slices, parity: int) -> _ffi.KdlExchange:
         x = _ffi.KdlExchange()
         x.n_ranks, x.rank = self.world, self.rank
         for r, base in enumerate(self.peer_ptrs):
-            x.tables[r] = base
-            x.calls[r] = base + self.calls_off
+            x.tables[r] = base + parity * self.table_bytes
+            x.calls[r] = base + self.calls_off + parity * self.n_slots
             x.ready[r] = base + self.flags_off
             x.done[r] = base + self.flags_off + 64
             x.foot_lo[r], x.foot_hi[r] = feet[r]
@@ -183,9 +212,17 @@ def _wrap_device_memory(ptr: int, shape, device, typestr="<i4"):
 
 
 class ShardedConsensus:
-    """One rank's part of a read-sharded pileup + vote.  `step()` is the whole exchange + vote."""
+    """One rank's part of a sharded pileup + vote.  `step()` is K1 on the shard + the exchange + the vote and
+    returns the COMPLETE call bytes on every rank.
 
-    def __init__(self, shard: bamio.ReadBatch, device, mode: str = "peer", group=None):
+    mode "fused" (default): no NCCL on the data path.  Tables and call buffers are double-buffered by epoch
+    parity, so the step's only cross-rank waits are on events of the SAME step: a halo chunk of K2x waits for the
+    neighbour whose footprint reaches into it (the core of a slice waits for nobody), and the gather K2g waits for
+    each peer's slice.  Nothing of step n has to finish before K1 of step n+1 starts overwriting the other
+    table.  "peer": the same vote kernel behind an NCCL barrier + all_gather.  "allreduce": NCCL all_reduce of
+    the 7 vote columns, vote replicated (what the north star words literally; the baseline)."""
+
+    def __init__(self, shard: bamio.ReadBatch, device, mode: str = "fused", group=None):
         import torch
         import torch.distributed as dist
 
@@ -201,97 +238,110 @@ class ShardedConsensus:
         self.epoch = 0
         if mode in ("peer", "fused"):
             self.tables = PeerTables(self.n_slots, device, group)
-            self.counts = self.tables.counts
             feet = [None] * self.world
             dist.all_gather_object(feet, footprint(shard), group=group)
+            self.feet = feet
             self.foot = feet[self.rank]
-            self.slices = owner_slices(self.n_slots, self.world)
-            self.xstruct = self.tables.exchange_struct(feet, self.slices)
+            self.slices = footprint_slices(feet, self.n_slots)
+            self.xstruct = [self.tables.exchange_struct(feet, self.slices, k) for k in range(2)]
             self.foot_lo = (C.c_int64 * self.world)(*[f[0] for f in feet])
             self.foot_hi = (C.c_int64 * self.world)(*[f[1] for f in feet])
-            self.ptr_arr = (C.c_void_p * self.world)(*self.tables.peer_ptrs)
-            self.slices = owner_slices(self.n_slots, self.world)
-            self.calls = torch.empty(self.n_slots, dtype=torch.uint8, device=device)
+            self.ptr_arr = [(C.c_void_p * self.world)(*[p + k * self.tables.table_bytes for p in self.tables.peer_ptrs])
+                            for k in range(2)]
+            self.table = [engine.CountTable(self.n_slots, device, tensor=self.tables.counts[k]) for k in range(2)]
             self.sizes = [hi - lo for lo, hi in self.slices]
         elif mode == "allreduce":
             self.tables = None
-            self.counts = torch.zeros((_ffi.KDL_NCOL, self.n_slots), dtype=torch.int32, device=device)
+            self.foot = (0, self.n_slots)
+            t = torch.zeros((_ffi.KDL_NCOL, self.n_slots), dtype=torch.int32, device=device)
+            self.table = [engine.CountTable(self.n_slots, device, tensor=t)] * 2
         else:
             raise ValueError("mode must be 'fused', 'peer' or 'allreduce'")
-        if mode == "allreduce":
-            self.foot = (0, self.n_slots)
-        self.table = engine.CountTable(self.n_slots, device, tensor=self.counts)
+        self.counts = self.table[0].t  # (the table of the LAST step: see `last_counts`)
+
+    @property
+    def last_counts(self):
+        """This rank's own count table of the most recent step (NOT reduced, except in allreduce mode)."""
+        return self.table[self.epoch & 1].t
 
     def step(self, min_depth=1, timers=None):
-        """zero, K1 on the shard, exchange, vote.  Returns the complete call bytes on every rank.
+        """K1 on the shard, exchange, vote.  Returns the complete call bytes on every rank.
         `timers`: optional pair of CUDA events recorded around K1 (bench.py's roofline leg)."""
         torch, dist, engine = self.torch, self.dist, self.engine
+        self.epoch += 1
+        par = self.epoch & 1
+        table = self.table[par]
         if timers:
             timers[0].record()
         if self.mode == "allreduce":
             # the all_reduce writes sums everywhere: the whole table is dirty every step
-            self.table.dirty = (0, self.n_slots)
-            self.table.dirty_rest = True  # columns 5, 6 hold sums over ALL ranks after the all_reduce
-            engine.pileup(self.dbatch, check=False, table=self.table)
+            table.dirty = (0, self.n_slots)
+            table.dirty_rest = True  # columns 5, 6 hold sums over ALL ranks after the all_reduce
+            engine.pileup(self.dbatch, check=False, table=table)
         else:  # only this shard's footprint is ever touched (kdl_table_alloc zero-filled the rest)
-            engine.pileup(self.dbatch, check=False, table=self.table, slot_range=self.foot)
+            engine.pileup(self.dbatch, check=False, table=table, slot_range=self.foot)
         if timers:
             timers[1].record()
         if self.mode == "fused":
-            # no NCCL on the data path: flags + reduction + vote (K2x) and the pull of the call slices
-            # (K2g) are two launches of this library over NVLink peer memory
-            self.epoch += 1
-            lo, hi = self.slices[self.rank]
             st = int(torch.cuda.current_stream(self.device).cuda_stream)
             with torch.cuda.device(self.device):
-                _ffi.check(self.lib.kdl_exchange_vote(C.byref(self.xstruct), self.n_slots, int(math.ceil(min_depth)),
+                _ffi.check(self.lib.kdl_exchange_vote(C.byref(self.xstruct[par]), self.n_slots, int(math.ceil(min_depth)),
                                                       self.epoch, st), "kdl_exchange_vote")
-                _ffi.check(self.lib.kdl_exchange_wait(C.byref(self.xstruct), self.epoch, st), "kdl_exchange_wait")
-            return self.tables.calls
+                _ffi.check(self.lib.kdl_exchange_wait(C.byref(self.xstruct[par]), self.epoch, st), "kdl_exchange_wait")
+            return self.tables.calls[par]
         if self.mode == "allreduce":
-            dist.all_reduce(self.counts[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(table.t[: _ffi.KDL_NVOTE_COL], op=dist.ReduceOp.SUM, group=self.group)
             if getattr(self, "_calls_ar", None) is None:
                 self._calls_ar = torch.empty(self.n_slots, dtype=torch.uint8, device=self.device)
-            return engine.vote(self.counts, min_depth, out=self._calls_ar)
-        # every table complete before anybody reads it over NVLink
+            return engine.vote(table.t, min_depth, out=self._calls_ar)
+        # "peer": every table complete before anybody reads it over NVLink
         dist.barrier(group=self.group)
         lo, hi = self.slices[self.rank]
+        calls = self.tables.calls[par]
         with torch.cuda.device(self.device):
             rc = self.lib.kdl_vote_peers_sparse(
-                self.ptr_arr, self.foot_lo, self.foot_hi, self.world, self.n_slots, lo, hi,
-                int(math.ceil(min_depth)), self.calls.data_ptr(), None,
+                self.ptr_arr[par], self.foot_lo, self.foot_hi, self.world, self.n_slots, lo, hi,
+                int(math.ceil(min_depth)), calls.data_ptr(), None,
                 int(torch.cuda.current_stream(self.device).cuda_stream))
         _ffi.check(rc, "kdl_vote_peers_sparse")
-        # 1 byte per slot; also the fence after which peers may overwrite their tables again
-        self._gather_calls(lo, hi)
-        return self.calls
+        # 1 byte per slot; also the fence after which peers may overwrite this parity's tables again
+        self._gather_calls(calls, lo, hi)
+        return calls
 
-    def _gather_calls(self, lo, hi):
+    def _gather_calls(self, calls, lo, hi):
         torch, dist = self.torch, self.dist
-        chunk = max(self.sizes)
-        if all(sz == chunk for sz in self.sizes):
-            dist.all_gather_into_tensor(self._recv(chunk), self.calls[lo:hi].clone(), group=self.group)
-            self.calls.copy_(self._recv(chunk))
-            return
+        chunk = max(max(self.sizes), 1)
         send = torch.zeros(chunk, dtype=torch.uint8, device=self.device)
-        send[: hi - lo] = self.calls[lo:hi]
+        send[: hi - lo] = calls[lo:hi]
         recv = self._recv(chunk)
         dist.all_gather_into_tensor(recv, send, group=self.group)
         for r, (a, b) in enumerate(self.slices):
-            self.calls[a:b] = recv[r * chunk: r * chunk + (b - a)]
+            calls[a:b] = recv[r * chunk: r * chunk + (b - a)]
 
     def _recv(self, chunk):
         if getattr(self, "_recv_buf", None) is None or self._recv_buf.numel() != chunk * self.world:
             self._recv_buf = self.torch.empty(chunk * self.world, dtype=self.torch.uint8, device=self.device)
         return self._recv_buf
 
+    def reduce_table(self, dst: int = 0):
+        """The full 19-column table of the whole job on rank `dst` (NCCL reduce of the last step's tables; for the
+        API paths that need more than call bytes: weights / features / --realign).  Returns it on `dst`, else None."""
+        torch, dist = self.torch, self.dist
+        t = self.last_counts.clone()
+        if self.mode != "allreduce":
+            dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=self.group)
+        else:  # columns 0..6 already hold the sums everywhere; the rest still per shard
+            dist.reduce(t[_ffi.KDL_NVOTE_COL:], dst=dst, op=dist.ReduceOp.SUM, group=self.group)
+        return t if self.rank == dst else None
+
     def check_errors(self):
-        """Raise the reference's exception if any rank's shard hit a data error (first rank wins)."""
+        """Raise the reference's exception if this rank's shard hit a data error."""
         # engine.pileup(check=False) leaves the flag unread in the hot loop; a checked pass is
         # `engine.pileup(self.dbatch)` on a scratch table, which raises exactly like one GPU.
-        counts = self.torch.zeros_like(self.counts)
+        counts = self.torch.zeros_like(self.last_counts)
         self.engine.pileup(self.dbatch, counts, check=True)
 
     def close(self):
         if self.tables is not None:
             self.tables.close()
+            self.tables = None

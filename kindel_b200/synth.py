@@ -75,13 +75,14 @@ def simple_reads(seed: int, contig_lens, depth: float, read_len: int = 150, sub_
 
 
 def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150, sub_rate: float = 0.01,
-                  edge_tail: bool = True, unsorted_tail: bool = False) -> bamio.ReadBatch:
+                  edge_tail: bool = True, unsorted_tail: bool = False, start_frac=None, read_seed=None,
+                  ref_seed=None) -> bamio.ReadBatch:
     """Config-3 shape: per read p=0.5 leading soft clip (1-29), p=0.5 trailing soft clip (1-29),
     0-3 indel events (I or D, length 1-4) between M segments; query length is always `read_len`.
     With edge_tail a few hundred reads using N / = / X / H / P ops, H-then-S, clips overhanging
     both contig ends and POS == 0 are added (all legal for the reference, no exceptions); unsorted_tail leaves them
     at the end of the batch (an unsorted file: the order-independent kernels take it)."""
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed if read_seed is None else read_seed)
     L = int(contig_len)
     n = int(round(depth * L / read_len))
     lead = np.where(rng.random(n) < 0.5, rng.integers(1, 30, size=n), 0)
@@ -103,7 +104,10 @@ def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150,
     seg = np.where(seg_on, seg + 10, 0)
     seg[np.arange(n), n_ev] += m_total - seg.sum(axis=1)  # rounding remainder into the last segment
     ref_span = m_total + del_total
-    start = np.sort(rng.integers(0, np.maximum(L - ref_span.max() - 1, 1), size=n))
+    span = max(int(L - ref_span.max() - 1), 1)  # start_frac: a weak-scaling shard's share of the start range
+    s_lo, s_hi = (0, span) if start_frac is None else (int(span * start_frac[0]),
+                                                       max(int(span * start_frac[1]), int(span * start_frac[0]) + 1))
+    start = np.sort(rng.integers(s_lo, s_hi, size=n))
 
     # ops as an [n, 9] grid: S, M0, E0, M1, E1, M2, E2, M3, S
     op_len = np.zeros((n, 9), dtype=np.int64)
@@ -121,7 +125,7 @@ def complex_reads(seed: int, contig_len: int, depth: float, read_len: int = 150,
     cig_off = np.concatenate([[0], np.cumsum(n_ops)])
 
     # bases: random everywhere, reference copy (+ substitutions) on M segments
-    ref = random_contig(rng, L)
+    ref = random_contig(rng if ref_seed is None else np.random.default_rng(ref_seed), L)
     words = (read_len + 7) // 8
     nib = _CODE[rng.integers(0, 4, size=(n, words * 8), dtype=np.uint8)]
     nib[:, read_len:] = 0
@@ -198,14 +202,19 @@ def on_contig(batch: bamio.ReadBatch, names, contig_lens, c: int) -> bamio.ReadB
                           batch.seq_len, batch.cig_off, batch.cigar, bases, n_records=batch.n_reads)
 
 
-def mixed_reads(seed: int, contig_lens, depth: float, complex_frac: float, read_len: int = 150) -> bamio.ReadBatch:
+def mixed_reads(seed: int, contig_lens, depth: float, complex_frac: float, read_len: int = 150, start_frac=None,
+                read_seed=None) -> bamio.ReadBatch:
     """What a real short-read alignment looks like: coordinate-sorted `read_len`M reads with a fraction of clipped /
-    indel reads (the config-3 generator without its edge-case tail) mixed in at the same depth profile."""
+    indel reads (the config-3 generator without its edge-case tail) mixed in at the same depth profile.
+    start_frac / read_seed: as in simple_reads (a weak-scaling shard)."""
     contig_lens = [int(x) for x in contig_lens]
     names = ["ctg%d" % i for i in range(len(contig_lens))]
-    parts = [simple_reads(seed, contig_lens, depth * (1.0 - complex_frac), read_len=read_len)]
+    parts = [simple_reads(seed, contig_lens, depth * (1.0 - complex_frac), read_len=read_len, start_frac=start_frac,
+                          read_seed=read_seed)]
     for c, L in enumerate(contig_lens):
-        cx = complex_reads(seed * 131 + c, L, depth * complex_frac, read_len=read_len, edge_tail=False)
+        rs = None if read_seed is None else list(np.atleast_1d(read_seed)) + [7, c]
+        cx = complex_reads(seed * 131 + c, L, depth * complex_frac, read_len=read_len, edge_tail=False,
+                           start_frac=start_frac, read_seed=rs)
         parts.append(on_contig(cx, names, contig_lens, c))
     return bamio.merge_batches(parts)
 

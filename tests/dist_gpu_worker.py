@@ -19,25 +19,32 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    for kind in ("simple", "complex", "multi"):
+    for kind in ("simple", "complex", "multi", "mixed", "contigs"):
         if kind == "simple":
             full = synth.simple_reads(31, [300_000], 120)
         elif kind == "complex":
             full = synth.complex_reads(32, 40_000, 300)
+        elif kind == "mixed":
+            full = synth.mixed_reads(34, [200_000], 100, 0.1)
         else:
             full = synth.simple_reads(33, [50_000] * 6, 90)
         oc, _ = coracle.pileup(full)
         want = coracle.vote(oc, 2)
-        shard = D.shard_batch(full, rank, world)
+        # "contigs": whole contigs per rank -- no slot is shared, nothing is reduced
+        shard = D.shard_by_contig(full, rank, world) if kind == "contigs" else D.shard_batch(full, rank, world)
         for mode in ("fused", "peer", "allreduce"):
             sc = D.ShardedConsensus(shard, dev, mode=mode)
-            for _ in range(3):  # repeated steps: the tables are re-zeroed and re-read safely
+            for it in range(5):  # repeated steps: both table parities are re-used and re-read safely
                 calls = sc.step(2)
-            torch.cuda.synchronize()
-            got = calls.cpu().numpy()
-            assert np.array_equal(got, want), (kind, mode, rank, int((got != want).sum()))
+                if it in (0, 4):
+                    torch.cuda.synchronize()
+                    got = calls.cpu().numpy()
+                    assert np.array_equal(got, want), (kind, mode, rank, it, int((got != want).sum()))
             if mode == "allreduce":
-                assert np.array_equal(sc.counts[:7].cpu().numpy(), oc[:7])
+                assert np.array_equal(sc.last_counts[:7].cpu().numpy(), oc[:7])
+            full_table = sc.reduce_table(0)
+            if rank == 0:
+                assert np.array_equal(full_table.cpu().numpy(), oc), (kind, mode, "reduce_table")
             sc.close()
     dist.barrier()
     if rank == 0:

@@ -317,6 +317,7 @@ inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift) {
     return (uint32_t)(((((uint64_t)hi << 32) | lo) << (shift & 31)) >> 32);
 }
 inline int atomicOr(int* p, int v) { const int old = *p; *p = old | v; return old; }
+inline unsigned atomicOr(unsigned* p, unsigned v) { const unsigned old = *p; *p = old | v; return old; }
 inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
     const unsigned long long old = *p; if (v < old) *p = v; return old;
 }
@@ -398,6 +399,13 @@ inline void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {  // mbarrier.ex
     reinterpret_cast<MbarBits*>(bar)->tx += (int32_t)bytes;
 }
 inline void producer_sync() { emu::named_barrier(1, 128); }  // bar.sync 1, 128
+inline bool producer_sync_or(bool pred) {                    // bar.red.or.pred on the same barrier
+    static unsigned tag[2] = {0u, 0u};  // generation of the barrier at which somebody last voted true, per parity
+    const unsigned g = emu::M().named_gen[1];
+    if (pred) tag[g & 1u] = g + 1u;
+    emu::named_barrier(1, 128);
+    return tag[g & 1u] == g + 1u;
+}
 template <int kRegs> inline void reg_dealloc() {}            // setmaxnreg: nothing to model
 template <int kRegs> inline void reg_alloc() {}
 // system-scope flag accesses of the exchange kernels (vote.cu): plain accesses here; a poll yields, so a flag

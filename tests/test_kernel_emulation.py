@@ -191,25 +191,33 @@ def test_peer_vote_over_footprints():
         np.testing.assert_array_equal(reduced[:, lo:hi], full[:7, lo:hi])
 
 
+@pytest.mark.parametrize("cut", ["equal", "footprint", "contigs"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_fused_exchange_epochs(world):
-    """K2x + K2g for all ranks of a read-sharded pileup, two epochs with different data (flags compare epochs):
-    every rank ends up with the complete call bytes of the summed table."""
+def test_fused_exchange_epochs(world, cut):
+    """K2x + K2g for all ranks of a sharded pileup, three epochs with different data (flags compare epochs), the
+    tables and call buffers alternating by epoch parity as distributed.ShardedConsensus does: every rank ends up
+    with the complete call bytes of the summed table.  Slices cut equally, along the footprints (the core of a
+    slice then reads no peer), or along whole contigs (no shared slot at all)."""
     from kindel_b200 import distributed as D
 
     flags = {k: [np.zeros(16, dtype=np.int32) for _ in range(world)] for k in ("ready", "done")}
     flags["counter"] = [np.zeros(1, dtype=np.int32) for _ in range(world)]
-    calls = None
-    for epoch, seed in ((1, 74), (2, 75)):
-        batch = synth.complex_reads(seed, 7000, 30)
+    bufs = None
+    for epoch, seed in ((1, 74), (2, 75), (3, 76)):
+        if cut == "contigs":
+            batch = synth.simple_reads(seed, [1800, 2500, 700, 1900], 25)
+            shards = [D.shard_by_contig(batch, r, world) for r in range(world)]
+        else:
+            batch = synth.complex_reads(seed, 7000, 30)
+            shards = [D.shard_batch(batch, r, world) for r in range(world)]
         full, _ = coracle.pileup(batch)
-        shards = [D.shard_batch(batch, r, world) for r in range(world)]
         tables = [coracle.pileup(s)[0] for s in shards]
         feet = [D.footprint(s) for s in shards]
         n_slots = full.shape[1]
-        slices = D.owner_slices(n_slots, world)
-        if calls is None:
-            calls = [np.full(n_slots, 0xEE, dtype=np.uint8) for _ in range(world)]
+        slices = D.owner_slices(n_slots, world) if cut == "equal" else D.footprint_slices(feet, n_slots)
+        if bufs is None:
+            bufs = [[np.full(n_slots, 0xEE, dtype=np.uint8) for _ in range(world)] for _ in range(2)]
+        calls = bufs[epoch & 1]
         E.exchange_epoch(tables, feet, slices, calls, flags, epoch, min_depth=2)
         want = coracle.vote(full, 2)
         for r in range(world):

@@ -463,25 +463,6 @@ def run_native(args):
     value = total_bases / (ms_per_step * 1e-3)
     step_q = quantiles(tm["step_ms"])
 
-    # ---- strong scaling beside the weak line (N > 1): the fixed N = 1 data set cut N ways
-    strong = None
-    if world > 1 and args.scaling == "weak" and not args.no_strong:
-        sc.close()
-        sb, s_total, s_sharding, s_step, s_sc = build_case("strong")
-        stm = time_steps(s_step, args.steps, args.warmup, torch, dist, world, dev, min_seconds=0.25)
-        s_got = hashlib.sha256(stm["out"].cpu().numpy().tobytes()).hexdigest()
-        s_par = s_got == oracle_digest(sb, torch, dist, world, dev)
-        tt = torch.tensor([stm["total_ms"], stm["k1_ms"], 0.0 if s_par else 1.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        s_ms = float(tt[0]) / stm["reps"]
-        strong = {"scaling": "strong", "workload": args.workload, "sharding": s_sharding,
-                  "aligned_bases_total": int(s_total), "ms_per_step": s_ms, "value": s_total / (s_ms * 1e-3),
-                  "unit": UNIT, "steps_timed": stm["reps"], "step_ms": quantiles(stm["step_ms"]),
-                  "k0_k1_ms": float(tt[1]), "parity": float(tt[2]) == 0.0}
-        s_sc.close()
-        del sb, s_step, s_sc
-        batch, total_bases, sharding, step, sc = build_case(args.scaling)  # the e2e leg runs on the weak case again
-
     # ---- e2e from pinned HOST buffers ---------------------------------------------------------------
     n_e2e = max(3, min(args.steps, 10))
     if world == 1:
@@ -541,6 +522,23 @@ def run_native(args):
                "parity": float(tt[2]) == 0.0,
                "api": "distributed.ShardedConsensus.step from pinned host buffers: per rank H2D of its shard, K0 + K1, "
                       "exchange + vote, D2H of the complete call bytes (byte counts are per rank; time = max over ranks)"}
+
+    # ---- strong scaling beside the weak line (N > 1): the fixed N = 1 data set cut N ways
+    strong = None
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        sb, s_total, s_sharding, s_step, s_sc = build_case("strong")
+        stm = time_steps(s_step, args.steps, args.warmup, torch, dist, world, dev, min_seconds=0.25)
+        s_got = hashlib.sha256(stm["out"].cpu().numpy().tobytes()).hexdigest()
+        s_par = s_got == oracle_digest(sb, torch, dist, world, dev)
+        tt = torch.tensor([stm["total_ms"], stm["k1_ms"], 0.0 if s_par else 1.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        s_ms = float(tt[0]) / stm["reps"]
+        strong = {"scaling": "strong", "workload": args.workload, "sharding": s_sharding,
+                  "aligned_bases_total": int(s_total), "ms_per_step": s_ms, "value": s_total / (s_ms * 1e-3),
+                  "unit": UNIT, "steps_timed": stm["reps"], "step_ms": quantiles(stm["step_ms"]),
+                  "k0_k1_ms": float(tt[1]), "parity": float(tt[2]) == 0.0}
+        s_sc.close()
+        del sb, s_step, s_sc
 
     if rank == 0:
         peak, peak_src = measured_peak()

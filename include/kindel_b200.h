@@ -122,7 +122,8 @@ typedef struct kdl_batch {
      * this is non-zero) and the ascending indices of the KDL_HARD ones, which K1g walks */
     int64_t n_complex;
     int64_t n_hard;
-    const uint32_t* hard_idx; /* [n_hard]; may be NULL when n_hard == 0 */
+    const uint32_t* complex_idx; /* [n_complex] ascending indices of ALL complex reads; may be NULL when n_complex == 0 */
+    const uint32_t* hard_idx;    /* [n_hard] ascending indices of the KDL_HARD ones; may be NULL when n_hard == 0 */
     /* scratch for the tile index kdl_pileup builds (K0): uint32[8 * n_slots / KDL_TILE], device
      * memory owned by the caller.  NULL, or reads_sorted == 0, selects the order-independent
      * atomic kernels instead of the tile-owner kernel. */
@@ -180,6 +181,28 @@ int kdl_vote(const int32_t* counts, int64_t n_slots, int64_t min_depth_ceil, uin
  * used by build_report (kindel.py:450).  out[5][n_slots] int32: consensus_depth, clip_start_depth,
  * clip_end_depth, clip_depth, acgt_depth. */
 int kdl_derive(const int32_t* counts, int64_t n_slots, int32_t* out, void* stream);
+
+/* K4 -- the per-position predicates of the --realign path (reference kindel/kindel.py:182-185,202,243-246,256) for
+ * slots [slot_lo, slot_hi):  flags[s] bit 0 = clip-dominant for right-clipped reads: clip_start_depth /
+ * (sum(weights) + deletions + 1) > 0.5; bit 1 = their clip consensus extends through s: clip_start_depth >
+ * (sum(weights) + deletions) * clip_decay_threshold; bits 2, 3 = the same for left-clipped reads (clip_end_*).
+ * bases[s]: low nibble = consensus()[0] of clip_start_weights[s] (0..4 = A,C,G,T,N), high nibble = of
+ * clip_end_weights[s].  Masking of the contig ends, pairing and the LCS merge stay with the caller. */
+int kdl_cdr_flags(const int32_t* counts, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
+                  double clip_decay_threshold, uint8_t* flags, uint8_t* bases, void* stream);
+
+/* K5 -- the consensus text of every contig from the call bytes (reference kindel/kindel.py:413-424): nothing for a
+ * 'D' call, the base letter (N for an 'N' call or a tie) otherwise, preceded by the insertion string for an 'I'
+ * call.  The strings of the 'I' slots come from the caller (ins_slot ascending, bytes ins_bytes[ins_off[k] ..
+ * ins_off[k+1]) as they are to be printed: the modal inserted string in lower case, or "N" for a tie).
+ * offsets: device uint32[n_slots + 1], out: offsets[s] = where slot s's text starts in `out`, offsets[n_slots] = total;
+ * contig c's sequence is out[offsets[contig_slot[c]] .. offsets[contig_slot[c] + contig_len[c]]).
+ * block_sums: device scratch of kdl_assemble_scratch_words(n_slots) uint32.  out: device bytes, at least
+ * (number of positions + total insertion bytes).  All pointers are device pointers. */
+int64_t kdl_assemble_scratch_words(int64_t n_slots);
+int kdl_assemble(const uint8_t* calls, int64_t n_slots, const int64_t* contig_slot, const int32_t* contig_len,
+                 int32_t n_contigs, const int64_t* ins_slot, const uint32_t* ins_off, const uint8_t* ins_bytes,
+                 int64_t n_ins, uint32_t* block_sums, uint32_t* offsets, uint8_t* out, void* stream);
 
 /* Fused cross-GPU count reduction + vote: sums the 7 vote columns of `n_peers`
  * tables that live on this and on peer GPUs (peer pointers mapped with CUDA IPC / P2P), votes on

@@ -53,6 +53,7 @@ class KdlBatch(C.Structure):
         ("contig_slot", C.c_void_p),
         ("n_complex", C.c_int64),
         ("n_hard", C.c_int64),
+        ("complex_idx", C.c_void_p),
         ("hard_idx", C.c_void_p),
         ("tile_index", C.c_void_p),
     ]
@@ -95,6 +96,10 @@ _PROTOTYPES = {
     "kdl_diagnose": (C.c_int, [C.POINTER(KdlBatch), C.c_void_p, C.c_void_p]),
     "kdl_vote": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "kdl_derive": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "kdl_cdr_flags": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_assemble_scratch_words": (C.c_int64, [C.c_int64]),
+    "kdl_assemble": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdl_vote_peers": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
     "kdl_vote_peers_sparse": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_int32,

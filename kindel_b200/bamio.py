@@ -64,7 +64,7 @@ class ReadBatch:
     cigar: np.ndarray             # uint32 [n_ops] (host only)
     seq4: np.ndarray              # uint32 [words]: per read its bases, complex reads followed by [n_ops][evt_off][ops]
     hard_idx: np.ndarray = field(default=None)      # uint32 [n_hard]: KDL_HARD reads (K1g walks them)
-    complex_idx: np.ndarray = field(default=None)   # uint32 [n_complex] (host only)
+    complex_idx: np.ndarray = field(default=None)   # uint32 [n_complex]: all complex reads (K1e walks the tile-eligible ones)
     n_events: int = 0
     reads_sorted: bool = False
     aligned_bases: int = 0        # sum of M/=/X lengths = sum of the weights table (the metric's unit)
@@ -91,7 +91,7 @@ class ReadBatch:
 
     def input_bytes(self) -> int:
         """Bytes of read data the device consumes (what the e2e path copies host->device)."""
-        arrs = (self.ref_start, self.seq_off, self.l_seq, self.seq4, self.hard_idx, self.contig_len,
+        arrs = (self.ref_start, self.seq_off, self.l_seq, self.seq4, self.complex_idx, self.hard_idx, self.contig_len,
                 self.contig_read_off, self.contig_slot)
         return int(sum(a.nbytes for a in arrs if a is not None))
 
@@ -320,6 +320,34 @@ def merge_batches(batches) -> ReadBatch:
                     cig_off, _ragged_gather(cigar, cig_at[order], nco), bases, n_records=int(order.shape[0]))
 
 
+_SAVE_FIELDS = ("contig_len", "contig_read_off", "contig_slot", "ref_start", "seq_off", "l_seq", "seq_len", "cig_off",
+                "cigar", "seq4", "hard_idx", "complex_idx")
+_SAVE_SCALARS = ("n_slots", "n_events", "reads_sorted", "aligned_bases", "n_records", "max_simple_len", "reach_right",
+                 "reach_left")
+
+
+def save_batch(directory: str, batch: ReadBatch) -> None:
+    """One .npy per array (so that several processes can map them) + a small json."""
+    import json
+
+    os.makedirs(directory, exist_ok=True)
+    for f in _SAVE_FIELDS:
+        np.save(os.path.join(directory, f + ".npy"), np.ascontiguousarray(getattr(batch, f)))
+    meta = {k: (bool(getattr(batch, k)) if k == "reads_sorted" else int(getattr(batch, k))) for k in _SAVE_SCALARS}
+    meta["contig_names"] = list(batch.contig_names)
+    with open(os.path.join(directory, "batch.json"), "w") as fh:
+        json.dump(meta, fh)
+
+
+def load_batch(directory: str, mmap: bool = True) -> ReadBatch:
+    import json
+
+    with open(os.path.join(directory, "batch.json")) as fh:
+        meta = json.load(fh)
+    arrays = {f: np.load(os.path.join(directory, f + ".npy"), mmap_mode="r" if mmap else None) for f in _SAVE_FIELDS}
+    return ReadBatch(contig_names=meta.pop("contig_names"), **arrays, **meta)
+
+
 # --------------------------------------------------------------------------------------- BGZF
 def _bgzf_blocks(data: bytes):
     """Yield (payload_start, payload_end, isize) for each BGZF block; None if not BGZF."""
@@ -394,22 +422,27 @@ def read_bam(path) -> ReadBatch:
     buf = inflate_bam(path)
     if buf[:4].tobytes() != b"BAM\x01":
         raise ValueError("not a BAM file: %s" % path)
-    raw = buf.tobytes() if buf.size < (1 << 20) else None  # header parse only needs the front
-    head = raw if raw is not None else buf[: 1 << 20].tobytes()
-    (l_text,) = struct.unpack_from("<i", head, 4)
-    if 8 + l_text + 4 > len(head):
-        head = buf[: 8 + l_text + (1 << 20)].tobytes()
-    text = head[8:8 + l_text].split(b"\x00", 1)[0].decode("utf-8", "replace")
+    # the binary header is parsed straight out of the inflated buffer (no truncated copy: a reference dictionary
+    # of 10^5 contigs is several MB long)
+    mv = memoryview(buf)
+    if buf.size < 12:
+        raise ValueError("truncated BAM header in %s" % path)
+    (l_text,) = struct.unpack_from("<i", mv, 4)
+    if l_text < 0 or 8 + l_text + 4 > buf.size:
+        raise ValueError("truncated BAM header in %s" % path)
+    text = bytes(mv[8:8 + l_text]).split(b"\x00", 1)[0].decode("utf-8", "replace")
     off = 8 + l_text
-    (n_ref,) = struct.unpack_from("<i", head, off)
+    (n_ref,) = struct.unpack_from("<i", mv, off)
     off += 4
     bin_names, bin_lens = [], []
     for _ in range(n_ref):
-        if off + 4 > len(head):
-            head = buf[: off + (1 << 22)].tobytes()
-        (l_name,) = struct.unpack_from("<i", head, off)
-        name = head[off + 4:off + 4 + l_name - 1].decode()
-        (l_ref,) = struct.unpack_from("<i", head, off + 4 + l_name)
+        if off + 4 > buf.size:
+            raise ValueError("truncated BAM reference dictionary in %s" % path)
+        (l_name,) = struct.unpack_from("<i", mv, off)
+        if l_name < 1 or off + 8 + l_name > buf.size:
+            raise ValueError("truncated BAM reference dictionary in %s" % path)
+        name = bytes(mv[off + 4:off + 4 + l_name - 1]).decode()
+        (l_ref,) = struct.unpack_from("<i", mv, off + 4 + l_name)
         off += 8 + l_name
         bin_names.append(name)
         bin_lens.append(l_ref)

@@ -17,30 +17,30 @@ from . import __version__
 
 
 def consensus(bam_path, realign=False, min_depth=1, min_overlap=7, clip_decay_threshold=0.1, mask_ends=50,
-              trim_ends=False, uppercase=False):
+              trim_ends=False, uppercase=False, gpus=None):
     """Infer consensus sequence(s) from alignment in SAM/BAM format"""
     from . import kindel
 
     res = kindel.bam_to_consensus(bam_path, realign, min_depth, min_overlap, clip_decay_threshold, mask_ends,
-                                  trim_ends, uppercase)
+                                  trim_ends, uppercase, devices=gpus)
     print("\n".join(res.refs_reports.values()), file=sys.stderr)
     for record in res.consensuses:
         print(f">{record.name}")
         print(record.sequence)
 
 
-def weights(bam_path, relative=False, confidence=True, confidence_alpha=0.01):
+def weights(bam_path, relative=False, confidence=True, confidence_alpha=0.01, gpus=None):
     """Returns table of per-site nucleotide frequencies and coverage"""
     from . import kindel
 
-    kindel.weights(bam_path, relative, confidence, confidence_alpha).to_csv(sys.stdout, sep="\t", index=False)
+    kindel.weights(bam_path, relative, confidence, confidence_alpha, devices=gpus).to_csv(sys.stdout, sep="\t", index=False)
 
 
-def features(bam_path):
+def features(bam_path, gpus=None):
     """Returns table of per-site nucleotide frequencies and coverage including indels"""
     from . import kindel
 
-    kindel.features(bam_path).to_csv(sys.stdout, sep="\t", index=False)
+    kindel.features(bam_path, devices=gpus).to_csv(sys.stdout, sep="\t", index=False)
 
 
 def variants(bam_path, abs_threshold=1, rel_threshold=0.01, only_variants=False, absolute=False):
@@ -63,6 +63,12 @@ def version():
     return f"kindel {__version__}"
 
 
+def _add_gpus(p):
+    # extension (not in the reference's CLI): shard the pileup over the GPUs of this node
+    p.add_argument("--gpus", type=int, default=None,
+                   help="number of GPUs of this node to shard the pileup over (default: $KINDEL_GPUS or 1)")
+
+
 def build_parser() -> argparse.ArgumentParser:
     fmt = argparse.ArgumentDefaultsHelpFormatter
     parser = argparse.ArgumentParser(prog="kindel", formatter_class=fmt)
@@ -81,8 +87,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("-t", "--trim-ends", action="store_true",
                    help="trim ambiguous nucleotides (Ns) from sequence ends")
     p.add_argument("-u", "--uppercase", action="store_true", help="close gaps using uppercase alphabet")
+    _add_gpus(p)
     p.set_defaults(func=lambda a: consensus(a.bam_path, a.realign, a.min_depth, a.min_overlap,
-                                            a.clip_decay_threshold, a.mask_ends, a.trim_ends, a.uppercase))
+                                            a.clip_decay_threshold, a.mask_ends, a.trim_ends, a.uppercase, a.gpus))
 
     p = sub.add_parser("weights", help=weights.__doc__, description=weights.__doc__, formatter_class=fmt)
     p.add_argument("bam_path", help="path to SAM/BAM file")
@@ -90,11 +97,13 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("-c", "--confidence", action="store_false", default=True,
                    help="calculate confidence interval for consensus")
     p.add_argument("--confidence-alpha", type=float, default=0.01, help="confidence interval alpha value")
-    p.set_defaults(func=lambda a: weights(a.bam_path, a.relative, a.confidence, a.confidence_alpha))
+    _add_gpus(p)
+    p.set_defaults(func=lambda a: weights(a.bam_path, a.relative, a.confidence, a.confidence_alpha, a.gpus))
 
     p = sub.add_parser("features", help=features.__doc__, description=features.__doc__, formatter_class=fmt)
     p.add_argument("bam_path", help="path to SAM/BAM file")
-    p.set_defaults(func=lambda a: features(a.bam_path))
+    _add_gpus(p)
+    p.set_defaults(func=lambda a: features(a.bam_path, a.gpus))
 
     # `variants` is listed by the reference's README (README.md:106-107) but absent from its code: an extension here
     p = sub.add_parser("variants", help=variants.__doc__, description=variants.__doc__, formatter_class=fmt)

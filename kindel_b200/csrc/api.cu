@@ -10,6 +10,7 @@
 #include "pileup_simple.cu"
 #include "pileup_tile.cu"
 #include "vote.cu"
+#include "assemble.cu"
 
 namespace {
 
@@ -57,13 +58,13 @@ inline int ensure_tile_smem() {
 
 template <int kFlush, bool kCx>
 inline int launch_tile(const kdl_batch& b, int32_t* counts, long long n_slots, long long tile_lo, long long n_tiles,
-                       int split, int32_t* ins_events, cudaStream_t st) {
+                       int split, cudaStream_t st) {
     int rc = ensure_tile_smem<kFlush, kCx>();
     if (rc != KDL_OK) return rc;
     const long long units = n_tiles * split, max_grid = (long long)sm_count() * 2;  // two CTAs per SM, persistent
     const long long grid = units < max_grid ? units : max_grid;
     kdl::pileup_tile_kernel<kFlush, kCx><<<(unsigned)grid, kdl::W_THREADS, sizeof(kdl::TileSmem<kdl::TileCfg<kCx>>), st>>>(
-        b, counts, n_slots, b.tile_index, tile_lo, n_tiles, split, ins_events);
+        b, counts, n_slots, b.tile_index, tile_lo, n_tiles, split);
     return KDL_OK;
 }
 
@@ -78,7 +79,7 @@ int validate_batch(const kdl_batch* b) {
     if (b->n_reads > 0 && (!b->ref_start || !b->seq_off || !b->l_seq || !b->seq4 ||
                            !b->contig_read_off || !b->contig_len || !b->contig_slot))
         return KDL_ERR_INVALID_ARG;
-    if (b->n_hard > 0 && !b->hard_idx) return KDL_ERR_INVALID_ARG;
+    if ((b->n_hard > 0 && !b->hard_idx) || (b->n_complex > 0 && !b->complex_idx)) return KDL_ERR_INVALID_ARG;
     if (b->reach_right < b->max_simple_len || b->reach_left < 0) return KDL_ERR_INVALID_ARG;
     return KDL_OK;
 }
@@ -153,16 +154,21 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             // K1: the tile-owner kernel
             const bool cx = batch->n_complex > batch->n_hard;  // tile-eligible complex reads present
             if (split > 1) {
-                rc = cx ? launch_tile<kdl::F_ATOMIC, true>(*batch, counts, n_slots, tile_lo, n_tiles, split, ins_events, st)
-                        : launch_tile<kdl::F_ATOMIC, false>(*batch, counts, n_slots, tile_lo, n_tiles, split, ins_events, st);
+                rc = cx ? launch_tile<kdl::F_ATOMIC, true>(*batch, counts, n_slots, tile_lo, n_tiles, split, st)
+                        : launch_tile<kdl::F_ATOMIC, false>(*batch, counts, n_slots, tile_lo, n_tiles, split, st);
             } else if (fresh) {
-                rc = cx ? launch_tile<kdl::F_STORE, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st)
-                        : launch_tile<kdl::F_STORE, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st);
+                rc = cx ? launch_tile<kdl::F_STORE, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st)
+                        : launch_tile<kdl::F_STORE, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st);
             } else {
-                rc = cx ? launch_tile<kdl::F_ADD, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st)
-                        : launch_tile<kdl::F_ADD, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, ins_events, st);
+                rc = cx ? launch_tile<kdl::F_ADD, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st)
+                        : launch_tile<kdl::F_ADD, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st);
             }
             if (rc != KDL_OK) return rc;
+            if ((rc = check_launch()) != KDL_OK) return rc;
+        }
+        if (batch->n_complex > batch->n_hard) {  // K1e: insertions / deletions / clips of the tile-eligible complex reads
+            const long long grid = (batch->n_complex + 255) / 256;
+            kdl::pileup_events_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events);
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
         if (batch->n_hard > 0) {  // K1g: the reads that may wrap or raise, atomically, after the tile stores
@@ -284,6 +290,41 @@ int kdl_exchange_vote(const kdl_exchange* x, int64_t n_slots, int64_t min_depth_
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;  // an empty slice still has to take part in the flag protocol
     kdl::vote_exchange_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(e, n_slots, min_depth_ceil, epoch);
+    return check_launch();
+}
+
+int kdl_cdr_flags(const int32_t* counts, int64_t n_slots, int64_t slot_lo, int64_t slot_hi,
+                  double clip_decay_threshold, uint8_t* flags, uint8_t* bases, void* stream) {
+    if (!counts || !flags || !bases || n_slots <= 0 || slot_lo < 0 || slot_hi > n_slots || slot_lo > slot_hi)
+        return KDL_ERR_INVALID_ARG;
+    if (slot_hi == slot_lo) return KDL_OK;
+    const long long grid = (slot_hi - slot_lo + 255) / 256;
+    kdl::cdr_flags_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(counts, n_slots, slot_lo, slot_hi,
+                                                                            clip_decay_threshold, flags, bases);
+    return check_launch();
+}
+
+int64_t kdl_assemble_scratch_words(int64_t n_slots) {
+    return n_slots < 0 ? 0 : (n_slots + 1 + kdl::A_BLOCK - 1) / kdl::A_BLOCK + 1;
+}
+
+int kdl_assemble(const uint8_t* calls, int64_t n_slots, const int64_t* contig_slot, const int32_t* contig_len,
+                 int32_t n_contigs, const int64_t* ins_slot, const uint32_t* ins_off, const uint8_t* ins_bytes,
+                 int64_t n_ins, uint32_t* block_sums, uint32_t* offsets, uint8_t* out, void* stream) {
+    if (!calls || n_slots <= 0 || !contig_slot || !contig_len || n_contigs < 0 || n_ins < 0 || !block_sums || !offsets ||
+        !out || (n_ins > 0 && (!ins_slot || !ins_off || !ins_bytes)))
+        return KDL_ERR_INVALID_ARG;
+    kdl::AssembleArgs a;
+    a.calls = calls; a.n_slots = n_slots; a.contig_slot = contig_slot; a.contig_len = contig_len; a.n_contigs = n_contigs;
+    a.ins_slot = ins_slot; a.ins_off = ins_off; a.ins_bytes = ins_bytes; a.n_ins = n_ins;
+    const long long n_blocks = (n_slots + 1 + kdl::A_BLOCK - 1) / kdl::A_BLOCK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    kdl::assemble_sums_kernel<<<(unsigned)n_blocks, kdl::A_THREADS, 0, st>>>(a, block_sums);
+    if ((rc = check_launch()) != KDL_OK) return rc;
+    kdl::assemble_scan_sums_kernel<<<1, kdl::A_THREADS, 0, st>>>(block_sums, n_blocks);
+    if ((rc = check_launch()) != KDL_OK) return rc;
+    kdl::assemble_scatter_kernel<<<(unsigned)n_blocks, kdl::A_THREADS, 0, st>>>(a, block_sums, offsets, out);
     return check_launch();
 }
 

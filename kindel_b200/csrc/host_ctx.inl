@@ -17,7 +17,7 @@ struct kdl_ctx {
         void* p = nullptr;
         size_t cap = 0;
     };
-    enum { B_REF_START, B_SEQ_OFF, B_L_SEQ, B_SEQ4, B_CREAD_OFF, B_CLEN, B_CSLOT, B_HARD_IDX, B_COUNTS, B_EVENTS,
+    enum { B_REF_START, B_SEQ_OFF, B_L_SEQ, B_SEQ4, B_CREAD_OFF, B_CLEN, B_CSLOT, B_CX_IDX, B_HARD_IDX, B_COUNTS, B_EVENTS,
            B_CALLS, B_FLAG, B_DIAG, B_TILE_IDX, B_N };
     Buf buf[B_N];
 
@@ -80,7 +80,7 @@ void kdl_ctx_destroy(kdl_ctx* c) {
 static int ctx_consensus_enqueued(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t n_events,
                                   int64_t min_depth_ceil, uint8_t* calls_out, int32_t* counts_out,
                                   int32_t* ins_events_out, kdl_diag* diag_out, int32_t* flag_host) {
-    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nh = (size_t)hb->n_hard;
+    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nh = (size_t)hb->n_hard, nx = (size_t)hb->n_complex;
     struct Copy { int which; const void* src; size_t bytes; };
     const Copy copies[] = {
         {kdl_ctx::B_REF_START, hb->ref_start, n * 4},
@@ -90,6 +90,7 @@ static int ctx_consensus_enqueued(kdl_ctx* c, const kdl_batch* hb, int64_t n_slo
         {kdl_ctx::B_CREAD_OFF, hb->contig_read_off, (nc + 1) * 8},
         {kdl_ctx::B_CLEN, hb->contig_len, nc * 4},
         {kdl_ctx::B_CSLOT, hb->contig_slot, nc * 8},
+        {kdl_ctx::B_CX_IDX, hb->complex_idx, nx * 4},
         {kdl_ctx::B_HARD_IDX, hb->hard_idx, nh * 4},
     };
     cudaStream_t st = c->stream;
@@ -109,6 +110,7 @@ static int ctx_consensus_enqueued(kdl_ctx* c, const kdl_batch* hb, int64_t n_slo
     db.contig_read_off = (const int64_t*)c->buf[kdl_ctx::B_CREAD_OFF].p;
     db.contig_len = (const int32_t*)c->buf[kdl_ctx::B_CLEN].p;
     db.contig_slot = (const int64_t*)c->buf[kdl_ctx::B_CSLOT].p;
+    db.complex_idx = nx ? (const uint32_t*)c->buf[kdl_ctx::B_CX_IDX].p : nullptr;
     db.hard_idx = nh ? (const uint32_t*)c->buf[kdl_ctx::B_HARD_IDX].p : nullptr;
     db.tile_index = (n_slots % KDL_TILE) == 0 ? (uint32_t*)c->buf[kdl_ctx::B_TILE_IDX].p : nullptr;
 
@@ -169,11 +171,11 @@ int kdl_ctx_consensus(kdl_ctx* c, const kdl_batch* hb, int64_t n_slots, int64_t 
     if (cudaSetDevice(c->device) != cudaSuccess) return KDL_ERR_CUDA;
     std::memset(diag_out, 0, sizeof(*diag_out));
     diag_out->read = -1;
-    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nh = (size_t)hb->n_hard;
+    const size_t n = (size_t)hb->n_reads, nc = (size_t)hb->n_contigs, nh = (size_t)hb->n_hard, nx = (size_t)hb->n_complex;
     const struct { int which; size_t bytes; } sizes[] = {
         {kdl_ctx::B_REF_START, n * 4}, {kdl_ctx::B_SEQ_OFF, n * 4}, {kdl_ctx::B_L_SEQ, n * 4},
         {kdl_ctx::B_SEQ4, (size_t)hb->seq4_words * 4 + 16}, {kdl_ctx::B_CREAD_OFF, (nc + 1) * 8},
-        {kdl_ctx::B_CLEN, nc * 4}, {kdl_ctx::B_CSLOT, nc * 8}, {kdl_ctx::B_HARD_IDX, nh * 4},
+        {kdl_ctx::B_CLEN, nc * 4}, {kdl_ctx::B_CSLOT, nc * 8}, {kdl_ctx::B_CX_IDX, nx * 4}, {kdl_ctx::B_HARD_IDX, nh * 4},
         {kdl_ctx::B_COUNTS, (size_t)n_slots * KDL_NCOL * 4}, {kdl_ctx::B_EVENTS, (size_t)n_events * 16},
         {kdl_ctx::B_CALLS, (size_t)n_slots}, {kdl_ctx::B_FLAG, 16}, {kdl_ctx::B_DIAG, sizeof(kdl_diag)},
         {kdl_ctx::B_TILE_IDX, (size_t)(n_slots / KDL_TILE + 1) * 32},

@@ -16,12 +16,11 @@
 //     words per lane and read, 7 full adders per 8 reads), and flushes at the end of a tile.  Consumers never
 //     touch global memory except for the table stores and never meet a CTA-wide barrier.
 //   * Complex reads (indels, clips; include/kindel_b200.h) carry their CIGAR behind their bases in seq4, so it
-//     arrives with the bulk copy.  A producer thread walks it ONCE per (read, tile): every M/=/X segment that
-//     overlaps the tile becomes a PIECE (virtual start = slot of the read's base 0, clipped slot range), which
-//     the consumers count with the same bit-sliced adders plus a nibble mask; I / D / clip updates that fall
-//     into the tile are sparse REDs issued by the producer (exactly once: slots are owned by tiles), insertion
-//     events are written to their deterministic rows.  Reads that could wrap a Python index or raise
-//     (KDL_HARD) are left to K1g.
+//     arrives with the bulk copy.  A producer thread tracks the two cursors through it once per (read, tile): every
+//     M/=/X segment that overlaps the tile becomes a PIECE (virtual start = slot of the read's base 0, clipped slot
+//     range), which the consumers count with the same bit-sliced adders plus a nibble mask.  The sparse rest of
+//     such a read -- insertion / deletion / clip updates, insertion events -- is K1e's (pileup_general.cu), once
+//     per read.  Reads that could wrap a Python index or raise (KDL_HARD) are left to K1g.
 //
 // Preconditions (checked by the host side of the ABI): reads_sorted, classification as in include/kindel_b200.h.
 #include "tile_common.cuh"
@@ -45,7 +44,7 @@ template <> struct TileCfg<false> {
 template <> struct TileCfg<true> {
     static constexpr int kRmax = 384;
     static constexpr int kCapW = 7168;   // 28 KB
-    static constexpr int kPcap = 704;
+    static constexpr int kPcap = 768;
 };
 
 enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
@@ -64,7 +63,6 @@ struct TileStage {
     // .w = shift | s0 << 8 | s1 << 20, [s0, s1) the piece's slots clipped to the tile.  px[kPcap] = a piece that
     // covers nothing (what idle lanes of a block read).
     int4 px[C::kPcap + 1];
-    unsigned short cxl[C::kPcap ? C::kRmax : 8];  // kCx: the item's tile-eligible complex reads (indices into the item)
     int gs[C::kRmax + 32];       // start slot relative to the tile (all reads: the array stays sorted)
     int cov[KDL_TILE];           // reads / pieces of THIS item covering each slot
     int diff[KDL_TILE + 32];     // producers only: +1 at a piece's first slot, -1 behind its last
@@ -97,8 +95,7 @@ static_assert(offsetof(TileStage<TileCfg<false>>, diff) % 16 == 0 && sizeof(Tile
 template <int kFlush, bool kCx>
 __global__ void __launch_bounds__(W_THREADS, 2)
 pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
-                   const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles, int split,
-                   int32_t* __restrict__ ins_events) {
+                   const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles, int split) {
     KDL_DYNAMIC_SMEM(smem_raw);
     using C = TileCfg<kCx>;
     using Smem = TileSmem<C>;
@@ -354,19 +351,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             }
                         }
                         st.gs[i] = gs;
-                        const int raddr = (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2));
-                        bool listed = false;
-                        if constexpr (kCx) {
-                            const uint32_t lw = (uint32_t)l[k];
-                            if ((lw & (KDL_COMPLEX | KDL_HARD)) == KDL_COMPLEX) {
-                                // .z = 0 keeps the entry inert in the simple loop; .x / .w carry the read's start, the
-                                // first slot of its pieces, its SEQ length and its M-op count to the exploding warp
-                                st.meta[i + (i >> 3)] = make_int4(gs, raddr, 0, (pre[k] & 0x3FF) | ((int)(lw & KDL_LEN_MASK) << 10));
-                                st.cxl[pre[k] >> 16] = (unsigned short)i;
-                                listed = true;
-                            }
-                        }
-                        if (!listed) st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2, raddr, nb, ((-gs) & 7) << 2);
+                        st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
+                                                          (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
+                                                          ((-gs) & 7) << 2);
                     }
                 }
                 if (ptid < 40) {  // sentinels behind the last read
@@ -382,91 +369,50 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 }
                 if constexpr (kCx) {
                     if (n_cx > 0) {
-                        // ---- explode the complex reads (their CIGARs came with the bulk copy): one WARP per read, one
-                        // LANE per CIGAR op.  The cursors at every op come from two warp scans; M/=/X ops become
-                        // pieces, I / D ops and clip counts are single REDs by their lane, the bases of a clip are
-                        // spread over the lanes.
-                        producer_sync();  // entries and list written
+                        // ---- the M / = / X segments of the complex reads become pieces (their CIGARs came with the
+                        // bulk copy).  One thread per read: it only tracks the two cursors through the ops -- the
+                        // insertion / deletion / clip updates of these reads are K1e's (pileup_general.cu), once per
+                        // read instead of once per tile it touches.
                         mbar_wait(&sm.landed[stage_id], (uint32_t)((item / W_STAGES) & 1));
-                        for (int j = pw; j < n_cx; j += W_PRODUCERS) {
-                            const int i = (int)st.cxl[j];
-                            const int4 en = st.meta[i + (i >> 3)];
-                            const int lseq = (en.w >> 10) & (int)KDL_LEN_MASK;
-                            const int nbw = (lseq + 7) >> 3;
-                            const uint32_t* rw = st.seq + (((uint32_t)en.y - seq_base) >> 2);  // the read's block
+#pragma unroll
+                        for (int k = 0; k < PER; ++k) {
+                            const int i = ptid + k * W_PT;
+                            const uint32_t lw = (uint32_t)l[k];
+                            if (i >= n_sub || (lw & (KDL_COMPLEX | KDL_HARD)) != KDL_COMPLEX) continue;
+                            const int nbw = ((int)(lw & KDL_LEN_MASK) + 7) >> 3;
+                            const uint32_t* rw = st.seq + ((long long)so[k] - wa);  // the read's block in shared memory
+                            const int raddr = (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2));
                             const int n_ops = (int)rw[nbw];
-                            uint32_t evt = rw[nbw + 1];
                             const uint32_t* ops = rw + nbw + 2;
-                            int pos = en.w & 0x3FF;
-                            int r0 = en.x, q0 = 0;
-                            auto nib = [&](int qq) { return (int)((rw[qq >> 3] >> (28 - 4 * (qq & 7))) & 0xFu); };
-                            auto red = [&](int col, int rel) {  // only slots of THIS tile: every slot has one owner
-                                if ((unsigned)rel < (unsigned)KDL_TILE)
-                                    atomicAdd(counts + (long long)col * n_slots + tile_slot + rel, 1);
-                            };
-                            for (int o0 = 0; o0 < n_ops; o0 += 32) {
-                                const int o = o0 + lane;
-                                const uint32_t cg = o < n_ops ? ops[o] : 0xFu;  // 0xF: a zero-length no-op
+                            int pos = pre[k] & 0xFFFF;
+                            const int pend = pos + (int)((lw >> KDL_NM_SHIFT) & KDL_NM_MASK);
+                            int r = gsv[k], q = 0;
+                            for (int o = 0; o < n_ops; ++o) {
+                                const uint32_t cg = ops[o];
                                 const int len = (int)(cg >> 4);
                                 const int op = (int)(cg & 0xF);
-                                const bool is_m = op == 0 || op == 7 || op == 8;
-                                const int radv = (is_m || op == 2 || (op == 4 && o > 0)) ? len : 0;
-                                const int qadv = (is_m || op == 1 || op == 4) ? len : 0;
-                                int ir = radv, iq = qadv;
-#pragma unroll
-                                for (int d = 1; d < 32; d <<= 1) {
-                                    const int a1 = __shfl_up_sync(0xffffffffu, ir, d), a2 = __shfl_up_sync(0xffffffffu, iq, d);
-                                    if (lane >= d) { ir += a1; iq += a2; }
-                                }
-                                const int r = r0 + ir - radv, q = q0 + iq - qadv;  // cursors when this lane's op starts
-                                const unsigned m_mask = __ballot_sync(0xffffffffu, is_m);
-                                const unsigned i_mask = __ballot_sync(0xffffffffu, op == 1);
-                                const unsigned s_mask = __ballot_sync(0xffffffffu, op == 4);
-                                const unsigned lt = (1u << lane) - 1u;
-                                if (is_m) {  // M = X (kindel.py:49-54): a piece, or a slot that covers nothing
+                                if (op == 0 || op == 7 || op == 8) {  // M = X (kindel.py:49-54)
                                     const int s0 = r < 0 ? 0 : r, s1 = r + len > KDL_TILE ? KDL_TILE : r + len;
-                                    int4 pc = make_int4(0x10000000, (int)seq_base, 0, 0);
                                     if (s0 < s1) {
                                         const int v = r - q;  // slot of the read's base 0
                                         atomicAdd(st.diff + s0, 1);
                                         atomicAdd(st.diff + s1, -1);
-                                        pc = make_int4(((v + 7) >> 3) << 2, en.y, nbw << 2, (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
+                                        st.px[pos++] = make_int4(((v + 7) >> 3) << 2, raddr, nbw << 2,
+                                                                 (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
                                     }
-                                    st.px[pos + __popc(m_mask & lt)] = pc;
-                                } else if (op == 1) {  // I (kindel.py:55-58)
-                                    if ((unsigned)r < (unsigned)KDL_TILE) {
-                                        atomicAdd(counts + (long long)KDL_INS * n_slots + tile_slot + r, 1);
-                                        if (ins_events)
-                                            reinterpret_cast<int4*>(ins_events)[evt + __popc(i_mask & lt)] =
-                                                make_int4((int)(tile_slot + r), (int)(c0 + i), q, len);
-                                    }
-                                } else if (op == 2) {  // D (kindel.py:59-62)
-                                    for (int d = 0; d < len; ++d) red(KDL_DEL, r + d);
-                                } else if (op == 4) {  // S: the count of the clip; its bases below
-                                    if (o == 0) red(KDL_CLIP_ENDS, r); else red(KDL_CLIP_STARTS, r - 1);
+                                    r += len;
+                                    q += len;
+                                } else if (op == 1) {  // I
+                                    q += len;
+                                } else if (op == 2) {  // D
+                                    r += len;
+                                } else if (op == 4) {  // S: op #0 is a left clip (query only), any other advances both
+                                    if (o) r += len;
+                                    q += len;
                                 }
                                 // N, H, P: no-op (kindel.py:49-63 has no branch for them)
-                                for (unsigned sm_ = s_mask; sm_; sm_ &= sm_ - 1) {  // clip bases, all lanes on one clip
-                                    const int src = __ffs(sm_) - 1;
-                                    const int sr = __shfl_sync(0xffffffffu, r, src), sq = __shfl_sync(0xffffffffu, q, src);
-                                    const int sl = __shfl_sync(0xffffffffu, len, src);
-                                    if (o0 + src == 0) {  // left clip (kindel.py:64-73): bases end where the read starts
-                                        for (int g = lane; g < sl; g += 32) {
-                                            const int rel = sr - sl + g;
-                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CEW_A + nib2col(nib(g)), rel);
-                                        }
-                                    } else {              // right clip (kindel.py:74-81); never reaches the contig end here
-                                        for (int d = lane; d < sl; d += 32) {
-                                            const int rel = sr + d;
-                                            if ((unsigned)rel < (unsigned)KDL_TILE) red(KDL_CSW_A + nib2col(nib(sq + d)), rel);
-                                        }
-                                    }
-                                }
-                                pos += __popc(m_mask);
-                                evt += (uint32_t)__popc(i_mask);
-                                r0 += __shfl_sync(0xffffffffu, ir, 31);
-                                q0 += __shfl_sync(0xffffffffu, iq, 31);
                             }
+                            while (pos < pend) st.px[pos++] = make_int4(0x10000000, (int)seq_base, 0, 0);  // covers nothing
                         }
                     }
                 }

@@ -24,6 +24,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 
@@ -33,23 +34,11 @@ from . import _ffi, bamio
 select_reads = bamio.select_reads
 
 
-def shard_batch(batch: bamio.ReadBatch, rank: int, world: int) -> bamio.ReadBatch:
-    """Rank's contiguous block of the reads of every contig (order and layout preserved)."""
-    if world == 1:
-        return batch
-    parts = []
-    for c in range(batch.n_contigs):
-        lo, hi = int(batch.contig_read_off[c]), int(batch.contig_read_off[c + 1])
-        parts.append(np.arange(lo + (hi - lo) * rank // world, lo + (hi - lo) * (rank + 1) // world, dtype=np.int64))
-    return select_reads(batch, np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64))
-
-
 def partition_contigs(batch: bamio.ReadBatch, world: int):
     """Contigs are independent units in the reference (kindel/kindel.py:143-151): give every rank a contiguous run
     of whole contigs with about 1/world of the reads (64 contigs -> 8 per rank).  Returns
     [(c_lo, c_hi)] per rank; a rank may get nothing when there are fewer contigs than ranks."""
-    reads = np.diff(batch.contig_read_off).astype(np.int64)
-    cum = np.concatenate(([0], np.cumsum(reads)))
+    cum = np.concatenate(([0], np.cumsum(np.diff(batch.contig_read_off).astype(np.int64))))
     total = int(cum[-1])
     cuts = [0]
     for r in range(1, world):
@@ -62,12 +51,54 @@ def partition_contigs(batch: bamio.ReadBatch, world: int):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def choose_plan(batch: bamio.ReadBatch, world: int) -> str:
+    """"contigs" when there are enough contigs to give every rank whole ones of comparable weight (no slot is then
+    shared between ranks: nothing to reduce), else "reads" (contiguous blocks of every contig's sorted reads)."""
+    if batch.n_contigs < world:
+        return "reads"
+    reads = np.diff(batch.contig_read_off).astype(np.int64)
+    parts = partition_contigs(batch, world)
+    loads = [int(reads[a:b].sum()) for a, b in parts]
+    return "contigs" if min(loads) * 2 >= max(loads) and min(loads) > 0 else "reads"
+
+
+def shard_indices(batch: bamio.ReadBatch, rank: int, world: int, plan: str = "reads") -> np.ndarray:
+    """Global indices of the reads rank `rank` piles (ascending)."""
+    if world == 1:
+        return np.arange(batch.n_reads, dtype=np.int64)
+    if plan == "contigs":
+        c_lo, c_hi = partition_contigs(batch, world)[rank]
+        return np.arange(int(batch.contig_read_off[c_lo]), int(batch.contig_read_off[c_hi]), dtype=np.int64)
+    parts = []
+    for c in range(batch.n_contigs):
+        lo, hi = int(batch.contig_read_off[c]), int(batch.contig_read_off[c + 1])
+        parts.append(np.arange(lo + (hi - lo) * rank // world, lo + (hi - lo) * (rank + 1) // world, dtype=np.int64))
+    return np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+
+
+def shard_batch(batch: bamio.ReadBatch, rank: int, world: int) -> bamio.ReadBatch:
+    """Rank's contiguous block of the reads of every contig (order and layout preserved)."""
+    return batch if world == 1 else select_reads(batch, shard_indices(batch, rank, world, "reads"))
+
+
 def shard_by_contig(batch: bamio.ReadBatch, rank: int, world: int) -> bamio.ReadBatch:
     """Rank's whole contigs (partition_contigs), as a batch over the SAME slot layout: its table is non-zero only
     on the slots of its own contigs, nobody else touches them, no count reduction is needed at all."""
-    c_lo, c_hi = partition_contigs(batch, world)[rank]
-    lo, hi = int(batch.contig_read_off[c_lo]), int(batch.contig_read_off[c_hi])
-    return select_reads(batch, np.arange(lo, hi, dtype=np.int64))
+    return select_reads(batch, shard_indices(batch, rank, world, "contigs"))
+
+
+def merge_events(per_rank_events, per_rank_index) -> np.ndarray:
+    """Insertion events of all shards as ONE list in the reference's iteration order: shard-local read numbers are
+    mapped back to global ones, rows sorted by global read (stable: a read's own events keep their order) -- the
+    rows a single GPU writes at evt_off[read] + k."""
+    rows = []
+    for ev, idx in zip(per_rank_events, per_rank_index):
+        ev = np.asarray(ev, dtype=np.int32).reshape(-1, 4).copy()
+        if ev.shape[0]:
+            ev[:, 1] = np.asarray(idx, dtype=np.int64)[ev[:, 1]]
+        rows.append(ev)
+    allrows = np.concatenate(rows) if rows else np.zeros((0, 4), dtype=np.int32)
+    return allrows[np.argsort(allrows[:, 1], kind="stable")]
 
 
 def footprint(batch: bamio.ReadBatch, align: int = 4):
@@ -345,3 +376,116 @@ class ShardedConsensus:
         if self.tables is not None:
             self.tables.close()
             self.tables = None
+
+
+# ------------------------------------------------------------------------------------------- public entry
+def _free_port() -> int:
+    import socket
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
+def _api_worker(rank: int, world: int, workdir: str, port: int, min_depth, mode: str, plan: str):
+    """One process per GPU: pile this rank's shard, exchange, vote; rank 0 leaves the job's results in workdir."""
+    import json
+    import os
+    import traceback
+
+    import torch
+    import torch.distributed as dist
+
+    from . import engine
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", device_id=dev)
+    sc = None
+    try:
+        batch = bamio.load_batch(os.path.join(workdir, "batch"))
+        idx = shard_indices(batch, rank, world, plan)
+        shard = select_reads(batch, idx)
+        sc = ShardedConsensus(shard, dev, mode=mode)
+        calls = sc.step(min_depth)
+        # data errors: the reference raises at the FIRST offending record in iteration order -- every rank
+        # reports its first one (global read number), the parent re-raises the smallest
+        err = None
+        try:
+            sc.check_errors()
+        except (IndexError, KeyError) as exc:
+            read = getattr(exc, "kdl_read", None)
+            err = {"type": type(exc).__name__, "args": list(exc.args),
+                   "read": int(idx[read]) if read is not None and 0 <= read < idx.shape[0] else int(idx[0]) if idx.size else 0}
+        errs = [None] * world
+        dist.all_gather_object(errs, err)
+        ev_local = sc.dbatch.tensors["_events"][: shard.n_events].cpu().numpy() if shard.n_events else np.zeros((0, 4), np.int32)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((ev_local, idx), gathered, dst=0)
+        table = sc.reduce_table(0)
+        if rank == 0:
+            out = os.path.join(workdir, "out")
+            os.makedirs(out, exist_ok=True)
+            first = min((e for e in errs if e), key=lambda e: e["read"], default=None)
+            with open(os.path.join(out, "status.json"), "w") as fh:
+                json.dump({"error": first}, fh)
+            if first is None:
+                np.save(os.path.join(out, "calls.npy"), calls.cpu().numpy())
+                np.save(os.path.join(out, "events.npy"), merge_events([g[0] for g in gathered], [g[1] for g in gathered]))
+                np.save(os.path.join(out, "counts.npy"), table.cpu().numpy())
+                np.save(os.path.join(out, "derived.npy"), engine.derive(table).cpu().numpy())
+        dist.barrier()
+    except Exception:  # noqa: BLE001  -- leave a trace for the parent, then fail the process
+        with open(os.path.join(workdir, "rank%d.err" % rank), "w") as fh:
+            fh.write(traceback.format_exc())
+        raise
+    finally:
+        if sc is not None:
+            sc.close()
+        dist.destroy_process_group()
+
+
+def run_sharded(batch: bamio.ReadBatch, devices: int, min_depth=1, mode: str = "fused", plan: str = None):
+    """Pileup + vote of `batch` over `devices` GPUs of this node: one process per GPU (torch.distributed, NCCL for
+    the plumbing, the fused peer-memory exchange on the data path), whole contigs per rank when there are enough
+    of them, else contiguous blocks of every contig's sorted reads.  Returns (calls uint8[n_slots], counts
+    int32[19, n_slots], derived int32[5, n_slots], events int32[n_events, 4]) in host memory -- bit-identical to
+    one GPU -- or raises the reference's IndexError / KeyError."""
+    import json
+    import shutil
+    import tempfile
+
+    import torch
+    import torch.multiprocessing as mp
+
+    from . import engine
+
+    engine.require_cuda()
+    n_gpu = torch.cuda.device_count()
+    if devices < 1 or devices > n_gpu:
+        raise ValueError("devices=%d but this node has %d GPU(s)" % (devices, n_gpu))
+    plan = plan or choose_plan(batch, devices)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    workdir = tempfile.mkdtemp(prefix="kindel_b200_", dir=base)
+    try:
+        bamio.save_batch(os.path.join(workdir, "batch"), batch)
+        try:
+            mp.spawn(_api_worker, args=(devices, workdir, _free_port(), min_depth, mode, plan), nprocs=devices, join=True)
+        except Exception as exc:
+            notes = []
+            for r in range(devices):
+                pth = os.path.join(workdir, "rank%d.err" % r)
+                if os.path.exists(pth):
+                    with open(pth) as fh:
+                        notes.append("rank %d:\n%s" % (r, fh.read()))
+            raise RuntimeError("sharded pileup failed\n" + "\n".join(notes)) from exc
+        out = os.path.join(workdir, "out")
+        with open(os.path.join(out, "status.json")) as fh:
+            err = json.load(fh)["error"]
+        if err:
+            raise (KeyError if err["type"] == "KeyError" else IndexError)(*err["args"])
+        return tuple(np.load(os.path.join(out, f + ".npy")) for f in ("calls", "counts", "derived", "events"))
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)

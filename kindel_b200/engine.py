@@ -67,12 +67,14 @@ def make_struct(host: ReadBatch, ptr: dict) -> _ffi.KdlBatch:
     s.contig_slot = ptr["contig_slot"]
     s.n_complex = host.n_complex
     s.n_hard = host.n_hard
+    s.complex_idx = ptr["complex_idx"] if host.n_complex else None
     s.hard_idx = ptr["hard_idx"] if host.n_hard else None
     s.tile_index = ptr.get("tile_index")
     return s
 
 
-_FIELDS = ("ref_start", "seq_off", "l_seq", "seq4", "contig_read_off", "contig_len", "contig_slot", "hard_idx")
+_FIELDS = ("ref_start", "seq_off", "l_seq", "seq4", "contig_read_off", "contig_len", "contig_slot", "complex_idx",
+           "hard_idx")
 
 
 def host_struct(host: ReadBatch):
@@ -99,9 +101,12 @@ def upload(host: ReadBatch, device=None, non_blocking: bool = False) -> DeviceBa
 
 def raise_like_reference(status: int, read: int, nibble: int, op_index: int):
     if status == _ffi.KDL_ERR_KEY:
-        raise KeyError(NIBBLES[nibble])  # e.g. KeyError('R'): kindel.py:52,72,79
-    raise IndexError("list index out of range (read %d, CIGAR op %d walks off its contig or its SEQ)"
-                     % (read, op_index))
+        exc = KeyError(NIBBLES[nibble])  # e.g. KeyError('R'): kindel.py:52,72,79
+    else:
+        exc = IndexError("list index out of range (read %d, CIGAR op %d walks off its contig or its SEQ)"
+                         % (read, op_index))
+    exc.kdl_read = int(read)  # which read of the batch raised (the sharded driver orders errors by it)
+    raise exc
 
 
 class CountTable:
@@ -208,6 +213,58 @@ def derive(counts: torch.Tensor) -> torch.Tensor:
         rc = lib.kdl_derive(counts.data_ptr(), n_slots, out.data_ptr(), _stream_ptr(dev))
         _ffi.check(rc, "kdl_derive")
     return out
+
+
+def cdr_flags(counts: torch.Tensor, slot_lo: int, slot_hi: int, clip_decay_threshold: float):
+    """K4: (flags uint8[slot_hi - slot_lo], bases uint8[...]) on the host for slots [slot_lo, slot_hi): the
+    --realign predicates (kindel.py:182-185,202,243-246,256), 2 bytes per slot instead of the 76-byte table row."""
+    lib = _ffi.load()
+    dev = counts.device
+    n_slots = counts.shape[1]
+    with torch.cuda.device(dev):
+        flags = torch.empty(n_slots, dtype=torch.uint8, device=dev)
+        bases = torch.empty(n_slots, dtype=torch.uint8, device=dev)
+        rc = lib.kdl_cdr_flags(counts.data_ptr(), n_slots, int(slot_lo), int(slot_hi), float(clip_decay_threshold),
+                               flags.data_ptr(), bases.data_ptr(), _stream_ptr(dev))
+        _ffi.check(rc, "kdl_cdr_flags")
+    return flags[slot_lo:slot_hi].cpu().numpy(), bases[slot_lo:slot_hi].cpu().numpy()
+
+
+def assemble(calls: torch.Tensor, host: ReadBatch, ins_slots: np.ndarray, ins_strings):
+    """K5: consensus text of every contig from the device call bytes.  ins_slots (ascending) / ins_strings: the
+    chosen insertion string of every slot whose call carries change 'I'.  Returns a list of str, one per contig."""
+    lib = _ffi.load()
+    dev = calls.device
+    n_slots = int(calls.shape[0])
+    enc = [x.encode("ascii") for x in ins_strings]
+    ins_off = np.zeros(len(enc) + 1, dtype=np.uint32)
+    if enc:
+        ins_off[1:] = np.cumsum([len(x) for x in enc])
+    blob = np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8)
+    with torch.cuda.device(dev):
+        def put(a):
+            a = np.ascontiguousarray(a)
+            return torch.from_numpy(a.view(np.int32) if a.dtype == np.uint32 else a).to(dev)
+
+        t_slot = put(np.asarray(host.contig_slot, dtype=np.int64))
+        t_len = put(np.asarray(host.contig_len, dtype=np.int32))
+        t_is = put(np.asarray(ins_slots, dtype=np.int64) if len(enc) else np.zeros(1, dtype=np.int64))
+        t_io = put(ins_off)
+        t_ib = put(blob.copy())
+        sums = torch.empty(int(lib.kdl_assemble_scratch_words(n_slots)), dtype=torch.int32, device=dev)
+        offsets = torch.empty(n_slots + 1, dtype=torch.int32, device=dev)
+        out = torch.empty(n_slots + int(ins_off[-1]) + 16, dtype=torch.uint8, device=dev)
+        rc = lib.kdl_assemble(calls.data_ptr(), n_slots, t_slot.data_ptr(), t_len.data_ptr(), host.n_contigs,
+                              t_is.data_ptr(), t_io.data_ptr(), t_ib.data_ptr(), len(enc), sums.data_ptr(),
+                              offsets.data_ptr(), out.data_ptr(), _stream_ptr(dev))
+        _ffi.check(rc, "kdl_assemble")
+        starts = torch.from_numpy(np.asarray(host.contig_slot, dtype=np.int64)).to(dev)
+        ends = starts + torch.from_numpy(np.asarray(host.contig_len, dtype=np.int64)).to(dev)
+        lo = offsets[starts].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        hi = offsets[ends].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+        total = int(offsets[n_slots].item()) & 0xFFFFFFFF
+        text = out[:total].cpu().numpy().tobytes()
+    return [text[a:b].decode("ascii") for a, b in zip(lo.tolist(), hi.tolist())]
 
 
 class HostContext:

@@ -52,6 +52,7 @@ class PileupRun:
         self.batch = batch
         self.dbatch = engine.upload(batch, device)
         self.counts, self.events = engine.pileup(self.dbatch)
+        self.calls_device = None
         self._host_counts = None
         self._host_derived = None
         self._ins = None
@@ -61,15 +62,16 @@ class PileupRun:
         """Wrap tables that already sit in host memory (results copied back by another path, e.g.
         the kdl_ctx_* host-buffer call or a multi-GPU reduction).  Does no computation."""
         run = cls.__new__(cls)
-        run.batch, run.dbatch, run.counts, run.events = batch, None, None, None
+        run.batch, run.dbatch, run.counts, run.events, run.calls_device = batch, None, None, None, None
         run._host_counts = np.ascontiguousarray(counts, dtype=np.int32)
         run._host_derived = np.ascontiguousarray(derived, dtype=np.int32)
         run._ins = InsertionTable(batch, events)
         return run
 
     def vote(self, min_depth=1) -> np.ndarray:
-        """K2 over the whole table -> call bytes on the host."""
-        return engine.vote(self.counts, min_depth).cpu().numpy()
+        """K2 over the whole table -> call bytes on the host (the device copy is kept for K5)."""
+        self.calls_device = engine.vote(self.counts, min_depth)
+        return self.calls_device.cpu().numpy()
 
     @property
     def ins_table(self) -> InsertionTable:
@@ -137,10 +139,32 @@ def parse_records(ref_id, ref_len, records):
     return PileupRun(flatten_records(ref_id, ref_len, records)).alignment(0)
 
 
-def parse_bam(bam_path):
+def _default_devices(devices):
+    """`devices` = number of GPUs of this node to shard the pileup over (None: $KINDEL_GPUS, else 1)."""
+    if devices is None:
+        devices = int(os.environ.get("KINDEL_GPUS", "1") or 1)
+    return max(1, int(devices))
+
+
+def pileup_run(bam_path, devices=None, min_depth=1):
+    """(PileupRun, calls) of an alignment file on `devices` GPUs.  devices > 1: one process per GPU, reads (or whole
+    contigs) sharded, counts exchanged over NVLink in front of the vote (distributed.run_sharded); the result is
+    bit-identical to one GPU."""
+    batch = bamio.read_alignment(bam_path)
+    devices = _default_devices(devices)
+    if devices <= 1:
+        run = PileupRun(batch)
+        return run, None
+    from . import distributed
+
+    calls, counts, derived, events = distributed.run_sharded(batch, devices, min_depth)
+    return PileupRun.from_host_tables(batch, counts, derived, events), calls
+
+
+def parse_bam(bam_path, devices=None):
     """Alignment information for each reference sequence, first-seen order
-    (reference kindel/kindel.py:131-153)."""
-    return PileupRun(bamio.read_alignment(bam_path)).alignments()
+    (reference kindel/kindel.py:131-153).  devices: extension, see pileup_run."""
+    return pileup_run(bam_path, devices)[0].alignments()
 
 
 # --------------------------------------------------------------------------------- consensus
@@ -296,11 +320,8 @@ def _cdr_inputs(weights, deletions, clip_weights, clip_depth, clip_decay_thresho
     return n, dominant, extend, bases
 
 
-def cdr_start_consensuses(weights, deletions, clip_start_weights, clip_start_depth, clip_decay_threshold,
-                          mask_ends):
-    """Right-clipped (->) consensuses of clip-dominant regions (reference kindel/kindel.py:156-213)."""
-    n, dominant, extend, bases = _cdr_inputs(weights, deletions, clip_start_weights, clip_start_depth,
-                                             clip_decay_threshold, mask_ends)
+def _start_regions(n, dominant, extend, bases):
+    """-> regions from the per-position predicates (reference kindel/kindel.py:156-213)."""
     stops = np.flatnonzero(~extend)
     regions = []
     for pos in np.flatnonzero(dominant).tolist():
@@ -313,14 +334,12 @@ def cdr_start_consensuses(weights, deletions, clip_start_weights, clip_start_dep
         else:  # ran to the contig end without decaying
             end = n - 1
             seq_end = n
-        regions.append(Region(pos, end, bases[pos:seq_end].tobytes().decode("ascii"), "→"))
+        regions.append(Region(pos, end, bases[pos:seq_end].tobytes().decode("ascii"), "\u2192"))
     return regions
 
 
-def cdr_end_consensuses(weights, deletions, clip_end_weights, clip_end_depth, clip_decay_threshold, mask_ends):
-    """Left-clipped (<-) consensuses of clip-dominant regions (reference kindel/kindel.py:216-275)."""
-    n, dominant, extend, bases = _cdr_inputs(weights, deletions, clip_end_weights, clip_end_depth,
-                                             clip_decay_threshold, mask_ends)
+def _end_regions(n, dominant, extend, bases):
+    """<- regions from the per-position predicates (reference kindel/kindel.py:216-275)."""
     stops = np.flatnonzero(~extend)
     regions = []
     for pos in np.flatnonzero(dominant)[::-1].tolist():
@@ -336,8 +355,43 @@ def cdr_end_consensuses(weights, deletions, clip_end_weights, clip_end_depth, cl
         else:
             start = 0
             seq = bases[0:pos + 1].tobytes().decode("ascii")
-        regions.append(Region(start, pos + 1, seq, "←"))
+        regions.append(Region(start, pos + 1, seq, "\u2190"))
     return regions
+
+
+def cdr_start_consensuses(weights, deletions, clip_start_weights, clip_start_depth, clip_decay_threshold,
+                          mask_ends):
+    """Right-clipped (->) consensuses of clip-dominant regions (reference kindel/kindel.py:156-213)."""
+    return _start_regions(*_cdr_inputs(weights, deletions, clip_start_weights, clip_start_depth, clip_decay_threshold,
+                                       mask_ends))
+
+
+def cdr_end_consensuses(weights, deletions, clip_end_weights, clip_end_depth, clip_decay_threshold, mask_ends):
+    """Left-clipped (<-) consensuses of clip-dominant regions (reference kindel/kindel.py:216-275)."""
+    return _end_regions(*_cdr_inputs(weights, deletions, clip_end_weights, clip_end_depth, clip_decay_threshold,
+                                     mask_ends))
+
+
+def _pair_regions(fwd, rev):
+    pairs = []
+    for f in fwd:
+        for r in rev:
+            if max(f.start, r.start) < min(f.end, r.end):
+                pairs.append((f, r))
+                break
+    return pairs
+
+
+def cdrps_from_device(counts, s, e, clip_decay_threshold, mask_ends):
+    """cdrp_consensuses for the contig at slots [s, e) straight from the device table: K4 evaluates the
+    clip-dominance and decay predicates and the clip consensus bases per position (2 bytes per position come
+    back instead of the 76-byte table row); regions, pairing and merging are the same host code."""
+    n = e - s
+    flags, bases = engine.cdr_flags(counts, s, e, clip_decay_threshold)
+    keep = ~_masked(n, mask_ends)
+    fwd = _start_regions(n, ((flags & 1) != 0) & keep, (flags & 2) != 0, _BASE_CHARS[bases & 7])
+    rev = _end_regions(n, ((flags & 4) != 0) & keep, (flags & 8) != 0, _BASE_CHARS[(bases >> 4) & 7])
+    return _pair_regions(fwd, rev)
 
 
 def cdrp_consensuses(weights, deletions, clip_start_weights, clip_end_weights, clip_start_depth, clip_end_depth,
@@ -347,13 +401,7 @@ def cdrp_consensuses(weights, deletions, clip_start_weights, clip_end_weights, c
                                 mask_ends)
     rev = cdr_end_consensuses(weights, deletions, clip_end_weights, clip_end_depth, clip_decay_threshold,
                               mask_ends)
-    pairs = []
-    for f in fwd:
-        for r in rev:
-            if max(f.start, r.start) < min(f.end, r.end):
-                pairs.append((f, r))
-                break
-    return pairs
+    return _pair_regions(fwd, rev)
 
 
 def merge_by_lcs(s1, s2, min_overlap):
@@ -434,15 +482,43 @@ def build_report(ref_id, weights, changes, cdr_patches, bam_path, realign, min_d
 
 # --------------------------------------------------------------------------------- public API
 def bam_to_consensus(bam_path, realign=False, min_depth=1, min_overlap=9, clip_decay_threshold=0.1,
-                     mask_ends=50, trim_ends=False, uppercase=False):
+                     mask_ends=50, trim_ends=False, uppercase=False, devices=None):
     """Consensus sequence(s) of an alignment file (reference kindel/kindel.py:488-555).
 
     Device work per file: one pileup (K1) and one vote (K2) over all contigs at once; only the
     call bytes, the insertion events and -- for --realign and the report -- count columns come
-    back to the host."""
-    run = PileupRun(bamio.read_alignment(bam_path))
-    return consensus_from_run(run, run.vote(min_depth), bam_path, realign, min_depth, min_overlap,
+    back to the host.  `devices` (extension; default $KINDEL_GPUS or 1) shards the pileup over that many GPUs of
+    the node."""
+    run, calls = pileup_run(bam_path, devices, min_depth)
+    if calls is None:
+        calls = run.vote(min_depth)
+    return consensus_from_run(run, calls, bam_path, realign, min_depth, min_overlap,
                               clip_decay_threshold, mask_ends, trim_ends, uppercase)
+
+
+def _changes_list(calls):
+    """Per-position change codes (None / 'D' / 'N' / 'I') of one contig's call bytes."""
+    change = (calls >> 4) & 3
+    out = [None] * calls.shape[0]
+    for k in np.flatnonzero(change).tolist():
+        out[k] = _CHANGE_LUT[change[k]]
+    return out
+
+
+def _device_texts(run, calls_all):
+    """K5: the consensus text of every contig assembled on the device (emitted-length scan + scatter); only the
+    insertion strings of the 'I' sites are resolved on the host (from the event list) and handed over."""
+    batch = run.batch
+    is_ins = ((calls_all >> 4) & 3) == 3
+    slots = np.flatnonzero(is_ins)
+    if slots.size:  # positions only: the extra slot behind a contig never emits (kindel.py:390 loops over weights)
+        c = np.searchsorted(batch.contig_slot, slots, side="right") - 1
+        slots = slots[slots < batch.contig_slot[c] + batch.contig_len[c].astype(np.int64)]
+    strings = []
+    for sl in slots.tolist():
+        text, tie = run.ins_table.consensus_at(sl)
+        strings.append("N" if tie else text.lower())
+    return engine.assemble(run.calls_device, batch, slots, strings)
 
 
 def consensus_from_run(run, calls_all, bam_path, realign=False, min_depth=1, min_overlap=9,
@@ -450,24 +526,36 @@ def consensus_from_run(run, calls_all, bam_path, realign=False, min_depth=1, min
     """Host half of bam_to_consensus: per contig, optional CDR patches, string assembly, report."""
     ins_table = run.ins_table
     consensuses, refs_changes, refs_reports = [], {}, {}
+    on_device = run.counts is not None
+    texts = _device_texts(run, calls_all) if (on_device and not realign and run.calls_device is not None) else None
     for c, ref_id in enumerate(run.batch.contig_names):
         s, e = run.contig_slice(c)
-        if realign or run.counts is None:
-            aln = run.alignment(c)  # host copy of the table: the CDR code walks it
-            report_weights = aln.weights
-        else:
-            # plain consensus needs only the call bytes, the insertion events and, for the report, the
-            # min / max ACGT depth -- reduced on the device instead of copying 76 B per position back
+        if on_device:
+            # the call bytes, the insertion events and, for the report, the min / max ACGT depth are all that is
+            # needed: reduced on the device instead of copying 76 B per position back
             d = run.counts[0:4, s:e - 1].sum(dim=0)
             report_weights = DepthRange(int(d.min().item()), int(d.max().item())) if e - 1 > s else DepthRange(0, 0)
+        else:
+            aln = run.alignment(c)  # host tables (another path produced them)
+            report_weights = aln.weights
         if realign:
-            cdrps = cdrp_consensuses(aln.weights, aln.deletions, aln.clip_start_weights, aln.clip_end_weights,
-                                     aln.clip_start_depth, aln.clip_end_depth, clip_decay_threshold, mask_ends)
+            if on_device:
+                cdrps = cdrps_from_device(run.counts, s, e - 1, clip_decay_threshold, mask_ends)
+            else:
+                cdrps = cdrp_consensuses(aln.weights, aln.deletions, aln.clip_start_weights, aln.clip_end_weights,
+                                         aln.clip_start_depth, aln.clip_end_depth, clip_decay_threshold, mask_ends)
             cdr_patches = merge_cdrps(cdrps, min_overlap)
         else:
             cdr_patches = None
-        cons, changes = assemble_consensus(calls_all[s:e - 1], lambda p, s=s: ins_table.consensus_at(s + p),
-                                           cdr_patches, trim_ends, uppercase)
+        if texts is not None:
+            cons, changes = texts[c], _changes_list(calls_all[s:e - 1])
+            if trim_ends:
+                cons = cons.strip("N")
+            if uppercase:
+                cons = cons.upper()
+        else:
+            cons, changes = assemble_consensus(calls_all[s:e - 1], lambda p, s=s: ins_table.consensus_at(s + p),
+                                               cdr_patches, trim_ends, uppercase)
         report = build_report(ref_id, report_weights, changes, cdr_patches, bam_path, realign, min_depth,
                               min_overlap, clip_decay_threshold, trim_ends, uppercase)
         consensuses.append(consensus_seqrecord(cons, ref_id))
@@ -477,11 +565,12 @@ def consensus_from_run(run, calls_all, bam_path, realign=False, min_depth=1, min
 
 
 def weights(bam_path: "path to SAM/BAM file", relative: "output relative nucleotide frequencies" = False,
-            confidence: "calculate confidence interval" = True, confidence_alpha: "confidence interval alpha" = 0.01):
+            confidence: "calculate confidence interval" = True, confidence_alpha: "confidence interval alpha" = 0.01,
+            devices=None):
     """DataFrame of per-site nucleotide frequencies, depth, consensus, clip starts/ends, confidence
     interval and entropy (reference kindel/kindel.py:558-630).  Integer columns come from the GPU
-    table; the float tail is the reference's arithmetic, vectorised."""
-    return weights_from_run(PileupRun(bamio.read_alignment(bam_path)), relative, confidence, confidence_alpha)
+    table; the float tail is the reference's arithmetic, vectorised.  devices: extension, see pileup_run."""
+    return weights_from_run(pileup_run(bam_path, devices)[0], relative, confidence, confidence_alpha)
 
 
 def weights_from_run(run, relative=False, confidence=True, confidence_alpha=0.01):
@@ -529,7 +618,7 @@ def weights_from_run(run, relative=False, confidence=True, confidence_alpha=0.01
 def variants(bam_path: "path to SAM/BAM file", abs_threshold: "absolute frequency above which to call variants" = 1,
              rel_threshold: "relative frequency (0.0-1.0) above which to call variants" = 0.01,
              only_variants: "exclude invariant sites from output" = False,
-             absolute: "report absolute variant frequencies" = False):
+             absolute: "report absolute variant frequencies" = False, devices=None):
     """EXTENSION -- not in the reference snapshot.  The reference's README (README.md:106-107) lists a `variants`
     sub-command ("Output variants exceeding specified absolute and relative frequency thresholds") but its code
     (kindel/kindel.py, kindel/cli.py) has no such function, so there is nothing to be bit-exact with: parity
@@ -538,8 +627,7 @@ def variants(bam_path: "path to SAM/BAM file", abs_threshold: "absolute frequenc
     exceeds `abs_threshold` AND whose share of the depth (A+C+G+T+N+deletions, as in `weights`) exceeds
     `rel_threshold`.  Columns: chrom, pos, depth, consensus (allele letter, `-` = deletion), then one column per
     allele holding its relative (default) or absolute frequency where it is a variant and 0 elsewhere."""
-    return variants_from_run(PileupRun(bamio.read_alignment(bam_path)), abs_threshold, rel_threshold, only_variants,
-                             absolute)
+    return variants_from_run(pileup_run(bam_path, devices)[0], abs_threshold, rel_threshold, only_variants, absolute)
 
 
 def variants_from_run(run, abs_threshold=1, rel_threshold=0.01, only_variants=False, absolute=False):
@@ -571,11 +659,12 @@ def variants_from_run(run, abs_threshold=1, rel_threshold=0.01, only_variants=Fa
     return pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=cols)
 
 
-def features(bam_path: "path to SAM/BAM file"):
+def features(bam_path: "path to SAM/BAM file", devices=None):
     """DataFrame of relative per-site nucleotide frequencies, indels and entropy
     (reference kindel/kindel.py:633-664), including its indexing of `i`/`d` by global row number
-    into the LAST contig's tables (IndexError on most multi-contig files)."""
-    return features_from_run(PileupRun(bamio.read_alignment(bam_path)))
+    into the LAST contig's tables (IndexError on most multi-contig files).
+    devices: extension, see pileup_run."""
+    return features_from_run(pileup_run(bam_path, devices)[0])
 
 
 def features_from_run(run):

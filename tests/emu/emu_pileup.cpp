@@ -38,13 +38,16 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
     const char* err = emu::launch(idx_grid, 256, [&] { kdl::tile_index_kernel(b, tile_lo, n_tiles, tile_index); });
     if (!err) {
         err = emu::launch((unsigned)grid, (unsigned)kdl::W_THREADS, [&] {
-#define KDL_EMU_TILE(M, X) kdl::pileup_tile_kernel<M, X>(b, counts, n_slots, tile_index, tile_lo, n_tiles, split, ins_events)
+#define KDL_EMU_TILE(M, X) kdl::pileup_tile_kernel<M, X>(b, counts, n_slots, tile_index, tile_lo, n_tiles, split)
             if (mode == 0) { if (cx) KDL_EMU_TILE(kdl::F_STORE, true); else KDL_EMU_TILE(kdl::F_STORE, false); }
             else if (mode == 1) { if (cx) KDL_EMU_TILE(kdl::F_ADD, true); else KDL_EMU_TILE(kdl::F_ADD, false); }
             else { if (cx) KDL_EMU_TILE(kdl::F_ATOMIC, true); else KDL_EMU_TILE(kdl::F_ATOMIC, false); }
 #undef KDL_EMU_TILE
         });
     }
+    if (!err && b.n_complex > b.n_hard)  // K1e: the sparse updates of the tile-eligible complex reads
+        err = emu::launch((unsigned)((b.n_complex + 255) / 256), 256,
+                          [&] { kdl::pileup_events_kernel(b, counts, n_slots, ins_events); });
     if (err) {
         snprintf(g_error, sizeof g_error, "%s", err);
         return 1;

@@ -37,8 +37,8 @@ def test_abi_version_and_status_strings():
 def test_struct_layouts_match_the_header():
     from kindel_b200 import _ffi
 
-    # kdl_batch: 2 x i64, 4 ptr, 6 x i32, 3 ptr, 2 x i64, 2 ptr
-    assert ctypes.sizeof(_ffi.KdlBatch) == 8 * (2 + 4 + 3 + 3 + 2 + 2)
+    # kdl_batch: 2 x i64, 4 ptr, 6 x i32, 3 ptr, 2 x i64, 3 ptr
+    assert ctypes.sizeof(_ffi.KdlBatch) == 8 * (2 + 4 + 3 + 3 + 2 + 3)
     assert ctypes.sizeof(_ffi.KdlDiag) == 24
 
 

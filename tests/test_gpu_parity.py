@@ -256,6 +256,46 @@ def test_multi_gpu_exchange_modes_match_one_gpu():
     assert "dist parity ok" in res.stdout
 
 
+def test_public_api_on_two_gpus(manifest, tmp_path):
+    """bam_to_consensus / weights / parse_bam with devices=2 (one process per GPU, reads or whole contigs sharded,
+    counts exchanged over NVLink) == devices=1, which the golden tests pin to the reference; including --realign
+    (needs the reduced 19-column table), a multi-contig file (contig partition) and the exception path."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under gpurun --gpus 2)")
+    import pandas as pd
+
+    from kindel_b200 import bamio, synth
+    from kindel_b200 import kindel as K
+
+    paths = [golden_input(manifest["files"][k]) for k in ("bwa_1_1", "mm2_multi", "ext_3_bc75") if k in manifest["files"]]
+    multi = tmp_path / "multi.bam"
+    contigs, recs = synth.to_records(synth.mixed_reads(41, [3000, 5000, 2500, 4000], 30, 0.3))
+    bamio.write_bam(multi, contigs, recs)
+    paths.append(str(multi))
+    for path in paths:
+        for realign in (False, True):
+            one = K.bam_to_consensus(path, realign=realign, min_depth=2)
+            two = K.bam_to_consensus(path, realign=realign, min_depth=2, devices=2)
+            assert [r.sequence for r in one.consensuses] == [r.sequence for r in two.consensuses], (path, realign)
+            assert one.refs_changes == two.refs_changes and one.refs_reports == two.refs_reports
+        pd.testing.assert_frame_equal(K.weights(path), K.weights(path, devices=2), check_exact=True)
+        a1, a2 = K.parse_bam(path), K.parse_bam(path, devices=2)
+        assert list(a1) == list(a2)
+        for k in a1:
+            np.testing.assert_array_equal(a1[k].table, a2[k].table)
+            nz = np.flatnonzero(a1[k].table[6])
+            assert all(list(a1[k].insertions[int(i)].items()) == list(a2[k].insertions[int(i)].items()) for i in nz)
+    # a read that walks off its contig: IndexError on one GPU and on two
+    bad = tmp_path / "bad.sam"
+    bad.write_text("@SQ\tSN:c\tLN:100\n" + "".join("r%d\t0\tc\t%d\t60\t50M\t*\t0\t0\t%s\t*\n" % (k, p, "ACGTA" * 10)
+                                                     for k, p in enumerate([1, 10, 40, 80, 90])))
+    for dv in (1, 2):
+        with pytest.raises(IndexError):
+            K.bam_to_consensus(str(bad), devices=dv)
+
+
 def test_count_table_reuse_without_memset():
     """CountTable: a reused table is never memset; kernels overwrite the weights and zero the other
     columns only when an earlier pileup dirtied them.  Every result must equal a fresh oracle run."""

@@ -250,3 +250,18 @@ def test_variants_extension(tmp_path):
     assert K.variants_from_run(run, rel_threshold=0.2, only_variants=True)["pos"].tolist() == [4]
     a = cli.build_parser().parse_args(["variants", "-a", "2", "-r", "0.1", "-o", "--absolute", "x.bam"])
     assert (a.abs_threshold, a.rel_threshold, a.only_variants, a.absolute) == (2, 0.1, True, True)
+
+
+def test_bam_with_a_long_reference_dictionary(tmp_path):
+    """A draft-assembly / metagenome style header: tens of thousands of contigs, several MB of binary dictionary
+    (read_bam used to parse it from a truncated copy of the buffer's front)."""
+    from kindel_b200 import bamio
+
+    n = 60_000
+    contigs = [("contig_%06d_with_a_rather_long_descriptive_name_%s" % (k, "x" * (k % 37)), 1000 + k % 50) for k in range(n)]
+    recs = [(k, 5, 0, [(20 << 4)], "ACGTACGTACGTACGTACGT") for k in (0, 17, n // 2, n - 1)]
+    path = tmp_path / "many.bam"
+    bamio.write_bam(path, contigs, recs, level=1)
+    b = bamio.read_alignment(path)
+    assert b.n_reads == 4 and b.contig_names == [contigs[k][0] for k in (0, 17, n // 2, n - 1)]
+    assert list(b.contig_len) == [contigs[k][1] for k in (0, 17, n // 2, n - 1)]

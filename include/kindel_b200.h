@@ -279,19 +279,31 @@ int kdl_ctx_consensus(kdl_ctx* ctx, const kdl_batch* batch, int64_t n_slots, int
 /* device time (ms) of the last kdl_ctx_consensus call, H2D / kernels / D2H, from CUDA events */
 int kdl_ctx_last_timing(kdl_ctx* ctx, float* h2d_ms, float* kernel_ms, float* d2h_ms);
 
-/* ---- host-side BAM record gather (no GPU involved; kindel_b200/csrc/bam_host.cpp) ----
- * Replaces the simplesam -> `samtools view` text round trip of kindel/kindel.py:136-145 for .bam
- * input.  `bam` is the INFLATED byte stream; first_record = offset of the first alignment record.
- *   kdl_bam_count: per_contig[n_ref][4] int64 = records seen, kept (mapped and l_seq > 1), CIGAR
- *                  ops kept, packed-SEQ 4-byte words kept; first_seen[n_ref] = rank or -1;
- *                  totals[4] = records, kept, contigs seen, bytes consumed.
- *   kdl_bam_fill : cursors[n_ref][3] int64 = next read / op / seq-word index per contig;
- *                  exotic[n_kept] (may be NULL) = 1 if the read holds a base outside A,C,G,T,N. */
-int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
-                  int64_t* per_contig, int32_t* first_seen, int64_t* totals);
-int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
-                 int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
-                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4, uint8_t* exotic);
+/* ---- host-side BAM decode (no GPU involved; kindel_b200/csrc/bam_host.cpp) ----
+ * Replaces the simplesam -> `samtools view` text round trip of kindel/kindel.py:136-145 for .bam input: BGZF blocks
+ * inflated by zlib in C++ threads, records filtered (kindel.py:43-46), classified and written straight into the
+ * layout above -- into caller-owned buffers, which may be pinned memory.
+ *   kdl_bam_open     read + inflate + parse the header (text, reference dictionary)
+ *   kdl_bam_prepare  ref_len[n_ref] = contig lengths to classify against (the @SQ LN values the reference uses;
+ *                    NULL = the binary dictionary's).  info[16] out: 0 records, 1 kept reads, 2 contigs seen,
+ *                    3 CIGAR ops of kept reads, 4 words of seq4, 5 complex reads, 6 hard reads, 7 aligned bases,
+ *                    9 reach_right, 10 reach_left, 11 longest simple read
+ *   kdl_bam_contigs  order[n_seen] = reference ids in first-seen order (kindel.py:143-151), read_off[n_seen + 1]
+ *   kdl_bam_fill     ref_start / seq_off / l_seq / seq_len [kept], cig_off [kept + 1], cigar [ops] (may be NULL),
+ *                    seq4 [words], complex_idx [complex], hard_idx [hard] (may be NULL); contig_slot[n_seen] = the slot
+ *                    layout; fills info[8] = insertion events, info[12] = reads_sorted */
+typedef struct kdl_bam kdl_bam;
+int kdl_bam_open(const char* path, int threads, kdl_bam** out);
+void kdl_bam_close(kdl_bam* h);
+const char* kdl_bam_header_text(const kdl_bam* h, int64_t* len);
+int32_t kdl_bam_n_ref(const kdl_bam* h);
+const char* kdl_bam_ref_name(const kdl_bam* h, int32_t ref_id);
+int32_t kdl_bam_ref_len(const kdl_bam* h, int32_t ref_id);
+int kdl_bam_prepare(kdl_bam* h, const int32_t* ref_len, int threads, int64_t* info);
+int kdl_bam_contigs(const kdl_bam* h, int32_t* order, int64_t* read_off);
+int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* ref_start, uint32_t* seq_off,
+                 int32_t* l_seq, int32_t* seq_len, uint32_t* cig_off, uint32_t* cigar, uint32_t* seq4,
+                 uint32_t* complex_idx, uint32_t* hard_idx, int64_t* info);
 
 #ifdef __cplusplus
 }

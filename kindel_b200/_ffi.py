@@ -117,8 +117,15 @@ _PROTOTYPES = {
     "kdl_ctx_consensus": (C.c_int, [C.c_void_p, C.POINTER(KdlBatch), C.c_int64, C.c_int64, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(KdlDiag)]),
     "kdl_ctx_last_timing": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
-    "kdl_bam_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "kdl_bam_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+    "kdl_bam_open": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "kdl_bam_close": (None, [C.c_void_p]),
+    "kdl_bam_header_text": (C.c_void_p, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "kdl_bam_n_ref": (C.c_int32, [C.c_void_p]),
+    "kdl_bam_ref_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
+    "kdl_bam_ref_len": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "kdl_bam_prepare": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "kdl_bam_contigs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kdl_bam_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -417,78 +417,79 @@ def _sq_from_text(text: str):
     return names, lens
 
 
-def read_bam(path) -> ReadBatch:
-    lib = _ffi.load()
-    buf = inflate_bam(path)
-    if buf[:4].tobytes() != b"BAM\x01":
-        raise ValueError("not a BAM file: %s" % path)
-    # the binary header is parsed straight out of the inflated buffer (no truncated copy: a reference dictionary
-    # of 10^5 contigs is several MB long)
-    mv = memoryview(buf)
-    if buf.size < 12:
-        raise ValueError("truncated BAM header in %s" % path)
-    (l_text,) = struct.unpack_from("<i", mv, 4)
-    if l_text < 0 or 8 + l_text + 4 > buf.size:
-        raise ValueError("truncated BAM header in %s" % path)
-    text = bytes(mv[8:8 + l_text]).split(b"\x00", 1)[0].decode("utf-8", "replace")
-    off = 8 + l_text
-    (n_ref,) = struct.unpack_from("<i", mv, off)
-    off += 4
-    bin_names, bin_lens = [], []
-    for _ in range(n_ref):
-        if off + 4 > buf.size:
-            raise ValueError("truncated BAM reference dictionary in %s" % path)
-        (l_name,) = struct.unpack_from("<i", mv, off)
-        if l_name < 1 or off + 8 + l_name > buf.size:
-            raise ValueError("truncated BAM reference dictionary in %s" % path)
-        name = bytes(mv[off + 4:off + 4 + l_name - 1]).decode()
-        (l_ref,) = struct.unpack_from("<i", mv, off + 4 + l_name)
-        off += 8 + l_name
-        bin_names.append(name)
-        bin_lens.append(l_ref)
-    text_names, text_lens = _sq_from_text(text)
-    text_len = dict(zip(text_names, text_lens))
-    ref_len = np.array([text_len.get(nm, ln) for nm, ln in zip(bin_names, bin_lens)], dtype=np.int64)
+def decode_threads() -> int:
+    """Threads of the C++ BAM decoder: $KINDEL_DECODE_THREADS, else the cores this process may use (at most 64)."""
+    ev = os.environ.get("KINDEL_DECODE_THREADS")
+    if ev:
+        return max(1, int(ev))
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(64, n))
 
-    ptr = buf.ctypes.data
-    per_contig = np.zeros((max(n_ref, 1), 4), dtype=np.int64)
-    first_seen = np.full(max(n_ref, 1), -1, dtype=np.int32)
-    totals = np.zeros(4, dtype=np.int64)
-    rc = lib.kdl_bam_count(ptr, buf.size, off, n_ref, per_contig.ctypes.data, first_seen.ctypes.data,
-                           totals.ctypes.data)
+
+def read_bam(path, threads: int = None, pinned: bool = False) -> ReadBatch:
+    """.bam -> ReadBatch through the C++ decoder (bam_host.cpp): BGZF inflate, filter, classification and the
+    device layout (inline CIGAR blocks included) in threads, no Python per-record or per-array work.
+    pinned=True puts the arrays the device consumes into page-locked memory (needs torch + CUDA)."""
+    import ctypes as C
+
+    lib = _ffi.load()
+    threads = threads or decode_threads()
+    h = C.c_void_p()
+    rc = lib.kdl_bam_open(os.fspath(path).encode(), threads, C.byref(h))
     if rc != 0:
-        raise ValueError("malformed BAM record stream in %s" % path)
-    seen = np.flatnonzero(first_seen[:n_ref] >= 0)
-    order = seen[np.argsort(first_seen[seen], kind="stable")]  # contigs in first-seen order
-    kept = per_contig[order, 1]
-    ops = per_contig[order, 2]
-    words = per_contig[order, 3]
-    read_off = np.concatenate(([0], np.cumsum(kept))).astype(np.int64)
-    op_off = np.concatenate(([0], np.cumsum(ops))).astype(np.int64)
-    word_off = np.concatenate(([0], np.cumsum(words))).astype(np.int64)
-    n, n_ops, n_words = int(read_off[-1]), int(op_off[-1]), int(word_off[-1])
-    if n_words >= (1 << 32) or n_ops >= (1 << 32):
-        raise ValueError("alignment file too large for 32-bit offsets; split it by contig")
-    cursors = np.zeros((max(n_ref, 1), 3), dtype=np.int64)
-    cursors[order, 0] = read_off[:-1]
-    cursors[order, 1] = op_off[:-1]
-    cursors[order, 2] = word_off[:-1]
-    ref_start = np.empty(n, dtype=np.int32)
-    seq_off = np.empty(n, dtype=np.uint32)
-    l_seq = np.empty(n, dtype=np.int32)
-    cig_off = np.empty(n + 1, dtype=np.uint32)
-    cigar = np.empty(max(n_ops, 1), dtype=np.uint32)[:n_ops]
-    seq4 = np.zeros(max(n_words, 1), dtype=np.uint32)[:n_words]
-    exotic = np.zeros(max(n, 1), dtype=np.uint8)[:n]
-    rc = lib.kdl_bam_fill(ptr, buf.size, off, n_ref, cursors.ctypes.data, ref_start.ctypes.data,
-                          seq_off.ctypes.data, l_seq.ctypes.data, cig_off.ctypes.data, cigar.ctypes.data,
-                          seq4.ctypes.data, exotic.ctypes.data)
-    if rc != 0:
-        raise ValueError("malformed BAM record stream in %s" % path)
-    cig_off[n] = n_ops
-    names = [bin_names[i] for i in order]
-    return finalize(names, ref_len[order], read_off, ref_start, seq_off, l_seq, cig_off, cigar, seq4,
-                    n_records=int(totals[0]), exotic=exotic)
+        raise ValueError("not a (readable) BAM file: %s" % path)
+    try:
+        n_ref = lib.kdl_bam_n_ref(h)
+        tl = C.c_int64()
+        tp = lib.kdl_bam_header_text(h, C.byref(tl))
+        text = C.string_at(tp, tl.value).decode("utf-8", "replace") if tp and tl.value else ""
+        bin_names = [lib.kdl_bam_ref_name(h, k).decode() for k in range(n_ref)]
+        bin_lens = [lib.kdl_bam_ref_len(h, k) for k in range(n_ref)]
+        text_names, text_lens = _sq_from_text(text)
+        text_len = dict(zip(text_names, text_lens))
+        ref_len = np.array([text_len.get(nm, ln) for nm, ln in zip(bin_names, bin_lens)], dtype=np.int32)
+        info = np.zeros(16, dtype=np.int64)
+        rc = lib.kdl_bam_prepare(h, ref_len.ctypes.data if n_ref else None, threads, info.ctypes.data)
+        if rc != 0:
+            raise ValueError("malformed BAM record stream in %s (or too large for 32-bit offsets)" % path)
+        n_rec, n, n_seen, n_ops, n_words, n_cx, n_hard = (int(x) for x in info[:7])
+        order = np.zeros(max(n_seen, 1), dtype=np.int32)[:n_seen]
+        read_off = np.zeros(n_seen + 1, dtype=np.int64)
+        _ffi.check(lib.kdl_bam_contigs(h, order.ctypes.data if n_seen else None, read_off.ctypes.data)
+                   if n_seen else 0, "kdl_bam_contigs")
+        contig_len = ref_len[order].astype(np.int32)
+        slot, n_slots = layout_slots(contig_len)
+
+        def buf(count, dtype):
+            if pinned:
+                import torch
+
+                tdt = {np.int32: torch.int32, np.uint32: torch.int32}[dtype]
+                return torch.empty(max(count, 1), dtype=tdt).pin_memory().numpy().view(dtype)[:count]
+            return np.empty(max(count, 1), dtype=dtype)[:count]
+
+        ref_start, seq_off, l_seq = buf(n, np.int32), buf(n, np.uint32), buf(n, np.int32)
+        seq_len = np.empty(max(n, 1), dtype=np.int32)[:n]
+        cig_off = np.empty(n + 1, dtype=np.uint32)
+        cigar = np.empty(max(n_ops, 1), dtype=np.uint32)[:n_ops]
+        stream = buf(n_words, np.uint32)
+        cx_idx, hard_idx = buf(n_cx, np.uint32), buf(n_hard, np.uint32)
+        rc = lib.kdl_bam_fill(h, threads, slot.ctypes.data if n_seen else None, ref_start.ctypes.data, seq_off.ctypes.data,
+                              l_seq.ctypes.data, seq_len.ctypes.data, cig_off.ctypes.data, cigar.ctypes.data,
+                              stream.ctypes.data, cx_idx.ctypes.data, hard_idx.ctypes.data, info.ctypes.data)
+        if rc != 0:
+            raise ValueError("malformed BAM record stream in %s" % path)
+    finally:
+        lib.kdl_bam_close(h)
+    return ReadBatch(
+        contig_names=[bin_names[i] for i in order], contig_len=contig_len, contig_read_off=read_off, contig_slot=slot,
+        n_slots=n_slots, ref_start=ref_start, seq_off=seq_off, l_seq=l_seq, seq_len=seq_len, cig_off=cig_off,
+        cigar=cigar, seq4=stream, hard_idx=hard_idx, complex_idx=cx_idx, n_events=int(info[8]),
+        reads_sorted=bool(info[12]) or n < 2, aligned_bases=int(info[7]), n_records=n_rec,
+        max_simple_len=int(info[11]), reach_right=int(info[9]), reach_left=int(info[10]))
 
 
 # ---------------------------------------------------------------------------------------- SAM

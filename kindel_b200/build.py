@@ -2,7 +2,7 @@
 
 `python -m kindel_b200.build` (or `__graft_entry__.build()`) compiles
 
-    kindel_b200/csrc/api.cu (+ the kernel files it includes) + scan.cu + bam_host.cpp
+    kindel_b200/csrc/api.cu (+ the kernel files it includes) + bam_host.cpp (links zlib)
         -> kindel_b200/_lib/libkindel_b200.so          nvcc, -gencode arch=compute_100a,code=sm_100a
     oracle/kindel_oracle.c -> oracle/_build/libkindel_oracle.so   gcc (test infrastructure)
 
@@ -54,7 +54,7 @@ def build_engine(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"),
-           os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "bam_host.cpp"), "-o", LIB_PATH]
+           os.path.join(CSRC, "api.cu"), os.path.join(CSRC, "bam_host.cpp"), "-lz", "-o", LIB_PATH]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(LIB_DIR, "build.log"), "w") as fh:

@@ -58,13 +58,13 @@ inline int ensure_tile_smem() {
 
 template <int kFlush, bool kCx>
 inline int launch_tile(const kdl_batch& b, int32_t* counts, long long n_slots, long long tile_lo, long long n_tiles,
-                       int split, cudaStream_t st) {
+                       int split, int zero_rest, cudaStream_t st) {
     int rc = ensure_tile_smem<kFlush, kCx>();
     if (rc != KDL_OK) return rc;
     const long long units = n_tiles * split, max_grid = (long long)sm_count() * 2;  // two CTAs per SM, persistent
     const long long grid = units < max_grid ? units : max_grid;
     kdl::pileup_tile_kernel<kFlush, kCx><<<(unsigned)grid, kdl::W_THREADS, sizeof(kdl::TileSmem<kdl::TileCfg<kCx>>), st>>>(
-        b, counts, n_slots, b.tile_index, tile_lo, n_tiles, split);
+        b, counts, n_slots, b.tile_index, tile_lo, n_tiles, split, zero_rest);
     return KDL_OK;
 }
 
@@ -137,9 +137,11 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
         }
         if (const char* ev = getenv("KDL_SPLIT")) { const int v = atoi(ev); if (v >= 1 && v <= 64) split = v; }
     }
-    // zeroing that the chosen kernels will not do themselves
+    // zeroing that the chosen kernels will not do themselves: the tile kernel overwrites the weight columns of a
+    // fresh table and, on request, zeroes columns 5..18 window by window in its flush
+    const int zero_in_k1 = (tiled && split == 1 && fresh && n_tiles > 0 && (flags & KDL_PILEUP_ZERO_REST)) ? 1 : 0;
     const int zero_from = (fresh && !(tiled && split == 1)) ? 0 : 5;
-    const int zero_to = (flags & KDL_PILEUP_ZERO_REST) ? KDL_NCOL : 5;
+    const int zero_to = ((flags & KDL_PILEUP_ZERO_REST) && !zero_in_k1) ? KDL_NCOL : 5;
     if (zero_to > zero_from && slot_hi > slot_lo) {
         kdl::zero_cols_kernel<<<sm_count() * 4, 256, 0, st>>>(counts, n_slots, zero_from, zero_to, slot_lo, slot_hi);
         if ((rc = check_launch()) != KDL_OK) return rc;
@@ -154,14 +156,14 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             // K1: the tile-owner kernel
             const bool cx = batch->n_complex > batch->n_hard;  // tile-eligible complex reads present
             if (split > 1) {
-                rc = cx ? launch_tile<kdl::F_ATOMIC, true>(*batch, counts, n_slots, tile_lo, n_tiles, split, st)
-                        : launch_tile<kdl::F_ATOMIC, false>(*batch, counts, n_slots, tile_lo, n_tiles, split, st);
+                rc = cx ? launch_tile<kdl::F_ATOMIC, true>(*batch, counts, n_slots, tile_lo, n_tiles, split, 0, st)
+                        : launch_tile<kdl::F_ATOMIC, false>(*batch, counts, n_slots, tile_lo, n_tiles, split, 0, st);
             } else if (fresh) {
-                rc = cx ? launch_tile<kdl::F_STORE, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st)
-                        : launch_tile<kdl::F_STORE, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st);
+                rc = cx ? launch_tile<kdl::F_STORE, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, zero_in_k1, st)
+                        : launch_tile<kdl::F_STORE, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, zero_in_k1, st);
             } else {
-                rc = cx ? launch_tile<kdl::F_ADD, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st)
-                        : launch_tile<kdl::F_ADD, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, st);
+                rc = cx ? launch_tile<kdl::F_ADD, true>(*batch, counts, n_slots, tile_lo, n_tiles, 1, 0, st)
+                        : launch_tile<kdl::F_ADD, false>(*batch, counts, n_slots, tile_lo, n_tiles, 1, 0, st);
             }
             if (rc != KDL_OK) return rc;
             if ((rc = check_launch()) != KDL_OK) return rc;

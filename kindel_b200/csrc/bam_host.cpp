@@ -1,40 +1,70 @@
-// bam_host.cpp -- host-side gather of BAM alignment records into the engine's flattened layout.
+// bam_host.cpp -- host-side decode of a BAM file into the engine's flattened layout, in C++ threads.
 //
 // This replaces, for .bam input, the record materialisation the reference does through
-// simplesam -> `samtools view` text (reference kindel/kindel.py:136-145): BAM's on-disk encodings
-// (CIGAR as len<<4|op uint32, SEQ as 4-bit nibbles) are already the device layout described in
-// include/kindel_b200.h, so a record is flattened with two memcpy's and no text round trip.
-// The inflated BAM byte stream comes from Python (zlib in a thread pool, kindel_b200/bamio.py).
+// simplesam -> `samtools view` text -> one Python object per record (reference kindel/kindel.py:136-145).
+// BAM's on-disk encodings (CIGAR as len<<4|op uint32, SEQ as 4-bit nibbles) are already the device layout
+// described in include/kindel_b200.h, so nothing is ever turned into text:
 //
-// Two passes, because the output is grouped by contig in first-seen order (kindel.py:143-151):
-//   kdl_bam_count : walk the block_size chain once; per contig: records seen (any flag), records
-//                   kept (mapped and l_seq > 1, kindel.py:43-46), CIGAR ops and packed-SEQ words
-//                   of kept records, and the first-seen rank of the contig.
-//   kdl_bam_fill  : walk again and append every kept record at its contig's running cursor.
+//   kdl_bam_open     read the file, inflate its BGZF blocks in parallel (zlib, one block per task), parse the
+//                    header (text + reference dictionary)
+//   kdl_bam_prepare  index the records (the block_size chain), then in parallel: filter (kindel.py:43-46: mapped and
+//                    len(seq) > 1), classify every kept record (simple / tile-eligible complex / hard, the rules of
+//                    include/kindel_b200.h) and size the outputs per contig; contigs are ordered by first appearance
+//                    over ALL records (kindel.py:143-151)
+//   kdl_bam_fill     in parallel: write every kept record at its place -- start, lengths, CIGAR words, the packed
+//                    bases byte-swapped into 32-bit words and, for complex reads, the inline block
+//                    [n_ops][evt_off][ops...] behind them -- straight into caller-owned (e.g. pinned) buffers
+//
+// No GIL, no Python zlib, no numpy passes: Python only parses the @SQ text lines (the reference takes contig
+// lengths from them, kindel.py:138-141) and wraps the arrays.  Ultra-long CIGARs stored in the CG:B,I tag
+// (n_cigar == 2, `<l_seq>S<ref_len>N` placeholder; SAM spec 4.2.2) are taken from the tag, as samtools does.
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
+#include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/kindel_b200.h"
 
 namespace {
 
+inline int32_t rd_i32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); return v; }
+inline uint32_t rd_u32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+inline uint16_t rd_u16(const uint8_t* p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
+
+template <class F>
+void parallel_for(int64_t n, int threads, F&& body) {  // body(task_index, thread_index), dynamic scheduling
+    if (threads < 1) threads = 1;
+    if (n <= 1 || threads == 1) {
+        for (int64_t i = 0; i < n; ++i) body(i, 0);
+        return;
+    }
+    std::atomic<int64_t> next{0};
+    std::vector<std::thread> pool;
+    const int nt = (int)std::min<int64_t>(threads, n);
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&, t] {
+            for (;;) {
+                const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
+                if (i >= n) break;
+                body(i, t);
+            }
+        });
+    for (auto& th : pool) th.join();
+}
+
 struct RecView {
     int32_t ref_id, pos, l_seq;
-    uint32_t n_cigar, flag, l_read_name;
-    const uint8_t* cigar;
+    uint32_t n_cigar, flag;
+    const uint8_t* cigar;  // n_cigar uint32 words (unaligned)
     const uint8_t* seq;
 };
-
-inline int32_t rd_i32(const uint8_t* p) {
-    int32_t v;
-    std::memcpy(&v, p, 4);
-    return v;
-}
-inline uint16_t rd_u16(const uint8_t* p) {
-    uint16_t v;
-    std::memcpy(&v, p, 2);
-    return v;
-}
 
 // Returns bytes consumed (4 + block_size) or 0 when the record is truncated / malformed.
 inline int64_t parse_record(const uint8_t* p, int64_t avail, RecView* r) {
@@ -44,109 +74,475 @@ inline int64_t parse_record(const uint8_t* p, int64_t avail, RecView* r) {
     const uint8_t* q = p + 4;
     r->ref_id = rd_i32(q);
     r->pos = rd_i32(q + 4);
-    r->l_read_name = q[8];
+    const uint32_t l_read_name = q[8];
     r->n_cigar = rd_u16(q + 12);
     r->flag = rd_u16(q + 14);
     r->l_seq = rd_i32(q + 16);
-    const int64_t need = 32 + (int64_t)r->l_read_name + 4ll * r->n_cigar + ((int64_t)r->l_seq + 1) / 2;
-    if (r->l_seq < 0 || need > block_size) return 0;
-    r->cigar = q + 32 + r->l_read_name;
+    if (r->l_seq < 0 || r->l_seq >= (1 << 30)) return 0;  // (the device word keeps two flag bits above the length)
+    const int64_t fixed = 32 + (int64_t)l_read_name + 4ll * r->n_cigar + ((int64_t)r->l_seq + 1) / 2;
+    if (fixed > block_size) return 0;
+    r->cigar = q + 32 + l_read_name;
     r->seq = r->cigar + 4ll * r->n_cigar;
+    // the real CIGAR of a read with more than 65535 ops lives in the CG:B,I tag behind the qualities
+    if (r->n_cigar == 2) {
+        const uint32_t c0 = rd_u32(r->cigar), c1 = rd_u32(r->cigar + 4);
+        if ((c0 & 15u) == 4u && (int64_t)(c0 >> 4) == r->l_seq && (c1 & 15u) == 3u) {
+            const uint8_t* a = r->seq + ((int64_t)r->l_seq + 1) / 2 + r->l_seq;  // aux data
+            const uint8_t* end = q + block_size;
+            while (a + 3 <= end) {
+                const char t0 = (char)a[0], t1 = (char)a[1], ty = (char)a[2];
+                a += 3;
+                int64_t skip = -1;
+                switch (ty) {
+                    case 'A': case 'c': case 'C': skip = 1; break;
+                    case 's': case 'S': skip = 2; break;
+                    case 'i': case 'I': case 'f': skip = 4; break;
+                    case 'Z': case 'H': { const uint8_t* z = a; while (z < end && *z) ++z; skip = (z - a) + 1; break; }
+                    case 'B': {
+                        if (a + 5 > end) return 4 + (int64_t)block_size;
+                        const char sub = (char)a[0];
+                        const uint32_t cnt = rd_u32(a + 1);
+                        const int w = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+                        if (t0 == 'C' && t1 == 'G' && sub == 'I' && a + 5 + 4ll * cnt <= end) {
+                            r->cigar = a + 5;
+                            r->n_cigar = cnt;
+                            return 4 + (int64_t)block_size;
+                        }
+                        skip = 5 + (int64_t)w * cnt;
+                        break;
+                    }
+                    default: return 4 + (int64_t)block_size;  // unknown type: leave the placeholder
+                }
+                if (skip < 0) break;
+                a += skip;
+            }
+        }
+    }
     return 4 + (int64_t)block_size;
 }
 
 inline bool kept(const RecView& r) { return !(r.flag & 0x4u) && r.l_seq > 1; }
 
+// one 32-bit word of packed bases (8 nibbles, first base in the most significant one) from BAM's byte order;
+// *bad |= nibbles that are not one of 1,2,4,8 (A,C,G,T) or 15 (N)
+inline uint32_t seq_word(const uint8_t* seq, int64_t n_bytes_seq, int64_t k, int32_t l_seq, bool last, uint32_t* bad) {
+    uint8_t b[4] = {0, 0, 0, 0};
+    const int64_t left = n_bytes_seq - 4 * k;
+    std::memcpy(b, seq + 4 * k, (size_t)(left < 4 ? left : 4));
+    uint32_t v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
+    uint32_t chk = v;
+    if (last && (l_seq & 7)) {
+        const uint32_t pad = 0xFFFFFFFFu >> (4 * (l_seq & 7));
+        v &= ~pad;
+        chk = v | (pad & 0x11111111u);  // padding counts as fine
+    }
+    const uint32_t h = chk | (chk >> 1), pair = chk & (chk >> 1);
+    const uint32_t two_plus = (pair | (pair >> 2) | (h & (h >> 2))) & 0x11111111u;
+    const uint32_t all4 = pair & (pair >> 2) & 0x11111111u;
+    const uint32_t zero = ~(h | (h >> 2)) & 0x11111111u;
+    *bad |= (two_plus & ~all4) | zero;
+    return v;
+}
+
+enum : uint8_t { CLS_DROP = 0, CLS_SIMPLE = 1, CLS_TILE = 2, CLS_HARD = 3 };
+
+struct Class {
+    uint8_t cls;
+    uint8_t n_match;     // M/=/X ops (tile-eligible reads)
+    uint16_t n_ins;      // I ops, saturating (only its sum over complex reads matters: recomputed in fill)
+};
+
+// the classification of include/kindel_b200.h (mirrors kindel_b200/bamio.py finalize)
+inline Class classify(const RecView& r, int64_t L, int64_t* reach_r, int64_t* reach_l, int64_t* aligned) {
+    Class c{CLS_HARD, 0, 0};
+    const int64_t lseq = r.l_seq, start = r.pos;
+    const int64_t n_bytes_seq = (lseq + 1) / 2, n_words = (lseq + 7) / 8;
+    uint32_t bad = 0;
+    for (int64_t k = 0; k < n_words; ++k) seq_word(r.seq, n_bytes_seq, k, r.l_seq, k == n_words - 1, &bad);
+    int64_t q_span = 0, r_span = 0, lead = 0, n_match = 0, al = 0;
+    for (uint32_t o = 0; o < r.n_cigar; ++o) {
+        const uint32_t cg = rd_u32(r.cigar + 4ull * o);
+        const int64_t len = cg >> 4;
+        const uint32_t op = cg & 15u;
+        const bool m = op == 0 || op == 7 || op == 8;
+        if (m) { ++n_match; al += len; }
+        if (m || op == 1 || op == 4) q_span += len;
+        if (m || op == 2 || (op == 4 && o > 0)) r_span += len;
+        if (op == 4 && o == 0) lead = len;
+    }
+    *aligned = al;
+    if (r.n_cigar == 1) {
+        const uint32_t cg = rd_u32(r.cigar);
+        const uint32_t op = cg & 15u;
+        const int64_t len = cg >> 4;
+        if ((op == 0 || op == 7 || op == 8) && len == lseq && start >= 0 && start + len <= L && len <= KDL_FAST_MAXLEN && !bad) {
+            c.cls = CLS_SIMPLE;
+            if (len > *reach_r) *reach_r = len;
+            return c;
+        }
+    }
+    const bool tile_ok = !bad && r.n_cigar <= KDL_TILE_MAXOPS && lseq <= KDL_FAST_MAXLEN && q_span <= lseq &&
+                         start - lead - 1 >= 0 && start + r_span <= L - 1 && r_span + 1 <= KDL_TILE_MAXREACH &&
+                         lead + 1 <= KDL_TILE_MAXREACH;
+    if (tile_ok) {
+        c.cls = CLS_TILE;
+        c.n_match = (uint8_t)n_match;
+        if (r_span + 1 > *reach_r) *reach_r = r_span + 1;
+        if (lead + 1 > *reach_l) *reach_l = lead + 1;
+    }
+    return c;
+}
+
 }  // namespace
+
+struct kdl_bam {
+    std::vector<uint8_t> data;          // the inflated BAM byte stream
+    int64_t first_record = 0;
+    std::string text;                   // header text
+    std::vector<std::string> ref_name;
+    std::vector<int32_t> ref_len;       // binary dictionary lengths (Python may override from the @SQ text)
+    // after prepare
+    std::vector<int64_t> rec_off;       // offset of every record (+ end)
+    std::vector<Class> cls;             // per record
+    std::vector<int32_t> order;         // contigs (ref ids) in first-seen order
+    std::vector<int64_t> read_off, op_off, word_off;  // per ordered contig (+ total)
+    std::vector<int64_t> chunk_lo;      // record ranges of the parallel tasks
+    std::vector<int64_t> cur_read, cur_op, cur_word;   // [task][n_ref] start cursors
+    int64_t n_records = 0, n_kept = 0, n_complex = 0, n_hard = 0, aligned = 0, n_events = 0;
+    int64_t reach_right = 0, reach_left = 0, max_simple = 0;
+    int32_t reads_sorted = 1;
+    bool prepared = false;
+};
 
 extern "C" {
 
-// per_contig[n_ref][4] int64: seen, kept, ops, seq_words.  first_seen[n_ref] int32: rank or -1.
-// totals[4]: records, kept, contigs seen, bytes consumed.
-int kdl_bam_count(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
-                  int64_t* per_contig, int32_t* first_seen, int64_t* totals) {
-    if (!bam || !per_contig || !first_seen || !totals || first_record < 0 || first_record > n_bytes)
-        return KDL_ERR_INVALID_ARG;
-    std::memset(per_contig, 0, sizeof(int64_t) * 4 * (size_t)n_ref);
-    for (int32_t c = 0; c < n_ref; ++c) first_seen[c] = -1;
-    int64_t off = first_record, n_rec = 0, n_kept = 0;
-    int32_t rank = 0;
-    RecView r;
-    while (off < n_bytes) {
-        const int64_t used = parse_record(bam + off, n_bytes - off, &r);
-        if (!used) return KDL_ERR_INVALID_ARG;
-        off += used;
-        ++n_rec;
-        if (r.ref_id < 0) continue;  // rname '*' is dropped wholesale (kindel.py:147-148)
-        if (r.ref_id >= n_ref) return KDL_ERR_INVALID_ARG;
-        int64_t* pc = per_contig + 4ll * r.ref_id;
-        if (first_seen[r.ref_id] < 0) first_seen[r.ref_id] = rank++;
-        pc[0] += 1;
-        if (kept(r)) {
-            pc[1] += 1;
-            pc[2] += r.n_cigar;
-            pc[3] += ((int64_t)r.l_seq + 7) / 8;  // nibbles -> 4-byte words
-            ++n_kept;
+// Reads and inflates `path` (BGZF, plain gzip members, or an uncompressed BAM stream) with `threads` threads and
+// parses the header.  Returns KDL_OK, KDL_ERR_INVALID_ARG for a file that is not a BAM.
+int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
+    if (!path || !out) return KDL_ERR_INVALID_ARG;
+    *out = nullptr;
+    FILE* fh = std::fopen(path, "rb");
+    if (!fh) return KDL_ERR_INVALID_ARG;
+    std::vector<uint8_t> raw;
+    {
+        std::fseek(fh, 0, SEEK_END);
+        const long sz = std::ftell(fh);
+        std::fseek(fh, 0, SEEK_SET);
+        if (sz < 0) { std::fclose(fh); return KDL_ERR_INVALID_ARG; }
+        raw.resize((size_t)sz);
+        if (sz && std::fread(raw.data(), 1, (size_t)sz, fh) != (size_t)sz) { std::fclose(fh); return KDL_ERR_INVALID_ARG; }
+        std::fclose(fh);
+    }
+    kdl_bam* h = new (std::nothrow) kdl_bam();
+    if (!h) return KDL_ERR_INVALID_ARG;
+    const size_t n = raw.size();
+    if (n >= 4 && !std::memcmp(raw.data(), "BAM\1", 4)) {
+        h->data.swap(raw);
+    } else {
+        // BGZF: gzip members with a BC extra field holding the block size; the chain of headers is walked
+        // sequentially (cheap), the payloads are inflated in parallel at their prefix-summed offsets
+        struct Blk { size_t pay, pay_len, out_off; uint32_t isize; };
+        std::vector<Blk> blks;
+        size_t off = 0, total = 0;
+        bool bgzf = true;
+        while (off < n) {
+            if (n - off < 18 || raw[off] != 0x1f || raw[off + 1] != 0x8b || raw[off + 2] != 8 || !(raw[off + 3] & 4)) { bgzf = false; break; }
+            const size_t xlen = rd_u16(&raw[off + 10]);
+            size_t p = off + 12, end_x = off + 12 + xlen;
+            long bsize = -1;
+            if (end_x > n) { bgzf = false; break; }
+            while (p + 4 <= end_x) {
+                const uint8_t si1 = raw[p], si2 = raw[p + 1];
+                const size_t slen = rd_u16(&raw[p + 2]);
+                if (si1 == 66 && si2 == 67 && slen == 2 && p + 6 <= end_x) bsize = rd_u16(&raw[p + 4]);
+                p += 4 + slen;
+            }
+            if (bsize < 0 || off + (size_t)bsize + 1 > n || (size_t)bsize + 1 < end_x - off + 8) { bgzf = false; break; }
+            const size_t blk_end = off + (size_t)bsize + 1;
+            const uint32_t isize = rd_u32(&raw[blk_end - 4]);
+            blks.push_back({end_x, blk_end - 8 - end_x, total, isize});
+            total += isize;
+            off = blk_end;
+        }
+        if (!bgzf) {  // a plain gzip stream (or garbage): one sequential inflate
+            z_stream zs;
+            std::memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, 15 + 32) != Z_OK) { delete h; return KDL_ERR_INVALID_ARG; }
+            zs.next_in = raw.data();
+            zs.avail_in = (uInt)n;
+            std::vector<uint8_t> outb(std::max<size_t>(n * 4, 1 << 16));
+            size_t have = 0;
+            int rc = Z_OK;
+            while (rc != Z_STREAM_END) {
+                if (have == outb.size()) outb.resize(outb.size() * 2);
+                zs.next_out = outb.data() + have;
+                zs.avail_out = (uInt)std::min<size_t>(outb.size() - have, 1u << 30);
+                const size_t before = zs.avail_out;
+                rc = inflate(&zs, Z_NO_FLUSH);
+                have += before - zs.avail_out;
+                if (rc == Z_STREAM_END && zs.avail_in > 0) {  // concatenated members
+                    if (inflateReset(&zs) != Z_OK) break;
+                    rc = Z_OK;
+                    continue;
+                }
+                if (rc != Z_OK && rc != Z_STREAM_END) break;
+                if (rc == Z_OK && zs.avail_in == 0 && before == zs.avail_out) break;
+            }
+            inflateEnd(&zs);
+            outb.resize(have);
+            h->data.swap(outb);
+        } else {
+            h->data.resize(total);
+            std::atomic<int> failed{0};
+            parallel_for((int64_t)blks.size(), threads, [&](int64_t i, int) {
+                const Blk& b = blks[(size_t)i];
+                if (!b.isize) return;
+                z_stream zs;
+                std::memset(&zs, 0, sizeof zs);
+                if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
+                zs.next_in = raw.data() + b.pay;
+                zs.avail_in = (uInt)b.pay_len;
+                zs.next_out = h->data.data() + b.out_off;
+                zs.avail_out = b.isize;
+                const int rc = inflate(&zs, Z_FINISH);
+                if (rc != Z_STREAM_END || zs.avail_out != 0) failed = 1;
+                inflateEnd(&zs);
+            });
+            if (failed) { delete h; return KDL_ERR_INVALID_ARG; }
         }
     }
-    totals[0] = n_rec;
-    totals[1] = n_kept;
-    totals[2] = rank;
-    totals[3] = off;
+    const std::vector<uint8_t>& d = h->data;
+    if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4)) { delete h; return KDL_ERR_INVALID_ARG; }
+    const int64_t l_text = rd_i32(&d[4]);
+    if (l_text < 0 || 8 + l_text + 4 > (int64_t)d.size()) { delete h; return KDL_ERR_INVALID_ARG; }
+    h->text.assign((const char*)&d[8], (size_t)l_text);
+    const size_t nul = h->text.find('\0');
+    if (nul != std::string::npos) h->text.resize(nul);
+    int64_t off = 8 + l_text;
+    const int64_t n_ref = rd_i32(&d[(size_t)off]);
+    off += 4;
+    if (n_ref < 0) { delete h; return KDL_ERR_INVALID_ARG; }
+    for (int64_t k = 0; k < n_ref; ++k) {
+        if (off + 4 > (int64_t)d.size()) { delete h; return KDL_ERR_INVALID_ARG; }
+        const int64_t l_name = rd_i32(&d[(size_t)off]);
+        if (l_name < 1 || off + 8 + l_name > (int64_t)d.size()) { delete h; return KDL_ERR_INVALID_ARG; }
+        h->ref_name.emplace_back((const char*)&d[(size_t)off + 4], (size_t)l_name - 1);
+        h->ref_len.push_back(rd_i32(&d[(size_t)(off + 4 + l_name)]));
+        off += 8 + l_name;
+    }
+    h->first_record = off;
+    *out = h;
     return KDL_OK;
 }
 
-// cursors[n_ref][3] int64: next read index, next op index, next seq word for each contig
-// (pre-set by the caller from the prefix sums of kdl_bam_count's output; advanced in place).
-// Outputs are sized for all kept records: ref_start/seq_off/l_seq/cig_start [n_kept],
-// cigar [total ops], seq4 [total words] uint32.
-int kdl_bam_fill(const uint8_t* bam, int64_t n_bytes, int64_t first_record, int32_t n_ref,
-                 int64_t* cursors, int32_t* ref_start, uint32_t* seq_off, int32_t* l_seq,
-                 uint32_t* cig_start, uint32_t* cigar, uint32_t* seq4, uint8_t* exotic) {
-    if (!bam || !cursors) return KDL_ERR_INVALID_ARG;
-    int64_t off = first_record;
-    RecView r;
-    while (off < n_bytes) {
-        const int64_t used = parse_record(bam + off, n_bytes - off, &r);
-        if (!used) return KDL_ERR_INVALID_ARG;
-        off += used;
-        if (r.ref_id < 0 || r.ref_id >= n_ref || !kept(r)) continue;
-        int64_t* cur = cursors + 3ll * r.ref_id;
-        const int64_t i = cur[0]++;
-        const int64_t o = cur[1];
-        const int64_t w = cur[2];
-        cur[1] += r.n_cigar;
-        cur[2] += ((int64_t)r.l_seq + 7) / 8;
-        ref_start[i] = r.pos;  // BAM pos is 0-based == SAM POS - 1 (kindel.py:42)
-        seq_off[i] = (uint32_t)w;
-        l_seq[i] = r.l_seq;
-        cig_start[i] = (uint32_t)o;
-        std::memcpy(cigar + o, r.cigar, 4ull * r.n_cigar);
-        // BAM packs two bases per byte, first base in the high nibble; the engine wants 8 bases
-        // per 32-bit word with the first base in the most significant nibble: a byte-swapped copy.
-        const int64_t n_bytes_seq = ((int64_t)r.l_seq + 1) / 2;
-        const int64_t n_words_seq = ((int64_t)r.l_seq + 7) / 8;
-        uint32_t bad = 0;
-        for (int64_t k = 0; k < n_words_seq; ++k) {
-            uint8_t b[4] = {0, 0, 0, 0};
-            const int64_t left = n_bytes_seq - 4 * k;
-            std::memcpy(b, r.seq + 4 * k, (size_t)(left < 4 ? left : 4));
-            uint32_t v = ((uint32_t)b[0] << 24) | ((uint32_t)b[1] << 16) | ((uint32_t)b[2] << 8) | b[3];
-            uint32_t chk = v;  // nibbles that must each be one of 1,2,4,8 (A,C,G,T) or 15 (N)
-            if (k == n_words_seq - 1 && (r.l_seq & 7)) {
-                const uint32_t pad = 0xFFFFFFFFu >> (4 * (r.l_seq & 7));
-                v &= ~pad;
-                chk = v | (pad & 0x11111111u);  // padding counts as fine
-            }
-            seq4[w + k] = v;
-            const uint32_t h = chk | (chk >> 1), pair = chk & (chk >> 1);
-            const uint32_t two_plus = (pair | (pair >> 2) | (h & (h >> 2))) & 0x11111111u;
-            const uint32_t all4 = pair & (pair >> 2) & 0x11111111u;
-            const uint32_t zero = ~(h | (h >> 2)) & 0x11111111u;
-            bad |= (two_plus & ~all4) | zero;
-        }
-        if (exotic) exotic[i] = bad ? 1 : 0;
+void kdl_bam_close(kdl_bam* h) { delete h; }
+
+const char* kdl_bam_header_text(const kdl_bam* h, int64_t* len) {
+    if (!h) return nullptr;
+    if (len) *len = (int64_t)h->text.size();
+    return h->text.c_str();
+}
+int32_t kdl_bam_n_ref(const kdl_bam* h) { return h ? (int32_t)h->ref_name.size() : 0; }
+const char* kdl_bam_ref_name(const kdl_bam* h, int32_t ref_id) {
+    return (h && ref_id >= 0 && ref_id < (int32_t)h->ref_name.size()) ? h->ref_name[(size_t)ref_id].c_str() : nullptr;
+}
+int32_t kdl_bam_ref_len(const kdl_bam* h, int32_t ref_id) {
+    return (h && ref_id >= 0 && ref_id < (int32_t)h->ref_len.size()) ? h->ref_len[(size_t)ref_id] : -1;
+}
+
+// ref_len[n_ref]: the contig lengths to classify against (the @SQ text's LN, as the reference uses; NULL = the binary
+// dictionary's).  info[16] out: 0 records, 1 kept reads, 2 contigs seen, 3 CIGAR ops of kept reads, 4 words of the
+// read stream, 5 complex reads, 6 hard reads, 7 aligned bases, 8 insertion events, 9 reach_right, 10 reach_left,
+// 11 longest simple read, 12 reads_sorted (valid after kdl_bam_fill).
+int kdl_bam_prepare(kdl_bam* h, const int32_t* ref_len, int threads, int64_t* info) {
+    if (!h || !info) return KDL_ERR_INVALID_ARG;
+    const uint8_t* d = h->data.data();
+    const int64_t n_bytes = (int64_t)h->data.size();
+    const int32_t n_ref = (int32_t)h->ref_name.size();
+    if (ref_len) h->ref_len.assign(ref_len, ref_len + n_ref);
+    // ---- the block_size chain (sequential: 4 bytes per record are touched)
+    h->rec_off.clear();
+    for (int64_t off = h->first_record; off < n_bytes;) {
+        if (n_bytes - off < 36) return KDL_ERR_INVALID_ARG;
+        const int64_t bs = rd_i32(d + off);
+        if (bs < 32 || off + 4 + bs > n_bytes) return KDL_ERR_INVALID_ARG;
+        h->rec_off.push_back(off);
+        off += 4 + bs;
     }
+    h->rec_off.push_back(n_bytes);
+    const int64_t n_rec = (int64_t)h->rec_off.size() - 1;
+    h->n_records = n_rec;
+    h->cls.assign((size_t)n_rec, Class{CLS_DROP, 0, 0});
+    // ---- parallel classify + count.  Tasks are contiguous record ranges, so "file order inside a contig" is
+    // task order then record order.
+    if (threads < 1) threads = 1;
+    int64_t n_tasks = std::min<int64_t>(std::max<int64_t>(1, n_rec / 4096), (int64_t)threads * 4);
+    if ((int64_t)n_ref * n_tasks > (1ll << 24)) n_tasks = std::max<int64_t>(1, (1ll << 24) / std::max(1, n_ref));  // bound the cursor tables
+    h->chunk_lo.resize((size_t)n_tasks + 1);
+    for (int64_t t = 0; t <= n_tasks; ++t) h->chunk_lo[(size_t)t] = n_rec * t / n_tasks;
+    struct Acc { int64_t kept = 0, ops = 0, words = 0, first = -1; };
+    std::vector<Acc> acc((size_t)n_tasks * (size_t)std::max(1, n_ref));
+    struct Tot { int64_t cx = 0, hard = 0, aligned = 0, rr = 0, rl = 0, ms = 0; int bad = 0; };
+    std::vector<Tot> tot((size_t)n_tasks);
+    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+        Acc* a = acc.data() + (size_t)t * (size_t)std::max(1, n_ref);
+        Tot& tt = tot[(size_t)t];
+        RecView r;
+        for (int64_t i = h->chunk_lo[(size_t)t]; i < h->chunk_lo[(size_t)t + 1]; ++i) {
+            const int64_t off = h->rec_off[(size_t)i];
+            if (!parse_record(d + off, h->rec_off[(size_t)i + 1] - off, &r)) { tt.bad = 1; return; }
+            if (r.ref_id < 0) continue;  // rname '*' is dropped wholesale (kindel.py:147-148)
+            if (r.ref_id >= n_ref) { tt.bad = 1; return; }
+            Acc& ac = a[r.ref_id];
+            if (ac.first < 0) ac.first = i;
+            if (!kept(r)) continue;
+            int64_t rr = 0, rl = 0, al = 0;
+            const Class c = classify(r, h->ref_len[(size_t)r.ref_id], &rr, &rl, &al);
+            h->cls[(size_t)i] = c;
+            ac.kept += 1;
+            ac.ops += r.n_cigar;
+            ac.words += ((int64_t)r.l_seq + 7) / 8 + (c.cls == CLS_SIMPLE ? 0 : 2 + (int64_t)r.n_cigar);
+            tt.aligned += al;
+            if (c.cls != CLS_SIMPLE) tt.cx += 1;
+            if (c.cls == CLS_HARD) tt.hard += 1;
+            if (c.cls == CLS_SIMPLE && rr > tt.ms) tt.ms = rr;
+            if (c.cls != CLS_HARD) { tt.rr = std::max(tt.rr, rr); tt.rl = std::max(tt.rl, rl); }
+        }
+    });
+    h->n_complex = h->n_hard = h->aligned = 0;
+    h->reach_right = h->reach_left = h->max_simple = 0;
+    for (const Tot& tt : tot) {
+        if (tt.bad) return KDL_ERR_INVALID_ARG;
+        h->n_complex += tt.cx; h->n_hard += tt.hard; h->aligned += tt.aligned;
+        h->reach_right = std::max(h->reach_right, tt.rr); h->reach_left = std::max(h->reach_left, tt.rl);
+        h->max_simple = std::max(h->max_simple, tt.ms);
+    }
+    // ---- contigs in first-seen order, sizes per contig, start cursors per (task, contig)
+    std::vector<int64_t> first((size_t)std::max(1, n_ref), -1), kept_c((size_t)std::max(1, n_ref), 0),
+        ops_c((size_t)std::max(1, n_ref), 0), words_c((size_t)std::max(1, n_ref), 0);
+    for (int64_t t = 0; t < n_tasks; ++t)
+        for (int32_t c = 0; c < n_ref; ++c) {
+            const Acc& ac = acc[(size_t)t * (size_t)n_ref + (size_t)c];
+            if (ac.first >= 0 && (first[(size_t)c] < 0 || ac.first < first[(size_t)c])) first[(size_t)c] = ac.first;
+            kept_c[(size_t)c] += ac.kept; ops_c[(size_t)c] += ac.ops; words_c[(size_t)c] += ac.words;
+        }
+    h->order.clear();
+    for (int32_t c = 0; c < n_ref; ++c) if (first[(size_t)c] >= 0) h->order.push_back(c);
+    std::sort(h->order.begin(), h->order.end(), [&](int32_t a, int32_t b) { return first[(size_t)a] < first[(size_t)b]; });
+    const size_t ns = h->order.size();
+    h->read_off.assign(ns + 1, 0); h->op_off.assign(ns + 1, 0); h->word_off.assign(ns + 1, 0);
+    for (size_t k = 0; k < ns; ++k) {
+        const size_t c = (size_t)h->order[k];
+        h->read_off[k + 1] = h->read_off[k] + kept_c[c];
+        h->op_off[k + 1] = h->op_off[k] + ops_c[c];
+        h->word_off[k + 1] = h->word_off[k] + words_c[c];
+    }
+    h->n_kept = h->read_off[ns];
+    if (h->word_off[ns] >= (1ll << 32) || h->op_off[ns] >= (1ll << 32) || h->n_kept >= (1ll << 31)) return KDL_ERR_INVALID_ARG;
+    const size_t tab = (size_t)n_tasks * (size_t)std::max(1, n_ref);
+    h->cur_read.assign(tab, 0); h->cur_op.assign(tab, 0); h->cur_word.assign(tab, 0);
+    for (size_t k = 0; k < ns; ++k) {
+        const size_t c = (size_t)h->order[k];
+        int64_t rr = h->read_off[k], oo = h->op_off[k], ww = h->word_off[k];
+        for (int64_t t = 0; t < n_tasks; ++t) {
+            const size_t ix = (size_t)t * (size_t)n_ref + c;
+            h->cur_read[ix] = rr; h->cur_op[ix] = oo; h->cur_word[ix] = ww;
+            rr += acc[ix].kept; oo += acc[ix].ops; ww += acc[ix].words;
+        }
+    }
+    h->prepared = true;
+    info[0] = n_rec; info[1] = h->n_kept; info[2] = (int64_t)ns; info[3] = h->op_off[ns]; info[4] = h->word_off[ns];
+    info[5] = h->n_complex; info[6] = h->n_hard; info[7] = h->aligned; info[8] = 0;
+    info[9] = std::max(h->reach_right, h->max_simple); info[10] = h->reach_left; info[11] = h->max_simple; info[12] = 1;
+    for (int k = 13; k < 16; ++k) info[k] = 0;
+    return KDL_OK;
+}
+
+// order[n_seen]: ref ids in first-seen order; read_off[n_seen + 1]
+int kdl_bam_contigs(const kdl_bam* h, int32_t* order, int64_t* read_off) {
+    if (!h || !h->prepared || !order || !read_off) return KDL_ERR_INVALID_ARG;
+    std::memcpy(order, h->order.data(), h->order.size() * sizeof(int32_t));
+    std::memcpy(read_off, h->read_off.data(), h->read_off.size() * sizeof(int64_t));
+    return KDL_OK;
+}
+
+// Caller-owned outputs (any memory, e.g. pinned): ref_start / seq_off / l_seq (device word) / seq_len [n_kept],
+// cig_off [n_kept + 1], cigar [n_ops], stream [stream_words], complex_idx [n_complex], hard_idx [n_hard].
+// contig_slot[n_seen]: the slot layout (for the coordinate-order check).  info[8] = insertion events,
+// info[12] = reads_sorted are filled in.
+int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* ref_start, uint32_t* seq_off,
+                 int32_t* l_seq, int32_t* seq_len, uint32_t* cig_off, uint32_t* cigar, uint32_t* stream,
+                 uint32_t* complex_idx, uint32_t* hard_idx, int64_t* info) {
+    if (!h || !h->prepared || !ref_start || !seq_off || !l_seq || !seq_len || !cig_off || !stream || !info)
+        return KDL_ERR_INVALID_ARG;
+    const uint8_t* d = h->data.data();
+    const int32_t n_ref = (int32_t)h->ref_name.size();
+    const int64_t n_tasks = (int64_t)h->chunk_lo.size() - 1;
+    const int64_t n = h->n_kept;
+    std::vector<uint32_t> ins_n((size_t)std::max<int64_t>(n, 1), 0);  // I ops per kept read (final order)
+    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+        std::vector<int64_t> cr(h->cur_read.begin() + t * n_ref, h->cur_read.begin() + (t + 1) * n_ref);
+        std::vector<int64_t> co(h->cur_op.begin() + t * n_ref, h->cur_op.begin() + (t + 1) * n_ref);
+        std::vector<int64_t> cw(h->cur_word.begin() + t * n_ref, h->cur_word.begin() + (t + 1) * n_ref);
+        RecView r;
+        for (int64_t i = h->chunk_lo[(size_t)t]; i < h->chunk_lo[(size_t)t + 1]; ++i) {
+            const Class c = h->cls[(size_t)i];
+            if (c.cls == CLS_DROP) continue;
+            const int64_t off = h->rec_off[(size_t)i];
+            parse_record(d + off, h->rec_off[(size_t)i + 1] - off, &r);
+            const size_t ci = (size_t)r.ref_id;
+            const int64_t k = cr[ci]++, o = co[ci], w = cw[ci];
+            const int64_t n_words = ((int64_t)r.l_seq + 7) / 8, n_bytes_seq = ((int64_t)r.l_seq + 1) / 2;
+            co[ci] += r.n_cigar;
+            cw[ci] += n_words + (c.cls == CLS_SIMPLE ? 0 : 2 + (int64_t)r.n_cigar);
+            ref_start[k] = r.pos;  // BAM pos is 0-based == SAM POS - 1 (kindel.py:42)
+            seq_off[k] = (uint32_t)w;
+            seq_len[k] = r.l_seq;
+            cig_off[k] = (uint32_t)o;
+            uint32_t lw;
+            if (c.cls == CLS_SIMPLE) lw = (uint32_t)r.l_seq;
+            else if (c.cls == CLS_TILE) lw = (uint32_t)r.l_seq | ((uint32_t)c.n_match << KDL_NM_SHIFT) | KDL_COMPLEX;
+            else lw = (uint32_t)r.l_seq | KDL_COMPLEX | KDL_HARD;
+            std::memcpy(&l_seq[k], &lw, 4);
+            if (cigar && r.n_cigar) std::memcpy(cigar + o, r.cigar, 4ull * r.n_cigar);
+            uint32_t bad = 0;
+            for (int64_t q = 0; q < n_words; ++q) stream[w + q] = seq_word(r.seq, n_bytes_seq, q, r.l_seq, q == n_words - 1, &bad);
+            uint32_t ni = 0;
+            for (uint32_t q = 0; q < r.n_cigar; ++q) ni += (rd_u32(r.cigar + 4ull * q) & 15u) == 1u;
+            ins_n[(size_t)k] = ni;
+            if (c.cls != CLS_SIMPLE) {
+                stream[w + n_words] = r.n_cigar;
+                stream[w + n_words + 1] = 0;  // evt_off: below
+                std::memcpy(stream + w + n_words + 2, r.cigar, 4ull * r.n_cigar);
+            }
+        }
+    });
+    cig_off[n] = (uint32_t)h->op_off[h->order.size()];
+    // ---- insertion-event rows (exclusive prefix of the I-op counts in read order), the complex / hard lists and the
+    // coordinate-order check: one cheap sequential pass over the per-read arrays
+    int64_t evt = 0, ncx = 0, nh = 0;
+    int32_t sorted_ok = 1;
+    size_t contig = 0;
+    long long prev_g = -(1ll << 62);
+    for (int64_t k = 0; k < n; ++k) {
+        while (contig + 1 < h->read_off.size() && k >= h->read_off[contig + 1]) ++contig;
+        const long long g = (contig_slot ? contig_slot[contig] : 0) + (long long)ref_start[k];
+        if (g < prev_g) sorted_ok = 0;
+        prev_g = g;
+        uint32_t lw;
+        std::memcpy(&lw, &l_seq[k], 4);
+        if (lw & KDL_COMPLEX) {
+            stream[(size_t)seq_off[k] + (size_t)(((int64_t)seq_len[k] + 7) / 8) + 1] = (uint32_t)evt;
+            if (complex_idx) complex_idx[ncx] = (uint32_t)k;
+            ++ncx;
+            if (lw & KDL_HARD) { if (hard_idx) hard_idx[nh] = (uint32_t)k; ++nh; }
+        }
+        evt += ins_n[(size_t)k];
+    }
+    h->n_events = evt;
+    h->reads_sorted = sorted_ok;
+    info[8] = evt;
+    info[12] = sorted_ok;
     return KDL_OK;
 }
 

@@ -76,7 +76,7 @@ struct TileStage {
 template <class C>
 struct TileSmem {
     TileStage<C> st[W_STAGES];
-    int raw[3][C::kRmax];          // producers: l_seq / ref_start / seq_off of the NEXT unit's first reads (cp.async)
+    int raw[3][C::kRmax + 4];      // producers: l_seq / ref_start / seq_off of the NEXT item's reads (cp.async), + 1 offset
     unsigned short queue[W_CONSUMERS][64];  // consumers (kCx): indices of the pieces that overlap the warp's window
     int scan[W_PRODUCERS * 4 + 4];  // producers (kCx): per-group piece totals, cut counter
     uint64_t full[W_STAGES];       // producers -> consumers: 4 warp arrivals (metadata, pieces, coverage written)
@@ -95,7 +95,8 @@ static_assert(offsetof(TileStage<TileCfg<false>>, diff) % 16 == 0 && sizeof(Tile
 template <int kFlush, bool kCx>
 __global__ void __launch_bounds__(W_THREADS, 2)
 pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
-                   const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles, int split) {
+                   const uint32_t* __restrict__ tile_index, long long tile_lo, long long n_tiles, int split,
+                   int zero_rest) {
     KDL_DYNAMIC_SMEM(smem_raw);
     using C = TileCfg<kCx>;
     using Smem = TileSmem<C>;
@@ -140,11 +141,12 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             if (lane == 0) mbar_arrive(&sm.full[s]);
         };
 
-        // The producers run a software pipeline of their own: the index entry of the next unit's tile and the
-        // three metadata words of its first reads are in flight (cp.async into sm.raw, each thread fetching
-        // exactly the elements it will consume) while the current item is being prepared.
+        // The producers run a software pipeline of their own: while an item is prepared, the three metadata words
+        // of the NEXT item's reads (the same unit's next chunk, or the next unit's first) stream into sm.raw with
+        // cp.async, together with the word offset of the read behind them -- so neither the item bounds nor the
+        // per-read metadata wait for a global load.  The index entry of the next unit's tile is loaded a unit ahead.
         constexpr int PER = W_RMAX / W_PT;  // reads per producer thread and item
-        struct Unit { long long lo, hi, plo, phi; uint32_t wa, wend; uint2 ic; long long cs; };
+        struct Unit { uint32_t lo, hi, plo, phi, wa, wend; uint2 ic; long long cs; };  // (read indices are < 2^31)
         auto load_unit = [&](long long w, Unit& u) {
             if (w >= n_units) { u.lo = u.hi = u.plo = u.phi = 0; u.wa = u.wend = 0; u.ic = make_uint2(0, 0); u.cs = 0; return; }
             const long long t = tile_lo + w / split;
@@ -155,23 +157,27 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             u.hi = ix.y;
             u.wa = ix.z;
             u.wend = ix.w;
-            const long long n = u.hi - u.lo;
-            u.plo = u.lo + n * part / split;
-            u.phi = u.lo + n * (part + 1) / split;
+            const long long n = (long long)u.hi - u.lo;
+            u.plo = u.lo + (uint32_t)(n * part / split);
+            u.phi = u.lo + (uint32_t)(n * (part + 1) / split);
             u.cs = b.contig_slot[u.ic.x];
         };
-        auto prefetch_raw = [&](const Unit& u) {
-            const long long n = u.phi - u.plo;
-            const int cnt = (int)(n < W_RMAX ? n : W_RMAX);
+        uint32_t pf_start = 0xFFFFFFFFu;  // sm.raw holds reads [pf_start, pf_start + pf_cnt) and seq_off of the one behind
+        int pf_cnt = 0;
+        auto prefetch_raw = [&](uint32_t start, uint32_t end) {
+            const int cnt = end > start ? (int)(end - start < (uint32_t)W_RMAX ? end - start : (uint32_t)W_RMAX) : 0;
+            pf_start = start;
+            pf_cnt = cnt;
             for (int i = ptid; i < cnt; i += W_PT) {
-                cp_async4(&sm.raw[0][i], b.l_seq + u.plo + i);
-                cp_async4(&sm.raw[1][i], b.ref_start + u.plo + i);
-                cp_async4(&sm.raw[2][i], b.seq_off + u.plo + i);
+                cp_async4(&sm.raw[0][i], b.l_seq + start + i);
+                cp_async4(&sm.raw[1][i], b.ref_start + start + i);
+                cp_async4(&sm.raw[2][i], b.seq_off + start + i);
             }
+            if (ptid == 0 && cnt > 0 && (long long)start + cnt < b.n_reads) cp_async4(&sm.raw[2][cnt], b.seq_off + start + cnt);
         };
         Unit u, nu;
         load_unit(blockIdx.x, u);
-        prefetch_raw(u);
+        prefetch_raw(u.plo, u.phi);
 
         for (long long w = blockIdx.x; w < n_units; w += gridDim.x) {
             load_unit(w + gridDim.x, nu);  // consumed at the end of this iteration
@@ -186,38 +192,45 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     publish(item);
                     ++item;
                 }
-                prefetch_raw(nu);  // nothing was in flight for an empty unit
+                cp_async_wait_all();  // (nothing useful was in flight for an empty unit)
+                producer_sync();
+                prefetch_raw(nu.plo, nu.phi);
                 u = nu;
                 continue;
             }
             const bool one_contig = u.ic.x == u.ic.y;
             const long long slot_base = one_contig ? u.cs - tile_slot : 0;
-            long long c0 = u.plo;
+            uint32_t c0 = u.plo;
             bool first = true;
-            bool raw_pending = true;
             while (c0 < u.phi) {
-                long long c1 = c0 + W_RMAX < u.phi ? c0 + W_RMAX : u.phi;
-                const long long wa = c0 == u.lo ? (long long)u.wa : (long long)(b.seq_off[c0] & ~3u);
-                long long wend = c1 == u.hi ? (long long)u.wend : (long long)b.seq_off[c1];
+                cp_async_wait_all();
+                producer_sync();  // this item's prefetched words are visible to every producer thread
+                const bool have = pf_start == c0 && pf_cnt > 0;
+                uint32_t c1 = u.phi - c0 > (uint32_t)W_RMAX ? c0 + W_RMAX : u.phi;
+                if (have && c1 > c0 + pf_cnt) c1 = c0 + pf_cnt;
+                auto word_off = [&](uint32_t r) -> uint32_t {  // seq_off[r] (r < n_reads), from sm.raw when it is there
+                    return (have && r - c0 <= (uint32_t)pf_cnt) ? (uint32_t)sm.raw[2][r - c0] : b.seq_off[r];
+                };
+                const uint32_t wa = c0 == u.lo ? u.wa : (word_off(c0) & ~3u);
+                uint32_t wend = c1 == u.hi ? u.wend : ((long long)c1 < b.n_reads ? word_off(c1) : (uint32_t)b.seq4_words);
                 bool skip = false;
-                while (wend - wa > W_CAPW) {
+                while (wend - wa > (uint32_t)W_CAPW) {
                     if (c1 - c0 == 1) { skip = true; break; }  // one read too long to stage: never tile-eligible
-                    const long long n = c1 - c0;               // cut where the capacity ends
-                    long long n2 = n * W_CAPW / (wend - wa);
+                    const uint32_t n = c1 - c0;                // cut where the capacity ends
+                    uint32_t n2 = (uint32_t)((unsigned long long)n * W_CAPW / (wend - wa));
                     n2 = n2 >= n ? n - 1 : (n2 < 1 ? 1 : n2);
                     c1 = c0 + n2;
-                    wend = (long long)b.seq_off[c1];
+                    wend = word_off(c1);
                 }
                 int n_sub = skip ? 0 : (int)(c1 - c0);
-                // this thread's reads of the item: from the prefetched words (first item of the unit) or directly
+                // this thread's reads of the item
                 int l[PER], rs[PER];
                 uint32_t so[PER];
-                if (c0 == u.plo && raw_pending) {
-                    cp_async_wait_all();
+                if (have) {
 #pragma unroll
                     for (int k = 0; k < PER; ++k) {
                         const int i = ptid + k * W_PT;
-                        const int ii = i < n_sub ? i : ptid;
+                        const int ii = i < n_sub ? i : 0;
                         l[k] = sm.raw[0][ii];
                         rs[k] = sm.raw[1][ii];
                         so[k] = (uint32_t)sm.raw[2][ii];
@@ -226,19 +239,34 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #pragma unroll
                     for (int k = 0; k < PER; ++k) {
                         const int i = ptid + k * W_PT;
-                        const long long r = c0 + (i < n_sub ? i : 0);
+                        const long long r = (long long)c0 + (i < n_sub ? i : 0);
                         l[k] = b.l_seq[r];
                         rs[k] = b.ref_start[r];
                         so[k] = b.seq_off[r];
                     }
                 }
-                if (raw_pending) {  // own elements are in registers: refill them for the next unit
-                    prefetch_raw(nu);
-                    raw_pending = false;
+                // ---- stage + bulk copy first: the bytes fly while the metadata is written.  (If the piece list
+                // later cuts the item short the copy has fetched a little more than needed: harmless.)
+                Stage& st = acquire_stage(item);
+                const int stage_id = (int)(item % W_STAGES);
+                const uint32_t seq_base = smem_u32(st.seq);
+                {
+                    const long long n_words = skip ? 0 : (long long)(wend - wa);
+                    const long long avail = b.seq4_words - (long long)wa;
+                    const long long want = (n_words + 3) & ~3ll;
+                    const long long bulk_words = want <= avail ? want : (avail & ~3ll);
+                    const uint32_t tx = (uint32_t)(bulk_words * 4);
+                    if (ptid == 0) {  // announce the bytes (one arrival), then let the TMA engine copy them
+                        mbar_expect_tx(&sm.landed[stage_id], tx);
+                        if (bulk_words) bulk_g2s(st.seq, b.seq4 + wa, tx, &sm.landed[stage_id]);
+                    }
+                    if (bulk_words < n_words && ptid < 4) {  // the (at most one) partial granule at the array's end, by hand
+                        const long long wq = bulk_words + ptid;
+                        st.seq[wq] = wq < avail ? b.seq4[wa + wq] : 0u;  // (visible to all after the barriers below)
+                    }
                 }
-                // ---- complex reads: where each one's pieces go and its rank among the item's complex reads (exclusive
-                // prefix in read order of: M-op count in the low 16 bits, 1 per tile-eligible complex read above),
-                // and a cut of the item if the pieces do not fit the list
+                // ---- complex reads: where each one's pieces go (exclusive prefix in read order of: M-op count in the
+                // low 16 bits, 1 per tile-eligible complex read above), and a cut of the item if they do not fit
                 int pre[PER];
                 int n_px = 0, n_cx = 0;  // pieces / tile-eligible complex reads of the item
                 if constexpr (kCx) {
@@ -288,7 +316,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             producer_sync();
                             n_sub = sm.scan[4 * W_PRODUCERS];  // >= 1: one read has at most KDL_TILE_MAXOPS <= kPcap pieces
                             c1 = c0 + n_sub;
-                            wend = (long long)b.seq_off[c1];   // c1 < u.phi <= n_reads here
 #pragma unroll
                             for (int k = 0; k < PER; ++k) {
                                 const int i = ptid + k * W_PT;
@@ -300,60 +327,44 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             n_cx = sm.scan[4 * W_PRODUCERS + 1] >> 16;
                             if (ptid == 0) sm.scan[4 * W_PRODUCERS] = 0;
                         }
-                        // (the next item's first write to sm.scan[g] comes after at least one more producer barrier of
-                        // this item: no thread still reads the totals then)
+                        // (the next item's first write to sm.scan[g] comes after at least one more producer barrier:
+                        // no thread still reads the totals then)
                     }
                 }
                 const bool last = c1 >= u.phi;
-                Stage& st = acquire_stage(item);
-                const int stage_id = (int)(item % W_STAGES);
-                const uint32_t seq_base = smem_u32(st.seq);
-                {
-                    const long long n_words = skip ? 0 : wend - wa;
-                    const long long avail = b.seq4_words - wa;
-                    const long long want = (n_words + 3) & ~3ll;
-                    const long long bulk_words = want <= avail ? want : (avail & ~3ll);
-                    const uint32_t tx = (uint32_t)(bulk_words * 4);
-                    if (ptid == 0) {  // announce the bytes (one arrival), then let the TMA engine copy them
-                        mbar_expect_tx(&sm.landed[stage_id], tx);
-                        if (bulk_words) bulk_g2s(st.seq, b.seq4 + wa, tx, &sm.landed[stage_id]);
-                    }
-                    if (bulk_words < n_words) {  // the (at most one) partial granule at the array's end, by hand
-                        if (ptid < 4) {
-                            const long long wq = bulk_words + ptid;
-                            st.seq[wq] = wq < avail ? b.seq4[wa + wq] : 0u;
-                        }
-                        if constexpr (kCx) producer_sync();  // a CIGAR may sit in those words (uniform branch)
-                    }
-                }
-                int gsv[PER];
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
                     const int i = ptid + k * W_PT;
-                    gsv[k] = 0;
                     if (i < n_sub) {
                         long long g;
                         if (one_contig) {
                             g = slot_base + rs[k];
                         } else {
-                            const int c = find_contig(b.contig_read_off, b.n_contigs, c0 + i);
+                            const int c = find_contig(b.contig_read_off, b.n_contigs, (long long)c0 + i);
                             g = b.contig_slot[c] + rs[k] - tile_slot;
                         }
                         const int gs = (int)g;  // inside (-reach_right, 512 + reach_left) by construction of the index
-                        gsv[k] = gs;
-                        int nb = 0;
+                        const int raddr = (int)(seq_base + ((so[k] - wa) << 2));
+                        const uint32_t lw = (uint32_t)l[k];
+                        int4 en;
                         if (l[k] > 0) {  // simple read (bit 31 clear)
-                            nb = ((l[k] + 7) >> 3) << 2;
                             const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
                             if (cs < ce) {
                                 atomicAdd(st.diff + cs, 1);
                                 atomicAdd(st.diff + ce, -1);
                             }
+                            en = make_int4(((gs + 7) >> 3) << 2, raddr, ((l[k] + 7) >> 3) << 2, ((-gs) & 7) << 2);
+                        } else if (kCx && (lw & KDL_HARD) == 0) {
+                            // tile-eligible complex read: .z = 0 keeps the entry inert in the simple loop; the rest is
+                            // what the explode below needs -- start, block address, first piece slot, SEQ length,
+                            // M-op count (.w: bit 31 = marker, 24..30 M ops, 10..23 length, 0..9 piece slot)
+                            en = make_int4(gs, raddr, 0, (int)(0x80000000u | (((lw >> KDL_NM_SHIFT) & KDL_NM_MASK) << 24) |
+                                                               ((lw & 0x3FFFu) << 10) | (uint32_t)(pre[k] & 0x3FF)));
+                        } else {
+                            en = make_int4(((gs + 7) >> 3) << 2, raddr, 0, 0);  // K1g's: adds nothing here
                         }
                         st.gs[i] = gs;
-                        st.meta[i + (i >> 3)] = make_int4(((gs + 7) >> 3) << 2,
-                                                          (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2)), nb,
-                                                          ((-gs) & 7) << 2);
+                        st.meta[i + (i >> 3)] = en;
                     }
                 }
                 if (ptid < 40) {  // sentinels behind the last read
@@ -374,19 +385,17 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         // insertion / deletion / clip updates of these reads are K1e's (pileup_general.cu), once per
                         // read instead of once per tile it touches.
                         mbar_wait(&sm.landed[stage_id], (uint32_t)((item / W_STAGES) & 1));
-#pragma unroll
-                        for (int k = 0; k < PER; ++k) {
-                            const int i = ptid + k * W_PT;
-                            const uint32_t lw = (uint32_t)l[k];
-                            if (i >= n_sub || (lw & (KDL_COMPLEX | KDL_HARD)) != KDL_COMPLEX) continue;
-                            const int nbw = ((int)(lw & KDL_LEN_MASK) + 7) >> 3;
-                            const uint32_t* rw = st.seq + ((long long)so[k] - wa);  // the read's block in shared memory
-                            const int raddr = (int)(seq_base + (uint32_t)(((long long)so[k] - wa) << 2));
+#pragma unroll 1
+                        for (int i = ptid; i < n_sub; i += W_PT) {  // (its own entries: no barrier needed)
+                            const int4 en = st.meta[i + (i >> 3)];
+                            if (en.w >= 0) continue;
+                            const int nbw = (((en.w >> 10) & 0x3FFF) + 7) >> 3;
+                            const uint32_t* rw = st.seq + (((uint32_t)en.y - seq_base) >> 2);  // the read's block
                             const int n_ops = (int)rw[nbw];
                             const uint32_t* ops = rw + nbw + 2;
-                            int pos = pre[k] & 0xFFFF;
-                            const int pend = pos + (int)((lw >> KDL_NM_SHIFT) & KDL_NM_MASK);
-                            int r = gsv[k], q = 0;
+                            int pos = en.w & 0x3FF;
+                            const int pend = pos + ((en.w >> 24) & 0x7F);
+                            int r = en.x, q = 0;
                             for (int o = 0; o < n_ops; ++o) {
                                 const uint32_t cg = ops[o];
                                 const int len = (int)(cg >> 4);
@@ -397,7 +406,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                                         const int v = r - q;  // slot of the read's base 0
                                         atomicAdd(st.diff + s0, 1);
                                         atomicAdd(st.diff + s1, -1);
-                                        st.px[pos++] = make_int4(((v + 7) >> 3) << 2, raddr, nbw << 2,
+                                        st.px[pos++] = make_int4(((v + 7) >> 3) << 2, en.y, nbw << 2,
                                                                  (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
                                     }
                                     r += len;
@@ -416,7 +425,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         }
                     }
                 }
-                producer_sync();  // difference array complete
+                producer_sync();  // difference array complete; nobody reads sm.raw any more
+                if (c1 < u.phi) prefetch_raw(c1, u.phi);   // the next item's words: this unit's next chunk ...
+                else prefetch_raw(nu.plo, nu.phi);          // ... or the next unit's first
                 {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
                     const int w0 = (KDL_TILE / W_PRODUCERS) * pw;
                     int pre_sum = 0;
@@ -616,6 +627,16 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             if (blocks_since_flush & 1) acc.template ripple<3>(pend8);
             if (kFresh && !stored) flush_window<F_STORE, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
             else flush_window<kAdd, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+            if (kFresh && zero_rest) {
+                // columns 5..18 of the window hold an earlier pileup's sparse counts: zero them here, under the
+                // counting, instead of in a pass of their own (K1e / K1g add to them after this kernel)
+                int32_t* z = counts + tile_slot + wlo + 8 * (lane & 7);
+                for (int col = 5 + quarter; col < KDL_NCOL; col += 4) {
+                    int4* zp = reinterpret_cast<int4*>(z + (long long)col * n_slots);
+                    zp[0] = make_int4(0, 0, 0, 0);
+                    zp[1] = make_int4(0, 0, 0, 0);
+                }
+            }
             blocks_since_flush = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) covacc[k] = 0;

@@ -30,7 +30,7 @@ void emu_set_schedule(int mode, unsigned long long seed) {
 // int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.
 // Returns 0, or 1 with emu_last_error() set.
 int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint32_t* tile_index, long long tile_lo,
-               long long n_tiles, int mode, int cx, int split, int32_t* ins_events, int grid) {
+               long long n_tiles, int mode, int cx, int split, int32_t* ins_events, int zero_rest, int grid) {
     g_error[0] = 0;
     if (n_tiles <= 0) return 0;
     const kdl_batch b = *batch;
@@ -38,7 +38,7 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
     const char* err = emu::launch(idx_grid, 256, [&] { kdl::tile_index_kernel(b, tile_lo, n_tiles, tile_index); });
     if (!err) {
         err = emu::launch((unsigned)grid, (unsigned)kdl::W_THREADS, [&] {
-#define KDL_EMU_TILE(M, X) kdl::pileup_tile_kernel<M, X>(b, counts, n_slots, tile_index, tile_lo, n_tiles, split)
+#define KDL_EMU_TILE(M, X) kdl::pileup_tile_kernel<M, X>(b, counts, n_slots, tile_index, tile_lo, n_tiles, split, zero_rest)
             if (mode == 0) { if (cx) KDL_EMU_TILE(kdl::F_STORE, true); else KDL_EMU_TILE(kdl::F_STORE, false); }
             else if (mode == 1) { if (cx) KDL_EMU_TILE(kdl::F_ADD, true); else KDL_EMU_TILE(kdl::F_ADD, false); }
             else { if (cx) KDL_EMU_TILE(kdl::F_ATOMIC, true); else KDL_EMU_TILE(kdl::F_ATOMIC, false); }

@@ -53,7 +53,7 @@ def load():
     lib.emu_last_error.restype = C.c_char_p
     lib.emu_pileup.restype = C.c_int
     lib.emu_pileup.argtypes = [C.POINTER(_ffi.KdlBatch), C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
-                               C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+                               C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
     vp = C.c_void_p
     lib.emu_pileup_simple.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, C.c_int]
     lib.emu_pileup_general.argtypes = [C.POINTER(_ffi.KdlBatch), vp, C.c_longlong, vp, vp, C.c_int, C.c_int]
@@ -83,11 +83,13 @@ def tileable(batch) -> bool:
 
 
 def run_pileup(batch, mode: int = F_STORE, grid: int = 5, tile_lo: int = 0, n_tiles: int = None,
-               counts: np.ndarray = None, split: int = 1, cx: bool = None, want_events: bool = False):
+               counts: np.ndarray = None, split: int = 1, cx: bool = None, want_events: bool = False,
+               zero_rest: bool = False):
     """K0 + K1 over tiles [tile_lo, tile_lo + n_tiles) of `batch` (a bamio.ReadBatch): everything but the KDL_HARD
     reads.
 
-    mode F_STORE: the weight columns of `counts` hold garbage on entry (the kernel must overwrite them);
+    mode F_STORE: the weight columns of `counts` hold garbage on entry (the kernel must overwrite them; with
+    zero_rest so do columns 5..18, which the kernel zeroes in its flush before K1e adds to them);
     F_ADD / F_ATOMIC: the kernel adds to what is there (F_ATOMIC with `split` CTAs per tile).  cx: which
     instantiation (default: what kdl_pileup_range picks).  Returns int32 [19, n_slots] (and the event rows)."""
     from kindel_b200 import engine
@@ -107,12 +109,14 @@ def run_pileup(batch, mode: int = F_STORE, grid: int = 5, tile_lo: int = 0, n_ti
         table[:] = 0
         if mode == F_STORE:
             table[0:5, tile_lo * 512:(tile_lo + n_tiles) * 512] = 0x5A5A5A5A
+            if zero_rest:
+                table[5:, tile_lo * 512:(tile_lo + n_tiles) * 512] = 0x3B3B3B3B
     else:
         table[:] = counts
     index = np.zeros(8 * (n_slots // 512), dtype=np.uint32)
     events = np.full((max(int(batch.n_events), 1), 4), -1, dtype=np.int32)
     rc = lib.emu_pileup(C.byref(st), table.ctypes.data, n_slots, index.ctypes.data, tile_lo, n_tiles, mode,
-                        1 if cx else 0, split, events.ctypes.data, grid)
+                        1 if cx else 0, split, events.ctypes.data, 1 if zero_rest else 0, grid)
     del keep
     if rc:
         raise RuntimeError(lib.emu_last_error().decode())
@@ -138,7 +142,7 @@ def pileup_pipeline(batch, grid: int = 3, split: int = 1):
             index = np.zeros(8 * (n_slots // 512), dtype=np.uint32)
             cx = batch.n_complex > batch.n_hard
             _check(lib.emu_pileup(C.byref(st), counts.ctypes.data, n_slots, index.ctypes.data, 0, n_slots // 512,
-                                  F_ATOMIC if split > 1 else F_ADD, 1 if cx else 0, split, events.ctypes.data, grid))
+                                  F_ATOMIC if split > 1 else F_ADD, 1 if cx else 0, split, events.ctypes.data, 0, grid))
             _check(lib.emu_pileup_general(C.byref(st), counts.ctypes.data, n_slots, events.ctypes.data,
                                           flag.ctypes.data, 0, grid))
         else:

@@ -68,8 +68,8 @@ def test_complex_reads_in_the_tile_kernel(name, split):
     got_c, got_e = E.pileup_pipeline(batch, split=split)
     np.testing.assert_array_equal(got_c, want_c)
     np.testing.assert_array_equal(got_e, want_e)
-    if split == 1:  # stale weight columns are overwritten, K1 alone = everything but the hard reads
-        got2, ev2 = E.run_pileup(batch, E.F_STORE, want_events=True)
+    if split == 1:  # stale columns are overwritten / zeroed in the flush, K1 + K1e = everything but the hard reads
+        got2, ev2 = E.run_pileup(batch, E.F_STORE, want_events=True, zero_rest=True)
         hard = __import__("kindel_b200.distributed", fromlist=["x"]).select_reads(batch, batch.hard_idx)
         wh, _ = coracle.pileup(hard)
         np.testing.assert_array_equal(got2, want_c - wh)

@@ -34,10 +34,11 @@
  *                            too long for a tile: SURVEY.md A-7..A-10); bit 30 clear = "tile-eligible": every
  *                            slot it touches lies in [1, L - 1] of its contig, its query span fits its SEQ,
  *                            it has at most KDL_TILE_MAXOPS ops and reaches at most KDL_TILE_MAXREACH slots
- *                            to either side of its start, and all its bases are A,C,G,T,N -- the tile
- *                            kernel K1 walks it without bounds or error logic.  bits 16..22 of a complex
- *                            read's word: number of M/=/X ops (saturating at 127; exact for tile-eligible
- *                            reads), so a tile can be sized before its bases are staged.
+ *                            to either side of its start, and all its bases are A,C,G,T,N -- K1 and K1e
+ *                            walk it without bounds or error logic.  A tile-eligible read keeps its SEQ
+ *                            length (<= KDL_FAST_MAXLEN) in bits 0..15 and its number of M/=/X ops in bits
+ *                            16..22, so a tile can be sized before its bases are staged; a hard read keeps
+ *                            its length in bits 0..29.
  *                            The flatten step classifies (kindel_b200/bamio.py).
  *     seq4[n_words]  uint32  one block per read, in read order.  Bases: BAM nibble codes
  *                            "=ACMGRSVTWYHKDBN", 8 per 32-bit word, FIRST base in the MOST significant
@@ -149,9 +150,10 @@ int64_t kdl_launch_count(void);
  * Adds every read's contribution to `counts` (caller zeroes it first, so several batches -- or
  * several read shards -- can accumulate into one table) and writes the insertion event rows.
  * err_flag: device int32[4], caller-zeroed; [0] becomes non-zero if any read raised.
- * Coordinate-sorted batches (reads_sorted, tile_index scratch given) take the tile-owner kernel
- * K1f (no atomics); anything else the order-independent atomic kernel K1s.  Complex reads always
- * take K1g. */
+ * Coordinate-sorted batches (reads_sorted, tile_index scratch given) take K0 (tile index) + the tile-owner
+ * kernel K1 (simple reads and the M/=/X bases of tile-eligible complex reads: no atomics), K1e (the sparse
+ * insertion / deletion / clip updates of those complex reads, once per read) and K1g (KDL_HARD reads, atomics);
+ * anything else the order-independent atomic kernels K1s + K1g. */
 int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t* ins_events,
                int32_t* err_flag, void* stream);
 
@@ -160,7 +162,8 @@ int kdl_pileup(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int32_t
  *   KDL_PILEUP_FRESH_WEIGHTS  columns 0..4 of the range hold stale data: the tile-owner kernel
  *                             OVERWRITES them (plain stores, no prior memset, no read-modify-write)
  *   KDL_PILEUP_ZERO_REST      columns 5..18 of the range are zeroed first (needed only when an
- *                             earlier pileup with complex reads dirtied them) */
+ *                             earlier pileup with complex reads dirtied them; with FRESH_WEIGHTS the tile-owner
+ *                             kernel does it window by window in its flush, no separate pass) */
 #define KDL_PILEUP_FRESH_WEIGHTS 1
 #define KDL_PILEUP_ZERO_REST 2
 int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, int64_t slot_lo,

@@ -32,18 +32,18 @@ constexpr int W_PRODUCERS = 4;   // producer warps
 constexpr int W_STAGES = 2;
 constexpr int W_THREADS = 32 * (W_CONSUMERS + W_PRODUCERS);
 constexpr int W_PT = 32 * W_PRODUCERS;  // producer threads
-template <bool kCx> struct TileRegs { static constexpr int kProducer = kCx ? 56 : 40, kConsumer = kCx ? 88 : 96; };  // 128 p + 256 c <= 384 * 80
+template <bool kCx> struct TileRegs { static constexpr int kProducer = 56, kConsumer = 88; };  // 128 * 56 + 256 * 88 <= 384 * 80
 
 // kCx = false: batches without tile-eligible complex reads (no piece list, larger stages)
 template <bool kCx> struct TileCfg;
 template <> struct TileCfg<false> {
     static constexpr int kRmax = 512;    // reads per item
-    static constexpr int kCapW = 9216;   // words of seq4 per item (36 KB: ~485 reads of 150 bases)
+    static constexpr int kCapW = 8576;   // words of seq4 per item (33.5 KB: ~451 reads of 150 bases)
     static constexpr int kPcap = 0;      // pieces of complex reads per item
 };
 template <> struct TileCfg<true> {
     static constexpr int kRmax = 384;
-    static constexpr int kCapW = 7168;   // 28 KB
+    static constexpr int kCapW = 6656;   // 26 KB
     static constexpr int kPcap = 768;
 };
 
@@ -76,11 +76,12 @@ struct TileStage {
 template <class C>
 struct TileSmem {
     TileStage<C> st[W_STAGES];
-    int raw[3][C::kRmax + 4];      // producers: l_seq / ref_start / seq_off of the NEXT item's reads (cp.async), + 1 offset
+    int raw[2][3][C::kRmax + 4];   // producers: l_seq / ref_start / seq_off of the next item's reads (cp.async; double-
+                                   // buffered by item parity), + the word offset of the read behind them
     unsigned short queue[W_CONSUMERS][64];  // consumers (kCx): indices of the pieces that overlap the warp's window
     int scan[W_PRODUCERS * 4 + 4];  // producers (kCx): per-group piece totals, cut counter
     uint64_t full[W_STAGES];       // producers -> consumers: 4 warp arrivals (metadata, pieces, coverage written)
-    uint64_t landed[W_STAGES];     // the bulk copy's bytes (1 arrival + tx): consumers, and producers that explode
+    uint64_t landed[W_STAGES];     // the bulk copy's bytes (1 arrival + tx): producers that explode, and the publisher
     uint64_t empty[W_STAGES];      // consumers -> producers: 8 warp arrivals
 };
 static_assert(sizeof(TileSmem<TileCfg<false>>) <= 113 * 1024 && sizeof(TileSmem<TileCfg<true>>) <= 113 * 1024,
@@ -138,7 +139,12 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         auto publish = [&](long long it) {  // this warp's part of the item is written
             const int s = (int)(it % W_STAGES);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.full[s]);
+            if (lane == 0) {
+                // producer warp 0 vouches for the bulk copy too: it arrives only after the bytes have landed (they
+                // have, long ago), so the consumers wait on ONE barrier
+                if (pw == 0) mbar_wait(&sm.landed[s], (uint32_t)((it / W_STAGES) & 1));
+                mbar_arrive(&sm.full[s]);
+            }
         };
 
         // The producers run a software pipeline of their own: while an item is prepared, the three metadata words
@@ -162,18 +168,23 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             u.phi = u.lo + (uint32_t)(n * (part + 1) / split);
             u.cs = b.contig_slot[u.ic.x];
         };
-        uint32_t pf_start = 0xFFFFFFFFu;  // sm.raw holds reads [pf_start, pf_start + pf_cnt) and seq_off of the one behind
-        int pf_cnt = 0;
+        // sm.raw[pf_buf] holds (or will, once the cp.async group lands) reads [pf_start, pf_start + pf_cnt) and the
+        // seq_off of the read behind them.  The buffers alternate: an item issues the prefetch for the next one as
+        // soon as its own bounds are known, a whole item ahead of its use.
+        uint32_t pf_start = 0xFFFFFFFFu;
+        int pf_cnt = 0, pf_buf = 0;
         auto prefetch_raw = [&](uint32_t start, uint32_t end) {
             const int cnt = end > start ? (int)(end - start < (uint32_t)W_RMAX ? end - start : (uint32_t)W_RMAX) : 0;
             pf_start = start;
             pf_cnt = cnt;
+            pf_buf ^= 1;
+            int (*raw)[W_RMAX + 4] = sm.raw[pf_buf];
             for (int i = ptid; i < cnt; i += W_PT) {
-                cp_async4(&sm.raw[0][i], b.l_seq + start + i);
-                cp_async4(&sm.raw[1][i], b.ref_start + start + i);
-                cp_async4(&sm.raw[2][i], b.seq_off + start + i);
+                cp_async4(&raw[0][i], b.l_seq + start + i);
+                cp_async4(&raw[1][i], b.ref_start + start + i);
+                cp_async4(&raw[2][i], b.seq_off + start + i);
             }
-            if (ptid == 0 && cnt > 0 && (long long)start + cnt < b.n_reads) cp_async4(&sm.raw[2][cnt], b.seq_off + start + cnt);
+            if (ptid == 0 && cnt > 0 && (long long)start + cnt < b.n_reads) cp_async4(&raw[2][cnt], b.seq_off + start + cnt);
         };
         Unit u, nu;
         load_unit(blockIdx.x, u);
@@ -192,8 +203,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     publish(item);
                     ++item;
                 }
-                cp_async_wait_all();  // (nothing useful was in flight for an empty unit)
-                producer_sync();
+                cp_async_wait_all();  // (two prefetches of one thread must not be in flight to the same buffer)
                 prefetch_raw(nu.plo, nu.phi);
                 u = nu;
                 continue;
@@ -206,10 +216,12 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 cp_async_wait_all();
                 producer_sync();  // this item's prefetched words are visible to every producer thread
                 const bool have = pf_start == c0 && pf_cnt > 0;
+                int (*raw)[W_RMAX + 4] = sm.raw[pf_buf];
+                const int have_cnt = pf_cnt;
                 uint32_t c1 = u.phi - c0 > (uint32_t)W_RMAX ? c0 + W_RMAX : u.phi;
-                if (have && c1 > c0 + pf_cnt) c1 = c0 + pf_cnt;
+                if (have && c1 > c0 + have_cnt) c1 = c0 + have_cnt;
                 auto word_off = [&](uint32_t r) -> uint32_t {  // seq_off[r] (r < n_reads), from sm.raw when it is there
-                    return (have && r - c0 <= (uint32_t)pf_cnt) ? (uint32_t)sm.raw[2][r - c0] : b.seq_off[r];
+                    return (have && r - c0 <= (uint32_t)have_cnt) ? (uint32_t)raw[2][r - c0] : b.seq_off[r];
                 };
                 const uint32_t wa = c0 == u.lo ? u.wa : (word_off(c0) & ~3u);
                 uint32_t wend = c1 == u.hi ? u.wend : ((long long)c1 < b.n_reads ? word_off(c1) : (uint32_t)b.seq4_words);
@@ -231,9 +243,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     for (int k = 0; k < PER; ++k) {
                         const int i = ptid + k * W_PT;
                         const int ii = i < n_sub ? i : 0;
-                        l[k] = sm.raw[0][ii];
-                        rs[k] = sm.raw[1][ii];
-                        so[k] = (uint32_t)sm.raw[2][ii];
+                        l[k] = raw[0][ii];
+                        rs[k] = raw[1][ii];
+                        so[k] = (uint32_t)raw[2][ii];
                     }
                 } else {
 #pragma unroll
@@ -245,6 +257,11 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         so[k] = b.seq_off[r];
                     }
                 }
+                // ---- the next item's words start streaming into the other buffer now: this unit's next chunk, or the
+                // next unit's first.  (Should the piece list cut this item short below, the prefetch is for the wrong
+                // reads and the next item falls back to direct loads.)
+                if (c1 < u.phi) prefetch_raw(c1, u.phi);
+                else prefetch_raw(nu.plo, nu.phi);
                 // ---- stage + bulk copy first: the bytes fly while the metadata is written.  (If the piece list
                 // later cuts the item short the copy has fetched a little more than needed: harmless.)
                 Stage& st = acquire_stage(item);
@@ -425,9 +442,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         }
                     }
                 }
-                producer_sync();  // difference array complete; nobody reads sm.raw any more
-                if (c1 < u.phi) prefetch_raw(c1, u.phi);   // the next item's words: this unit's next chunk ...
-                else prefetch_raw(nu.plo, nu.phi);          // ... or the next unit's first
+                producer_sync();  // difference array complete
                 {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
                     const int w0 = (KDL_TILE / W_PRODUCERS) * pw;
                     int pre_sum = 0;
@@ -536,8 +551,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
     for (long long item = 0;; ++item) {
         const int s = (int)(item % W_STAGES);
         const uint32_t parity = (uint32_t)((item / W_STAGES) & 1);
-        mbar_wait(&sm.full[s], parity);
-        mbar_wait(&sm.landed[s], parity);
+        mbar_wait(&sm.full[s], parity);  // (includes the bulk copy: see publish)
         Stage& st = sm.st[s];
         const int flags = st.flags;
         const int n_sub = st.n_sub;

@@ -137,6 +137,8 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
         }
         if (const char* ev = getenv("KDL_SPLIT")) { const int v = atoi(ev); if (v >= 1 && v <= 64) split = v; }
     }
+    bool cx_by_atomics = (batch->n_complex - batch->n_hard) * 16 < batch->n_reads;
+    if (const char* ev = getenv("KDL_CX")) cx_by_atomics = !strcmp(ev, "atomics") ? true : (!strcmp(ev, "pieces") ? false : cx_by_atomics);
     // zeroing that the chosen kernels will not do themselves: the tile kernel overwrites the weight columns of a
     // fresh table and, on request, zeroes columns 5..18 window by window in its flush
     const int zero_in_k1 = (tiled && split == 1 && fresh && n_tiles > 0 && (flags & KDL_PILEUP_ZERO_REST)) ? 1 : 0;
@@ -153,8 +155,10 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             kdl::tile_index_kernel<<<(unsigned)((n_tiles * 32 + 255) / 256), 256, 0, st>>>(*batch, tile_lo, n_tiles,
                                                                                           batch->tile_index);
             if ((rc = check_launch()) != KDL_OK) return rc;
-            // K1: the tile-owner kernel
-            const bool cx = batch->n_complex > batch->n_hard;  // tile-eligible complex reads present
+            // K1: the tile-owner kernel.  Tile-eligible complex reads go through its piece machinery (kCx) when
+            // they are a sizeable share of the batch; when they are rare (< 1/16 of the reads) the lean instantiation
+            // runs and K1e counts their bases too, with REDs
+            const bool cx = batch->n_complex > batch->n_hard && !cx_by_atomics;
             if (split > 1) {
                 rc = cx ? launch_tile<kdl::F_ATOMIC, true>(*batch, counts, n_slots, tile_lo, n_tiles, split, 0, st)
                         : launch_tile<kdl::F_ATOMIC, false>(*batch, counts, n_slots, tile_lo, n_tiles, split, 0, st);
@@ -170,7 +174,8 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
         }
         if (batch->n_complex > batch->n_hard) {  // K1e: insertions / deletions / clips of the tile-eligible complex reads
             const long long grid = (batch->n_complex + 255) / 256;
-            kdl::pileup_events_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events);
+            kdl::pileup_events_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events,
+                                                                     cx_by_atomics ? 1 : 0);
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
         if (batch->n_hard > 0) {  // K1g: the reads that may wrap or raise, atomically, after the tile stores

@@ -132,8 +132,13 @@ pileup_general_kernel(kdl_batch b, const uint32_t* __restrict__ list, long long 
 // increments per read, done here once per read with REDs: one THREAD per read walks its CIGAR (by the flatten
 // contract such a read cannot wrap an index or raise, so there are no checks), a million threads hide the
 // dependent loads.  Insertion events go to their deterministic rows.
+// with_m: also count the reads' M/=/X bases here, with REDs into the weight columns -- what kdl_pileup_range asks
+// for when tile-eligible complex reads are RARE (a few per cent of a short-read BAM): the tile kernel then runs its
+// lean instantiation and treats them as inert, and their ~130 bases each cost less as atomics than the piece
+// machinery costs every item.  (Stream order puts these REDs behind the tile kernel's plain stores.)
 __global__ void __launch_bounds__(256)
-pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots, int32_t* __restrict__ ins_events) {
+pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots, int32_t* __restrict__ ins_events,
+                     int with_m) {
     const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= b.n_complex) return;
     const long long r = (long long)b.complex_idx[j];
@@ -152,7 +157,10 @@ pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slot
         const uint32_t cg = ops[o];
         const int len = (int)(cg >> 4);
         const int op = (int)(cg & 0xF);
-        if (op == 0 || op == 7 || op == 8) {  // M = X: the tile kernel's
+        if (op == 0 || op == 7 || op == 8) {  // M = X: the tile kernel's, unless with_m
+            if (with_m)
+                for (int d = 0; d < len; ++d)
+                    atomicAdd(tab + (long long)(KDL_W_A + nib2col(nibble_at(seq, q_pos + d))) * n_slots + r_pos + d, 1);
             r_pos += len;
             q_pos += len;
         } else if (op == 1) {  // I

@@ -38,12 +38,12 @@ template <bool kCx> struct TileRegs { static constexpr int kProducer = 56, kCons
 template <bool kCx> struct TileCfg;
 template <> struct TileCfg<false> {
     static constexpr int kRmax = 512;    // reads per item
-    static constexpr int kCapW = 8576;   // words of seq4 per item (33.5 KB: ~451 reads of 150 bases)
+    static constexpr int kCapW = 9216;   // words of seq4 per item (36 KB: ~485 reads of 150 bases)
     static constexpr int kPcap = 0;      // pieces of complex reads per item
 };
 template <> struct TileCfg<true> {
     static constexpr int kRmax = 384;
-    static constexpr int kCapW = 6656;   // 26 KB
+    static constexpr int kCapW = 7168;   // 28 KB
     static constexpr int kPcap = 768;
 };
 
@@ -76,12 +76,11 @@ struct TileStage {
 template <class C>
 struct TileSmem {
     TileStage<C> st[W_STAGES];
-    int raw[2][3][C::kRmax + 4];   // producers: l_seq / ref_start / seq_off of the next item's reads (cp.async; double-
-                                   // buffered by item parity), + the word offset of the read behind them
+    int raw[3][C::kRmax];          // producers: l_seq / ref_start / seq_off of the NEXT item's reads (cp.async)
     unsigned short queue[W_CONSUMERS][64];  // consumers (kCx): indices of the pieces that overlap the warp's window
     int scan[W_PRODUCERS * 4 + 4];  // producers (kCx): per-group piece totals, cut counter
     uint64_t full[W_STAGES];       // producers -> consumers: 4 warp arrivals (metadata, pieces, coverage written)
-    uint64_t landed[W_STAGES];     // the bulk copy's bytes (1 arrival + tx): producers that explode, and the publisher
+    uint64_t landed[W_STAGES];     // the bulk copy's bytes (1 arrival + tx): consumers, and producers that explode
     uint64_t empty[W_STAGES];      // consumers -> producers: 8 warp arrivals
 };
 static_assert(sizeof(TileSmem<TileCfg<false>>) <= 113 * 1024 && sizeof(TileSmem<TileCfg<true>>) <= 113 * 1024,
@@ -139,61 +138,58 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         auto publish = [&](long long it) {  // this warp's part of the item is written
             const int s = (int)(it % W_STAGES);
             __syncwarp();
-            if (lane == 0) {
-                // producer warp 0 vouches for the bulk copy too: it arrives only after the bytes have landed (they
-                // have, long ago), so the consumers wait on ONE barrier
-                if (pw == 0) mbar_wait(&sm.landed[s], (uint32_t)((it / W_STAGES) & 1));
-                mbar_arrive(&sm.full[s]);
-            }
+            if (lane == 0) mbar_arrive(&sm.full[s]);
         };
 
         // The producers run a software pipeline of their own: while an item is prepared, the three metadata words
         // of the NEXT item's reads (the same unit's next chunk, or the next unit's first) stream into sm.raw with
-        // cp.async, together with the word offset of the read behind them -- so neither the item bounds nor the
-        // per-read metadata wait for a global load.  The index entry of the next unit's tile is loaded a unit ahead.
+        // cp.async -- each thread fetches exactly the elements it will consume, so they need no barrier -- and the
+        // index entry of the next unit's tile is loaded a unit ahead.  The few seq_off lookups that size an item are
+        // plain loads of lines the prefetch has just pulled into L1.
         constexpr int PER = W_RMAX / W_PT;  // reads per producer thread and item
-        struct Unit { uint32_t lo, hi, plo, phi, wa, wend; uint2 ic; long long cs; };  // (read indices are < 2^31)
-        auto load_unit = [&](long long w, Unit& u) {
-            if (w >= n_units) { u.lo = u.hi = u.plo = u.phi = 0; u.wa = u.wend = 0; u.ic = make_uint2(0, 0); u.cs = 0; return; }
-            const long long t = tile_lo + w / split;
-            const int part = (int)(w % split);
+        struct Unit { uint32_t lo, hi, wa, wend; uint2 ic; uint2 cs; };  // as K0 wrote it (read indices are < 2^31)
+        auto load_unit = [&](long long w, Unit& u) {  // loads only: nothing here waits for them
+            if (w >= n_units) { u.lo = u.hi = u.wa = u.wend = 0; u.ic = make_uint2(0, 0); u.cs = make_uint2(0, 0); return; }
+            const long long t = tile_lo + (split == 1 ? w : w / split);
             const uint4 ix = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * t));
-            u.ic = __ldg(reinterpret_cast<const uint2*>(tile_index + F_IDX * t + 4));
-            u.lo = ix.x;
-            u.hi = ix.y;
-            u.wa = ix.z;
-            u.wend = ix.w;
-            const long long n = (long long)u.hi - u.lo;
-            u.plo = u.lo + (uint32_t)(n * part / split);
-            u.phi = u.lo + (uint32_t)(n * (part + 1) / split);
-            u.cs = b.contig_slot[u.ic.x];
+            const uint4 iy = __ldg(reinterpret_cast<const uint4*>(tile_index + F_IDX * t + 4));
+            u.lo = ix.x; u.hi = ix.y; u.wa = ix.z; u.wend = ix.w;
+            u.ic = make_uint2(iy.x, iy.y);
+            u.cs = make_uint2(iy.z, iy.w);
         };
-        // sm.raw[pf_buf] holds (or will, once the cp.async group lands) reads [pf_start, pf_start + pf_cnt) and the
-        // seq_off of the read behind them.  The buffers alternate: an item issues the prefetch for the next one as
-        // soon as its own bounds are known, a whole item ahead of its use.
-        uint32_t pf_start = 0xFFFFFFFFu;
-        int pf_cnt = 0, pf_buf = 0;
+        auto part_of = [&](const Unit& u, long long w, uint32_t& plo, uint32_t& phi) {  // this unit's share of the tile's reads
+            if (split == 1) { plo = u.lo; phi = u.hi; return; }
+            const long long n = (long long)u.hi - u.lo;
+            const int part = (int)(w % split);
+            plo = u.lo + (uint32_t)(n * part / split);
+            phi = u.lo + (uint32_t)(n * (part + 1) / split);
+        };
+        uint32_t pf_start = 0xFFFFFFFFu;  // sm.raw holds (once this thread's cp.async group lands) reads [pf_start, + pf_cnt)
+        int pf_cnt = 0;
         auto prefetch_raw = [&](uint32_t start, uint32_t end) {
             const int cnt = end > start ? (int)(end - start < (uint32_t)W_RMAX ? end - start : (uint32_t)W_RMAX) : 0;
             pf_start = start;
             pf_cnt = cnt;
-            pf_buf ^= 1;
-            int (*raw)[W_RMAX + 4] = sm.raw[pf_buf];
             for (int i = ptid; i < cnt; i += W_PT) {
-                cp_async4(&raw[0][i], b.l_seq + start + i);
-                cp_async4(&raw[1][i], b.ref_start + start + i);
-                cp_async4(&raw[2][i], b.seq_off + start + i);
+                cp_async4(&sm.raw[0][i], b.l_seq + start + i);
+                cp_async4(&sm.raw[1][i], b.ref_start + start + i);
+                cp_async4(&sm.raw[2][i], b.seq_off + start + i);
             }
-            if (ptid == 0 && cnt > 0 && (long long)start + cnt < b.n_reads) cp_async4(&raw[2][cnt], b.seq_off + start + cnt);
         };
         Unit u, nu;
         load_unit(blockIdx.x, u);
-        prefetch_raw(u.plo, u.phi);
+        {
+            uint32_t plo, phi;
+            part_of(u, blockIdx.x, plo, phi);
+            prefetch_raw(plo, phi);
+        }
 
         for (long long w = blockIdx.x; w < n_units; w += gridDim.x) {
             load_unit(w + gridDim.x, nu);  // consumed at the end of this iteration
-            const long long tile_slot = (tile_lo + w / split) * KDL_TILE;
-            if (u.plo >= u.phi) {
+            const long long tile_slot = (tile_lo + (split == 1 ? w : w / split)) * KDL_TILE;
+            uint32_t plo, phi;
+            part_of(u, w, plo, phi);
+            if (plo >= phi) {
                 if (kFresh) {  // consumers must store zeros: a header-only item
                     Stage& st = acquire_stage(item);
                     if (ptid == 0) {
@@ -203,28 +199,23 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     publish(item);
                     ++item;
                 }
-                cp_async_wait_all();  // (two prefetches of one thread must not be in flight to the same buffer)
-                prefetch_raw(nu.plo, nu.phi);
+                cp_async_wait_all();  // (a thread never has two prefetches in flight to the same words)
+                uint32_t nplo, nphi;
+                part_of(nu, w + gridDim.x, nplo, nphi);
+                prefetch_raw(nplo, nphi);
                 u = nu;
                 continue;
             }
             const bool one_contig = u.ic.x == u.ic.y;
-            const long long slot_base = one_contig ? u.cs - tile_slot : 0;
-            uint32_t c0 = u.plo;
+            const long long slot_base = one_contig ? (long long)(((unsigned long long)u.cs.y << 32) | u.cs.x) - tile_slot : 0;
+            uint32_t c0 = plo;
             bool first = true;
-            while (c0 < u.phi) {
-                cp_async_wait_all();
-                producer_sync();  // this item's prefetched words are visible to every producer thread
+            while (c0 < phi) {
+                cp_async_wait_all();  // this thread's prefetched words have landed
                 const bool have = pf_start == c0 && pf_cnt > 0;
-                int (*raw)[W_RMAX + 4] = sm.raw[pf_buf];
-                const int have_cnt = pf_cnt;
-                uint32_t c1 = u.phi - c0 > (uint32_t)W_RMAX ? c0 + W_RMAX : u.phi;
-                if (have && c1 > c0 + have_cnt) c1 = c0 + have_cnt;
-                auto word_off = [&](uint32_t r) -> uint32_t {  // seq_off[r] (r < n_reads), from sm.raw when it is there
-                    return (have && r - c0 <= (uint32_t)have_cnt) ? (uint32_t)raw[2][r - c0] : b.seq_off[r];
-                };
-                const uint32_t wa = c0 == u.lo ? u.wa : (word_off(c0) & ~3u);
-                uint32_t wend = c1 == u.hi ? u.wend : ((long long)c1 < b.n_reads ? word_off(c1) : (uint32_t)b.seq4_words);
+                uint32_t c1 = phi - c0 > (uint32_t)W_RMAX ? c0 + W_RMAX : phi;
+                const uint32_t wa = c0 == u.lo ? u.wa : (b.seq_off[c0] & ~3u);
+                uint32_t wend = c1 == u.hi ? u.wend : ((long long)c1 < b.n_reads ? b.seq_off[c1] : (uint32_t)b.seq4_words);
                 bool skip = false;
                 while (wend - wa > (uint32_t)W_CAPW) {
                     if (c1 - c0 == 1) { skip = true; break; }  // one read too long to stage: never tile-eligible
@@ -232,7 +223,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     uint32_t n2 = (uint32_t)((unsigned long long)n * W_CAPW / (wend - wa));
                     n2 = n2 >= n ? n - 1 : (n2 < 1 ? 1 : n2);
                     c1 = c0 + n2;
-                    wend = word_off(c1);
+                    wend = b.seq_off[c1];
                 }
                 int n_sub = skip ? 0 : (int)(c1 - c0);
                 // this thread's reads of the item
@@ -242,10 +233,10 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #pragma unroll
                     for (int k = 0; k < PER; ++k) {
                         const int i = ptid + k * W_PT;
-                        const int ii = i < n_sub ? i : 0;
-                        l[k] = raw[0][ii];
-                        rs[k] = raw[1][ii];
-                        so[k] = (uint32_t)raw[2][ii];
+                        const int ii = i < n_sub ? i : ptid;  // (its own elements only: nobody else's have to be visible)
+                        l[k] = sm.raw[0][ii];
+                        rs[k] = sm.raw[1][ii];
+                        so[k] = (uint32_t)sm.raw[2][ii];
                     }
                 } else {
 #pragma unroll
@@ -257,11 +248,16 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         so[k] = b.seq_off[r];
                     }
                 }
-                // ---- the next item's words start streaming into the other buffer now: this unit's next chunk, or the
-                // next unit's first.  (Should the piece list cut this item short below, the prefetch is for the wrong
-                // reads and the next item falls back to direct loads.)
-                if (c1 < u.phi) prefetch_raw(c1, u.phi);
-                else prefetch_raw(nu.plo, nu.phi);
+                // ---- own elements are in registers: the next item's words start streaming in -- this unit's next
+                // chunk, or the next unit's first.  (Should the piece list cut this item short below, the prefetch is
+                // for the wrong reads and the next item loads directly.)
+                if (c1 < phi) {
+                    prefetch_raw(c1, phi);
+                } else {
+                    uint32_t nplo, nphi;
+                    part_of(nu, w + gridDim.x, nplo, nphi);
+                    prefetch_raw(nplo, nphi);
+                }
                 // ---- stage + bulk copy first: the bytes fly while the metadata is written.  (If the piece list
                 // later cuts the item short the copy has fetched a little more than needed: harmless.)
                 Stage& st = acquire_stage(item);
@@ -282,6 +278,11 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         st.seq[wq] = wq < avail ? b.seq4[wa + wq] : 0u;  // (visible to all after the barriers below)
                     }
                 }
+                // the stage's difference array still holds its previous item's entries (every producer thread has read
+                // them: two barriers of the item in between have passed): clean it, then a barrier, then the atomics
+                for (int k = ptid; k < (KDL_TILE + 32) / 4; k += W_PT)
+                    reinterpret_cast<int4*>(st.diff)[k] = make_int4(0, 0, 0, 0);
+                bool diff_clean = false;  // has a producer barrier passed since the stores above?
                 // ---- complex reads: where each one's pieces go (exclusive prefix in read order of: M-op count in the
                 // low 16 bits, 1 per tile-eligible complex read above), and a cut of the item if they do not fit
                 int pre[PER];
@@ -298,7 +299,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         pre[k] = 0;
                         mine |= ub[k] != 0;
                     }
-                    if (producer_sync_or(mine)) {  // (items without complex reads pay one barrier, nothing else)
+                    const bool any_cx = producer_sync_or(mine);  // (also the barrier behind the cleaning of diff)
+                    diff_clean = true;
+                    if (any_cx) {
 #pragma unroll
                         for (int k = 0; k < PER; ++k) {
                             int incl = ub[k];  // reads ptid + k * 128: group g = 4 k + pw holds 32 consecutive reads
@@ -348,7 +351,8 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         // no thread still reads the totals then)
                     }
                 }
-                const bool last = c1 >= u.phi;
+                if (!diff_clean) producer_sync();
+                const bool last = c1 >= phi;
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
                     const int i = ptid + k * W_PT;
@@ -467,9 +471,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #pragma unroll
                     for (int k = 0; k < E; ++k) { acc += v[k]; st.cov[w0 + E * lane + k] = acc; }
                 }
-                producer_sync();  // everybody has read diff: clean it for the stage's next use
-                for (int k = ptid; k < (KDL_TILE + 32) / 4; k += W_PT)
-                    reinterpret_cast<int4*>(st.diff)[k] = make_int4(0, 0, 0, 0);
                 publish(item);
                 ++item;
                 first = false;
@@ -551,7 +552,8 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
     for (long long item = 0;; ++item) {
         const int s = (int)(item % W_STAGES);
         const uint32_t parity = (uint32_t)((item / W_STAGES) & 1);
-        mbar_wait(&sm.full[s], parity);  // (includes the bulk copy: see publish)
+        mbar_wait(&sm.full[s], parity);
+        mbar_wait(&sm.landed[s], parity);
         Stage& st = sm.st[s];
         const int flags = st.flags;
         const int n_sub = st.n_sub;

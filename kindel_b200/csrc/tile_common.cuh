@@ -23,7 +23,7 @@ static_assert(F_FLUSH_BLOCKS % 2 == 1, "the counting loop folds exactly one pend
 //   [0] lo, [1] hi   index range of the reads that can touch the tile: global start slot in
 //                    [tile_lo - reach_right + 1, tile_hi + reach_left)
 //   [2] wa, [3] wend word range of their blocks in seq4 (wa rounded down to a 16-byte boundary)
-//   [4] c_lo, [5] c_hi contigs of read lo and of read hi - 1
+//   [4] c_lo, [5] c_hi contigs of read lo and of read hi - 1;  [6], [7] first slot of contig c_lo (64 bits)
 // global slot of a read's first base = contig_slot[c] + ref_start; reads are sorted by it.
 constexpr int F_IDX = 8;  // uint32 per tile in the index
 
@@ -99,10 +99,12 @@ tile_index_kernel(kdl_batch b, long long tile_lo, long long n_tiles, uint32_t* _
     e[1] = (uint32_t)hi;
     e[2] = lo < b.n_reads ? (b.seq_off[lo] & ~3u) : 0u;
     e[3] = hi < b.n_reads ? b.seq_off[hi] : (uint32_t)b.seq4_words;
-    e[4] = lo < hi ? (uint32_t)find_contig(b.contig_read_off, b.n_contigs, lo) : 0u;
+    const int c_lo = lo < hi ? find_contig(b.contig_read_off, b.n_contigs, lo) : 0;
+    e[4] = (uint32_t)c_lo;
     e[5] = lo < hi ? (uint32_t)find_contig(b.contig_read_off, b.n_contigs, hi - 1) : 0u;
-    e[6] = 0u;
-    e[7] = 0u;
+    const unsigned long long cs = lo < hi ? (unsigned long long)b.contig_slot[c_lo] : 0ull;
+    e[6] = (uint32_t)cs;          // first slot of contig c_lo: K1 then needs no dependent load for it
+    e[7] = (uint32_t)(cs >> 32);
 }
 
 // (KDL_HOST_EMU: tests/emu/ compiles this file for the host and supplies functional stand-ins for the PTX

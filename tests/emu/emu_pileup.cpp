@@ -25,8 +25,8 @@ void emu_set_schedule(int mode, unsigned long long seed) {
 }
 
 // K0 + K1 as kdl_pileup_range launches them.  mode: 0 = F_STORE (weight columns hold garbage), 1 = F_ADD,
-// 2 = F_ATOMIC (`split` CTAs share a tile; the table must be zero or hold counts to add to).  cx: the kCx
-// instantiation (piece lists for tile-eligible complex reads).  All pointers are HOST pointers; `counts` is
+// 2 = F_ATOMIC (`split` CTAs share a tile; the table must be zero or hold counts to add to).  cx: 1 = the kCx
+// instantiation (piece lists for tile-eligible complex reads), 0 = the lean one with K1e counting their bases too.  All pointers are HOST pointers; `counts` is
 // int32 [KDL_NCOL][n_slots]; tile_index is scratch of 8 words per tile of the whole slot space.
 // Returns 0, or 1 with emu_last_error() set.
 int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint32_t* tile_index, long long tile_lo,
@@ -47,7 +47,7 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
     }
     if (!err && b.n_complex > b.n_hard)  // K1e: the sparse updates of the tile-eligible complex reads
         err = emu::launch((unsigned)((b.n_complex + 255) / 256), 256,
-                          [&] { kdl::pileup_events_kernel(b, counts, n_slots, ins_events); });
+                          [&] { kdl::pileup_events_kernel(b, counts, n_slots, ins_events, cx ? 0 : 1); });
     if (err) {
         snprintf(g_error, sizeof g_error, "%s", err);
         return 1;

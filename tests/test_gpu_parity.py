@@ -449,6 +449,31 @@ def mixed_reads(seed, L, depth, complex_frac):
     return synth.mixed_reads(seed, [L], depth, complex_frac)
 
 
+@pytest.mark.parametrize("mode", ["atomics", "pieces"])
+def test_complex_read_modes(monkeypatch, mode):
+    """Tile-eligible complex reads either way kdl_pileup_range can take them (it picks by their share of the batch;
+    KDL_CX forces one): as masked pieces through K1's bit-sliced counters, or -- when rare -- with K1 treating them
+    as inert and K1e counting their bases with REDs.  Fresh-table mode included (CountTable)."""
+    import torch
+
+    from kindel_b200 import engine, synth
+    from oracle import coracle
+
+    monkeypatch.setenv("KDL_CX", mode)
+    for b in (mixed_reads(79, 400_000, 150, 0.05), synth.complex_reads(72, 30_000, 400), mixed_reads(80, 300_000, 40, 0.5)):
+        _against_oracle(b)
+        db = engine.upload(b)
+        table = engine.CountTable(b.n_slots, db.device)
+        table.t.fill_(7)                       # garbage everywhere: the first pileup must overwrite / zero it all
+        table.dirty, table.dirty_rest = (0, b.n_slots), True
+        for _ in range(2):
+            counts, events = engine.pileup(db, table=table)
+        torch.cuda.synchronize()
+        oc, oe = coracle.pileup(b)
+        np.testing.assert_array_equal(counts.cpu().numpy(), oc)
+        np.testing.assert_array_equal(events.cpu().numpy(), oe)
+
+
 @pytest.mark.parametrize("split", [2, 7])
 def test_depth_split_of_small_references(monkeypatch, split):
     """Fewer tiles than CTA slots: `split` CTAs share a tile by read range and flush with REDs (kdl_pileup_range

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import emu_harness as E
+from kindel_b200 import distributed as D
 from kindel_b200 import synth
 from oracle import coracle
 
@@ -55,6 +56,19 @@ CX_CASES = {
     "cfg3_deep":    lambda: synth.complex_reads(91, 1500, 900, edge_tail=False),  # piece list overflows: items are cut
     "long_complex": lambda: synth.complex_reads(92, 9000, 30, read_len=900, edge_tail=False),
 }
+
+
+@pytest.mark.parametrize("name", list(CX_CASES) + ["mixed"])
+def test_rare_complex_reads_by_atomics(name):
+    """The other way kdl_pileup_range handles tile-eligible complex reads (when they are rare): the lean K1 treats them
+    as inert and K1e counts their M/=/X bases too, with REDs behind the tile stores."""
+    batch = synth.mixed_reads(93, [9000, 4000], 80, 0.05) if name == "mixed" else CX_CASES[name]()
+    want_c, want_e = coracle.pileup(batch)
+    hard = D.select_reads(batch, batch.hard_idx)
+    wh = coracle.pileup(hard)[0] if batch.n_hard else 0
+    for mode in (E.F_ADD, E.F_STORE):
+        got, ev = E.run_pileup(batch, mode, cx=False, want_events=True, zero_rest=mode == E.F_STORE)
+        np.testing.assert_array_equal(got, want_c - wh)
 
 
 @pytest.mark.parametrize("split", [1, 3])

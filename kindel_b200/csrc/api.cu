@@ -173,7 +173,7 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
         if (batch->n_complex > batch->n_hard) {  // K1e: insertions / deletions / clips of the tile-eligible complex reads
-            const long long grid = (batch->n_complex + 255) / 256;
+            const long long grid = (batch->n_complex + 7) / 8;  // one warp per complex read
             kdl::pileup_events_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events,
                                                                      cx_by_atomics ? 1 : 0);
             if ((rc = check_launch()) != KDL_OK) return rc;

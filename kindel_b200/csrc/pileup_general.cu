@@ -129,9 +129,11 @@ pileup_general_kernel(kdl_batch b, const uint32_t* __restrict__ list, long long 
 // ---- K1e: the sparse updates of the TILE-ELIGIBLE complex reads ------------------------------------------
 // The tile kernel counts these reads' M/=/X bases (pileup_tile.cu); what is left of the reference's loop --
 // insertions (kindel.py:55-58), deletions (:59-62), clip counts and clip bases (:64-81) -- is a handful of
-// increments per read, done here once per read with REDs: one THREAD per read walks its CIGAR (by the flatten
-// contract such a read cannot wrap an index or raise, so there are no checks), a million threads hide the
-// dependent loads.  Insertion events go to their deterministic rows.
+// increments per read, done here once per read with REDs.  One WARP per read: the op word is a uniform load, the
+// lanes stride over the op's bases, so a clip's (or, with_m, a match segment's) 32 consecutive slots are one
+// coalesced RED instruction.  By the flatten contract such a read cannot wrap an index or raise: no checks.
+// Insertion events go to their deterministic rows.
+//
 // with_m: also count the reads' M/=/X bases here, with REDs into the weight columns -- what kdl_pileup_range asks
 // for when tile-eligible complex reads are RARE (a few per cent of a short-read BAM): the tile kernel then runs its
 // lean instantiation and treats them as inert, and their ~130 bases each cost less as atomics than the piece
@@ -139,13 +141,15 @@ pileup_general_kernel(kdl_batch b, const uint32_t* __restrict__ list, long long 
 __global__ void __launch_bounds__(256)
 pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots, int32_t* __restrict__ ins_events,
                      int with_m) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per listed read
     if (j >= b.n_complex) return;
     const long long r = (long long)b.complex_idx[j];
     const uint32_t lraw = (uint32_t)b.l_seq[r];
     if ((lraw & (KDL_COMPLEX | KDL_HARD)) != KDL_COMPLEX) return;  // hard reads: K1g walks all of their ops
     const int c = find_contig(b.contig_read_off, b.n_contigs, r);
-    int32_t* __restrict__ tab = counts + b.contig_slot[c];  // column 0 at this contig's first slot
+    const long long slot0 = b.contig_slot[c];
+    int32_t* __restrict__ tab = counts + slot0;  // column 0 at this contig's first slot
     const uint32_t* __restrict__ seq = b.seq4 + (size_t)b.seq_off[r];
     const uint32_t* __restrict__ blk = seq + (((lraw & KDL_LEN_MASK) + 7) >> 3);  // [n_ops][evt_off][ops...]
     const int n_ops = (int)blk[0];
@@ -159,30 +163,32 @@ pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slot
         const int op = (int)(cg & 0xF);
         if (op == 0 || op == 7 || op == 8) {  // M = X: the tile kernel's, unless with_m
             if (with_m)
-                for (int d = 0; d < len; ++d)
+                for (int d = lane; d < len; d += 32)
                     atomicAdd(tab + (long long)(KDL_W_A + nib2col(nibble_at(seq, q_pos + d))) * n_slots + r_pos + d, 1);
             r_pos += len;
             q_pos += len;
         } else if (op == 1) {  // I
-            atomicAdd(tab + (long long)KDL_INS * n_slots + r_pos, 1);
-            if (ins_events)
-                reinterpret_cast<int4*>(ins_events)[evt] = make_int4((int)(b.contig_slot[c] + r_pos), (int)r, q_pos, len);
+            if (lane == 0) {
+                atomicAdd(tab + (long long)KDL_INS * n_slots + r_pos, 1);
+                if (ins_events)
+                    reinterpret_cast<int4*>(ins_events)[evt] = make_int4((int)(slot0 + r_pos), (int)r, q_pos, len);
+            }
             evt += 1;
             q_pos += len;
         } else if (op == 2) {  // D
-            for (int d = 0; d < len; ++d) atomicAdd(tab + (long long)KDL_DEL * n_slots + r_pos + d, 1);
+            for (int d = lane; d < len; d += 32) atomicAdd(tab + (long long)KDL_DEL * n_slots + r_pos + d, 1);
             r_pos += len;
         } else if (op == 4) {  // S
             if (o == 0) {      // left clip: its bases end where the read starts
-                atomicAdd(tab + (long long)KDL_CLIP_ENDS * n_slots + r_pos, 1);
-                for (int g = 0; g < len; ++g) {
+                if (lane == 0) atomicAdd(tab + (long long)KDL_CLIP_ENDS * n_slots + r_pos, 1);
+                for (int g = lane; g < len; g += 32) {
                     const long long rel = r_pos - len + g;
                     if (rel >= 0) atomicAdd(tab + (long long)(KDL_CEW_A + nib2col(nibble_at(seq, g))) * n_slots + rel, 1);
                 }
                 q_pos += len;
             } else {           // right clip (never reaches the contig end for these reads)
-                atomicAdd(tab + (long long)KDL_CLIP_STARTS * n_slots + r_pos - 1, 1);
-                for (int d = 0; d < len; ++d)
+                if (lane == 0) atomicAdd(tab + (long long)KDL_CLIP_STARTS * n_slots + r_pos - 1, 1);
+                for (int d = lane; d < len; d += 32)
                     atomicAdd(tab + (long long)(KDL_CSW_A + nib2col(nibble_at(seq, q_pos + d))) * n_slots + r_pos + d, 1);
                 r_pos += len;
                 q_pos += len;

@@ -173,9 +173,12 @@ int kdl_pileup_range(const kdl_batch* batch, int32_t* counts, int64_t n_slots, i
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
         if (batch->n_complex > batch->n_hard) {  // K1e: insertions / deletions / clips of the tile-eligible complex reads
-            const long long grid = (batch->n_complex + 7) / 8;  // one warp per complex read
-            kdl::pileup_events_kernel<<<(unsigned)grid, 256, 0, st>>>(*batch, counts, n_slots, ins_events,
-                                                                     cx_by_atomics ? 1 : 0);
+            if (cx_by_atomics)  // their bases too: 8 lanes per read
+                kdl::pileup_events_kernel<8><<<(unsigned)((batch->n_complex + 31) / 32), 256, 0, st>>>(
+                    *batch, counts, n_slots, ins_events, 1);
+            else                // a few scattered REDs per read: one thread per read
+                kdl::pileup_events_kernel<1><<<(unsigned)((batch->n_complex + 255) / 256), 256, 0, st>>>(
+                    *batch, counts, n_slots, ins_events, 0);
             if ((rc = check_launch()) != KDL_OK) return rc;
         }
         if (batch->n_hard > 0) {  // K1g: the reads that may wrap or raise, atomically, after the tile stores

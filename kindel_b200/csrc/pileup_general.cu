@@ -129,20 +129,25 @@ pileup_general_kernel(kdl_batch b, const uint32_t* __restrict__ list, long long 
 // ---- K1e: the sparse updates of the TILE-ELIGIBLE complex reads ------------------------------------------
 // The tile kernel counts these reads' M/=/X bases (pileup_tile.cu); what is left of the reference's loop --
 // insertions (kindel.py:55-58), deletions (:59-62), clip counts and clip bases (:64-81) -- is a handful of
-// increments per read, done here once per read with REDs.  One WARP per read: the op word is a uniform load, the
-// lanes stride over the op's bases, so a clip's (or, with_m, a match segment's) 32 consecutive slots are one
-// coalesced RED instruction.  By the flatten contract such a read cannot wrap an index or raise: no checks.
-// Insertion events go to their deterministic rows.
+// increments per read, done here once per read with REDs.  By the flatten contract such a read cannot wrap an index
+// or raise: no checks.  Insertion events go to their deterministic rows.
 //
 // with_m: also count the reads' M/=/X bases here, with REDs into the weight columns -- what kdl_pileup_range asks
 // for when tile-eligible complex reads are RARE (a few per cent of a short-read BAM): the tile kernel then runs its
 // lean instantiation and treats them as inert, and their ~130 bases each cost less as atomics than the piece
 // machinery costs every item.  (Stream order puts these REDs behind the tile kernel's plain stores.)
+// kLanes threads per read, striding over an op's bases.  1: 32 reads per warp instruction -- the cheapest way through
+// the op loops when the updates are a few scattered REDs per read (a million threads hide the dependent loads).
+// 8: what with_m (130 bases per read, few reads) wants -- 8 consecutive slots per RED, four reads' load chains in
+// flight per warp.
+template <int kLanes>
 __global__ void __launch_bounds__(256)
 pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots, int32_t* __restrict__ ins_events,
                      int with_m) {
-    const int lane = threadIdx.x & 31;
-    const long long j = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per listed read
+    const int lane = (int)(threadIdx.x % kLanes);
+    constexpr int kStep = kLanes;
+    const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j = gtid / kLanes;
     if (j >= b.n_complex) return;
     const long long r = (long long)b.complex_idx[j];
     const uint32_t lraw = (uint32_t)b.l_seq[r];
@@ -163,7 +168,7 @@ pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slot
         const int op = (int)(cg & 0xF);
         if (op == 0 || op == 7 || op == 8) {  // M = X: the tile kernel's, unless with_m
             if (with_m)
-                for (int d = lane; d < len; d += 32)
+                for (int d = lane; d < len; d += kStep)
                     atomicAdd(tab + (long long)(KDL_W_A + nib2col(nibble_at(seq, q_pos + d))) * n_slots + r_pos + d, 1);
             r_pos += len;
             q_pos += len;
@@ -176,19 +181,19 @@ pileup_events_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slot
             evt += 1;
             q_pos += len;
         } else if (op == 2) {  // D
-            for (int d = lane; d < len; d += 32) atomicAdd(tab + (long long)KDL_DEL * n_slots + r_pos + d, 1);
+            for (int d = lane; d < len; d += kStep) atomicAdd(tab + (long long)KDL_DEL * n_slots + r_pos + d, 1);
             r_pos += len;
         } else if (op == 4) {  // S
             if (o == 0) {      // left clip: its bases end where the read starts
                 if (lane == 0) atomicAdd(tab + (long long)KDL_CLIP_ENDS * n_slots + r_pos, 1);
-                for (int g = lane; g < len; g += 32) {
+                for (int g = lane; g < len; g += kStep) {
                     const long long rel = r_pos - len + g;
                     if (rel >= 0) atomicAdd(tab + (long long)(KDL_CEW_A + nib2col(nibble_at(seq, g))) * n_slots + rel, 1);
                 }
                 q_pos += len;
             } else {           // right clip (never reaches the contig end for these reads)
                 if (lane == 0) atomicAdd(tab + (long long)KDL_CLIP_STARTS * n_slots + r_pos - 1, 1);
-                for (int d = lane; d < len; d += 32)
+                for (int d = lane; d < len; d += kStep)
                     atomicAdd(tab + (long long)(KDL_CSW_A + nib2col(nibble_at(seq, q_pos + d))) * n_slots + r_pos + d, 1);
                 r_pos += len;
                 q_pos += len;

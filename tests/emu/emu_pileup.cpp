@@ -45,9 +45,12 @@ int emu_pileup(const kdl_batch* batch, int32_t* counts, long long n_slots, uint3
 #undef KDL_EMU_TILE
         });
     }
-    if (!err && b.n_complex > b.n_hard)  // K1e: the sparse updates of the tile-eligible complex reads
-        err = emu::launch((unsigned)((b.n_complex + 7) / 8), 256,
-                          [&] { kdl::pileup_events_kernel(b, counts, n_slots, ins_events, cx ? 0 : 1); });
+    if (!err && b.n_complex > b.n_hard) {  // K1e: the sparse updates of the tile-eligible complex reads
+        if (cx) err = emu::launch((unsigned)((b.n_complex + 255) / 256), 256,
+                                  [&] { kdl::pileup_events_kernel<1>(b, counts, n_slots, ins_events, 0); });
+        else err = emu::launch((unsigned)((b.n_complex + 31) / 32), 256,
+                               [&] { kdl::pileup_events_kernel<8>(b, counts, n_slots, ins_events, 1); });
+    }
     if (err) {
         snprintf(g_error, sizeof g_error, "%s", err);
         return 1;

@@ -1,4 +1,4 @@
-"""The offline kernel tools (tools/) keep working: static SASS cost model, SASS comparison, ncu phase budget.
+"""The offline kernel tools (tools/) keep working: opcode census of the built library, per-source-line ncu budget.
 They need the CUDA toolkit's cuobjdump / nvdisasm / ncu but no GPU."""
 import os
 import shutil
@@ -18,10 +18,23 @@ def _run(*args):
 
 
 @pytest.mark.skipif(shutil.which("ncu") is None, reason="needs ncu")
-def test_ncu_regions_on_a_saved_report():
-    rep = os.path.join(ROOT, "gpurun_out", "prof_k1f_final.ncu-rep")
-    if not os.path.exists(rep):
+def test_ncu_lines_on_a_saved_report():
+    import glob
+
+    reps = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "r02*_k1_*.ncu-rep")))
+    if not reps:
         pytest.skip("no saved ncu report in gpurun_out/ (scratch, not committed)")
-    res = _run("tools/ncu_regions.py", rep)
+    res = _run("tools/ncu_lines.py", reps[-1], "10")
     assert res.returncode == 0, res.stderr
-    assert "MAIN LOOP" in res.stdout and "per-read metadata" in res.stdout
+    assert "executed warp instructions" in res.stdout and "pileup_tile.cu" in res.stdout
+
+
+def test_opcode_census_proves_the_design_claims():
+    res = _run("tools/opcode_census.py")
+    assert res.returncode == 0, res.stderr
+    tile = [ln for ln in res.stdout.splitlines() if "pileup_tile_kernel" in ln]
+    assert len(tile) == 6 and "sm_100a" in res.stdout
+    for ln in tile:  # total, UBLKCP, SYNCS, LDGSTS, USETMAXREG ... UTCMMA, HMMA
+        f = ln.split()
+        nums = [int(x) for x in f[-18:]]
+        assert nums[1] >= 1 and nums[2] >= 10 and nums[3] >= 10 and nums[4] == 2 and nums[-1] == 0 and nums[-2] == 0

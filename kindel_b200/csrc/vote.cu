@@ -130,9 +130,13 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(Exchange x, int ep
     if (threadIdx.x == 0)
         while (ld_acquire_sys(x.done_local + p) < epoch) __nanosleep(32);
     __syncthreads();
-    const long long lo = x.slice_lo[p], n16 = (x.slice_hi[p] - lo) >> 4;  // slices are multiples of 16 here
-    const uint4* src = reinterpret_cast<const uint4*>(x.calls[p] + lo);
-    uint4* dst = reinterpret_cast<uint4*>(x.calls[x.rank] + lo);
+    // the peer's slice [lo, hi) (multiples of 4): 16-byte vector copies over its 16-aligned middle, bytes at the rims
+    const long long lo = x.slice_lo[p], hi = x.slice_hi[p];
+    long long a16 = (lo + 15) & ~15ll, b16 = hi & ~15ll;
+    if (a16 > b16) a16 = b16 = hi;  // (a slice shorter than one vector: bytes only; lo..hi below)
+    const long long n16 = (b16 - a16) >> 4;
+    const uint4* src = reinterpret_cast<const uint4*>(x.calls[p] + a16);
+    uint4* dst = reinterpret_cast<uint4*>(x.calls[x.rank] + a16);
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; v + 3 * stride < n16; v += 4 * stride) {  // four NVLink reads in flight per thread
@@ -140,15 +144,13 @@ __global__ void __launch_bounds__(256) exchange_gather_kernel(Exchange x, int ep
         dst[v] = a0; dst[v + stride] = a1; dst[v + 2 * stride] = a2; dst[v + 3 * stride] = a3;
     }
     for (; v < n16; v += stride) dst[v] = src[v];
-    const long long tail0 = lo + (n16 << 4);
-    if (blockIdx.x == 0)
-        for (long long s = tail0 + threadIdx.x; s < x.slice_hi[p]; s += blockDim.x) x.calls[x.rank][s] = x.calls[p][s];
+    if (blockIdx.x == 0) {
+        const long long head_end = a16 < hi ? a16 : hi;
+        for (long long s = lo + threadIdx.x; s < head_end; s += blockDim.x) x.calls[x.rank][s] = x.calls[p][s];
+        for (long long s = (b16 > head_end ? b16 : head_end) + threadIdx.x; s < hi; s += blockDim.x) x.calls[x.rank][s] = x.calls[p][s];
+    }
 }
 
-// K2x.  Every CTA takes ONE contiguous chunk of the rank's slot slice and waits only for the peers whose
-// footprint reaches into that chunk: with coordinate-block shards and slices cut along the footprints that is
-// nobody for the core of the slice (those CTAs run at the speed of the plain vote, straight after the rank's own
-// pileup) and one neighbour for the halo chunks.
 __global__ void __launch_bounds__(256)
 vote_exchange_kernel(Exchange x, long long n_slots, long long min_depth_ceil, int epoch) {
     // this kernel runs after the rank's pileup kernels in stream order, so its own table is complete:

@@ -116,13 +116,19 @@ def footprint(batch: bamio.ReadBatch, align: int = 4):
     reach = np.maximum(lseq, span) + 2
     lo = int((gstart - reach).min())
     hi = int((gstart + reach).max()) + 1
-    # Python negative indices wrap to the END of the contig (POS == 0, or clip_starts[r_pos - 1]
-    # of a non-first S at r_pos == 0): only KDL_HARD reads can do that, and their exact reach is not modelled
-    # here -- a shard holding any hard read that starts within `reach` of its contig's start claims everything
+    # nothing a read does leaves its contig's slots [slot_c, slot_c + L_c] (a Python negative index wraps INSIDE the
+    # contig's own lists): the footprint lies within the contigs that have reads here
+    have = np.flatnonzero(per_contig > 0)
+    c_lo = int(batch.contig_slot[have[0]])
+    c_hi = int(batch.contig_slot[have[-1]]) + int(batch.contig_len[have[-1]]) + 1
+    # wrapping (POS == 0, or clip_starts[r_pos - 1] of a non-first S at r_pos == 0) reaches the END of the contig:
+    # only KDL_HARD reads can do that, and their exact reach is not modelled here -- a shard holding a hard read that
+    # starts within `reach` of its contig's start claims all of its contigs
     if batch.n_hard:
         h = batch.hard_idx.astype(np.int64)
         if (batch.ref_start[h].astype(np.int64) - reach[h] < 0).any():
-            return 0, int(batch.n_slots)
+            lo, hi = c_lo, c_hi
+    lo, hi = max(lo, c_lo), min(hi, c_hi)
     lo = max(0, lo) // align * align
     hi = min(int(batch.n_slots), (hi + align - 1) // align * align)
     return lo, hi
@@ -147,7 +153,10 @@ def footprint_slices(feet, n_slots: int, align: int = 64):
         return owner_slices(n_slots, world, 512)
     bounds = [0]  # bounds[k] .. bounds[k + 1] = slice of the k-th live shard
     for a, b in zip(live, live[1:]):
-        mid = (feet[a][1] + feet[b][0]) // 2 // align * align
+        if feet[a][1] <= feet[b][0] + 4:  # disjoint (whole contigs per rank): cut exactly where b starts
+            mid = feet[b][0] // 4 * 4
+        else:
+            mid = (feet[a][1] + feet[b][0]) // 2 // align * align
         bounds.append(min(max(mid, bounds[-1]), n_slots))
     bounds.append(n_slots)
     out, k = [], 0

@@ -81,3 +81,41 @@ def test_shards_partition_the_reads():
         sl = D.owner_slices(full.n_slots, w)
         assert sl[0][0] == 0 and sl[-1][1] == full.n_slots
         assert all(a[1] == b[0] for a, b in zip(sl, sl[1:])) and all(lo % 512 == 0 for lo, _ in sl)
+
+
+def test_plans_partitions_and_event_merge():
+    """Host logic of the public multi-GPU entry: plan choice, whole-contig partition, slices cut along footprints,
+    and the merge of per-shard insertion events back into the single-GPU order."""
+    multi = synth.mixed_reads(11, [3000, 5000, 2500, 4000, 3500, 4500], 25, 0.3)
+    single = synth.complex_reads(12, 6000, 80)
+    assert D.choose_plan(multi, 2) == "contigs" and D.choose_plan(multi, 8) == "reads" and D.choose_plan(single, 2) == "reads"
+    want_c, want_e = coracle.pileup(multi)
+    for world, plan in ((2, "contigs"), (3, "contigs"), (3, "reads")):
+        idx = [D.shard_indices(multi, r, world, plan) for r in range(world)]
+        assert sorted(np.concatenate(idx).tolist()) == list(range(multi.n_reads))
+        shards = [D.select_reads(multi, i) for i in idx]
+        tabs, evs = zip(*(coracle.pileup(s) for s in shards))
+        np.testing.assert_array_equal(sum(t.astype(np.int64) for t in tabs), want_c)
+        np.testing.assert_array_equal(D.merge_events(evs, idx), want_e)
+        feet = [D.footprint(s) for s in shards]
+        for (lo, hi), t in zip(feet, tabs):
+            assert not t[:, :lo].any() and not t[:, hi:].any()
+        sl = D.footprint_slices(feet, multi.n_slots)
+        assert sl[0][0] == 0 and sl[-1][1] == multi.n_slots and all(a[1] == b[0] for a, b in zip(sl, sl[1:]))
+        if plan == "contigs":  # nothing is shared: every slice's slots are covered by its own table only
+            for r, (a, b) in enumerate(sl):
+                others = sum(tabs[p][:, a:b].astype(np.int64) for p in range(world) if p != r)
+                assert not np.any(others)
+    assert D.footprint_slices([(0, 0), (0, 0)], 4096) == D.owner_slices(4096, 2)
+
+
+def test_batch_save_load_roundtrip(tmp_path):
+    from kindel_b200 import bamio
+
+    b = synth.complex_reads(13, 4000, 30)
+    bamio.save_batch(str(tmp_path / "b"), b)
+    back = bamio.load_batch(str(tmp_path / "b"))
+    for f in bamio._SAVE_FIELDS:
+        np.testing.assert_array_equal(getattr(back, f), getattr(b, f), err_msg=f)
+    assert back.contig_names == b.contig_names and back.n_events == b.n_events and back.reach_right == b.reach_right
+    np.testing.assert_array_equal(coracle.pileup(back)[0], coracle.pileup(b)[0])

@@ -44,7 +44,7 @@ template <> struct TileCfg<false> {
 template <> struct TileCfg<true> {
     static constexpr int kRmax = 384;
     static constexpr int kCapW = 7168;   // 28 KB
-    static constexpr int kPcap = 768;
+    static constexpr int kPcap = 672;
 };
 
 enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
@@ -64,20 +64,23 @@ struct TileStage {
     // covers nothing (what idle lanes of a block read).
     int4 px[C::kPcap + 1];
     int gs[C::kRmax + 32];       // start slot relative to the tile (all reads: the array stays sorted)
-    int cov[KDL_TILE];           // reads / pieces of THIS item covering each slot
-    int diff[KDL_TILE + 32];     // producers only: +1 at a piece's first slot, -1 behind its last
+    // +1 at a piece's first slot, -1 behind its last.  Two of them, alternating by the stage's use count (`dz`):
+    // while an item's atomics go to one, the other -- which the consumers finished reading two items ago -- is
+    // cleaned, so the producers need no barrier between cleaning and counting (the full / empty mbarriers order it)
+    int diff[2][KDL_TILE + 32];
     long long tile_slot;
     int n_sub;
     int flags;
     int n_px;
-    int pad;
+    int dz;                      // which diff this item uses
 };
 
 template <class C>
 struct TileSmem {
     TileStage<C> st[W_STAGES];
     int raw[3][C::kRmax];          // producers: l_seq / ref_start / seq_off of the NEXT item's reads (cp.async)
-    unsigned short queue[W_CONSUMERS][64];  // consumers (kCx): indices of the pieces that overlap the warp's window
+    int cov[W_CONSUMERS][F_WIN];   // consumers: coverage of the warp's window by the current item (private per warp)
+    unsigned short queue[W_CONSUMERS][C::kPcap ? 64 : 4];  // consumers (kCx): indices of the pieces that overlap the warp's window
     int scan[W_PRODUCERS * 4 + 4];  // producers (kCx): per-group piece totals, cut counter
     uint64_t full[W_STAGES];       // producers -> consumers: 4 warp arrivals (metadata, pieces, coverage written)
     uint64_t landed[W_STAGES];     // the bulk copy's bytes (1 arrival + tx): consumers, and producers that explode
@@ -87,6 +90,7 @@ static_assert(sizeof(TileSmem<TileCfg<false>>) <= 113 * 1024 && sizeof(TileSmem<
               "K1 must fit two CTAs per SM");
 static_assert(offsetof(TileStage<TileCfg<false>>, diff) % 16 == 0 && sizeof(TileStage<TileCfg<false>>) % 16 == 0 &&
               offsetof(TileStage<TileCfg<true>>, diff) % 16 == 0 && sizeof(TileStage<TileCfg<true>>) % 16 == 0 &&
+              (sizeof(int) * (KDL_TILE + 32)) % 16 == 0 &&
               offsetof(TileStage<TileCfg<true>>, px) % 16 == 0 && offsetof(TileStage<TileCfg<true>>, meta) % 16 == 0,
               "128-bit shared loads of the difference array, the metadata and the pieces");
 
@@ -117,7 +121,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         }
     }
     for (int s = 0; s < W_STAGES; ++s) {
-        for (int k = tid; k < KDL_TILE + 32; k += W_THREADS) sm.st[s].diff[k] = 0;
+        for (int k = tid; k < 2 * (KDL_TILE + 32); k += W_THREADS) (&sm.st[s].diff[0][0])[k] = 0;
         if (tid == 0) sm.st[s].px[W_PCAP] = make_int4(0x10000000, (int)smem_u32(sm.st[s].seq), 0, 0);
     }
     if (tid < W_PRODUCERS * 4 + 4) sm.scan[tid] = 0;
@@ -129,6 +133,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         const int pw = warp - W_CONSUMERS;          // 0..3
         const int ptid = tid - 32 * W_CONSUMERS;    // 0..127
         long long item = 0;
+        int stage_uses = 0;  // bit s: parity of the real (non-empty) items stage s has carried
         auto acquire_stage = [&](long long it) -> Stage& {
             const int s = (int)(it % W_STAGES);
             const uint32_t round = (uint32_t)(it / W_STAGES);
@@ -278,11 +283,13 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         st.seq[wq] = wq < avail ? b.seq4[wa + wq] : 0u;  // (visible to all after the barriers below)
                     }
                 }
-                // the stage's difference array still holds its previous item's entries (every producer thread has read
-                // them: two barriers of the item in between have passed): clean it, then a barrier, then the atomics
+                // this item's atomics go to diff[dz]; the other array still holds the stage's previous item's entries,
+                // which the consumers have finished with (they released the stage): clean it for the stage's next use
+                const int dz = (stage_uses >> stage_id) & 1;  // alternates per REAL item of the stage (header-only items skip)
+                stage_uses ^= 1 << stage_id;
+                int* diff = st.diff[dz];
                 for (int k = ptid; k < (KDL_TILE + 32) / 4; k += W_PT)
-                    reinterpret_cast<int4*>(st.diff)[k] = make_int4(0, 0, 0, 0);
-                bool diff_clean = false;  // has a producer barrier passed since the stores above?
+                    reinterpret_cast<int4*>(st.diff[dz ^ 1])[k] = make_int4(0, 0, 0, 0);
                 // ---- complex reads: where each one's pieces go (exclusive prefix in read order of: M-op count in the
                 // low 16 bits, 1 per tile-eligible complex read above), and a cut of the item if they do not fit
                 int pre[PER];
@@ -299,9 +306,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         pre[k] = 0;
                         mine |= ub[k] != 0;
                     }
-                    const bool any_cx = producer_sync_or(mine);  // (also the barrier behind the cleaning of diff)
-                    diff_clean = true;
-                    if (any_cx) {
+                    if (producer_sync_or(mine)) {  // (items without complex reads pay one barrier, nothing else)
 #pragma unroll
                         for (int k = 0; k < PER; ++k) {
                             int incl = ub[k];  // reads ptid + k * 128: group g = 4 k + pw holds 32 consecutive reads
@@ -351,7 +356,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         // no thread still reads the totals then)
                     }
                 }
-                if (!diff_clean) producer_sync();
                 const bool last = c1 >= phi;
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
@@ -371,8 +375,8 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         if (l[k] > 0) {  // simple read (bit 31 clear)
                             const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
                             if (cs < ce) {
-                                atomicAdd(st.diff + cs, 1);
-                                atomicAdd(st.diff + ce, -1);
+                                atomicAdd(diff + cs, 1);
+                                atomicAdd(diff + ce, -1);
                             }
                             en = make_int4(((gs + 7) >> 3) << 2, raddr, ((l[k] + 7) >> 3) << 2, ((-gs) & 7) << 2);
                         } else if (kCx && (lw & KDL_HARD) == 0) {
@@ -397,6 +401,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     st.tile_slot = tile_slot;
                     st.n_sub = n_sub;
                     st.n_px = n_px;
+                    st.dz = dz;
                     st.flags = (first ? ITEM_FIRST : 0) | (last ? ITEM_LAST : 0);
                 }
                 if constexpr (kCx) {
@@ -425,8 +430,8 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                                     const int s0 = r < 0 ? 0 : r, s1 = r + len > KDL_TILE ? KDL_TILE : r + len;
                                     if (s0 < s1) {
                                         const int v = r - q;  // slot of the read's base 0
-                                        atomicAdd(st.diff + s0, 1);
-                                        atomicAdd(st.diff + s1, -1);
+                                        atomicAdd(diff + s0, 1);
+                                        atomicAdd(diff + s1, -1);
                                         st.px[pos++] = make_int4(((v + 7) >> 3) << 2, en.y, nbw << 2,
                                                                  (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
                                     }
@@ -445,31 +450,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             while (pos < pend) st.px[pos++] = make_int4(0x10000000, (int)seq_base, 0, 0);  // covers nothing
                         }
                     }
-                }
-                producer_sync();  // difference array complete
-                {   // coverage: producer warp pw scans slots [128 pw, 128 pw + 128)
-                    const int w0 = (KDL_TILE / W_PRODUCERS) * pw;
-                    int pre_sum = 0;
-                    for (int k = 4 * lane; k < w0; k += 128) {  // w0 is a multiple of 128, diff is 16-byte aligned
-                        const int4 v4 = *reinterpret_cast<const int4*>(st.diff + k);
-                        pre_sum += (v4.x + v4.y) + (v4.z + v4.w);
-                    }
-#pragma unroll
-                    for (int d = 16; d; d >>= 1) pre_sum += __shfl_xor_sync(0xffffffffu, pre_sum, d);
-                    constexpr int E = KDL_TILE / W_PRODUCERS / 32;  // entries per lane
-                    int v[E];
-                    int run = 0;
-#pragma unroll
-                    for (int k = 0; k < E; ++k) { v[k] = st.diff[w0 + E * lane + k]; run += v[k]; }
-                    int incl = run;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int o = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += o;
-                    }
-                    int acc = pre_sum + incl - run;
-#pragma unroll
-                    for (int k = 0; k < E; ++k) { acc += v[k]; st.cov[w0 + E * lane + k] = acc; }
                 }
                 publish(item);
                 ++item;
@@ -564,9 +544,29 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             blocks_since_flush = 0;  // (already 0 after the previous tile's final flush)
         }
         if (n_sub > 0) {
-            {
-                const int4 ca = *reinterpret_cast<const int4*>(st.cov + wlo + 8 * (lane & 7));
-                const int4 cb = *reinterpret_cast<const int4*>(st.cov + wlo + 8 * (lane & 7) + 4);
+            {   // coverage of this warp's 64 slots by the item's reads / pieces: prefix sum of its difference array
+                const int* diff = st.diff[st.dz];
+                int pre = 0;
+                for (int k = 4 * lane; k < wlo; k += 128) {  // wlo is a multiple of 64, diff is 16-byte aligned
+                    const int4 v4 = *reinterpret_cast<const int4*>(diff + k);
+                    pre += (v4.x + v4.y) + (v4.z + v4.w);
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
+                const int2 dd = *reinterpret_cast<const int2*>(diff + wlo + 2 * lane);
+                int run = dd.x + dd.y;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, run, d);
+                    if (lane >= d) run += o;
+                }
+                const int before = pre + run - dd.x - dd.y;
+                int* cw = sm.cov[warp];
+                *reinterpret_cast<int2*>(cw + 2 * lane) = make_int2(before + dd.x, before + dd.x + dd.y);
+                __syncwarp();
+                const int4 ca = *reinterpret_cast<const int4*>(cw + 8 * (lane & 7));
+                const int4 cb = *reinterpret_cast<const int4*>(cw + 8 * (lane & 7) + 4);
+                __syncwarp();  // (the next item overwrites cw)
                 covacc[0] += ca.x; covacc[1] += ca.y; covacc[2] += ca.z; covacc[3] += ca.w;
                 covacc[4] += cb.x; covacc[5] += cb.y; covacc[6] += cb.z; covacc[7] += cb.w;
             }

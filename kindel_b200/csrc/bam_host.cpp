@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <thread>
@@ -196,7 +197,10 @@ inline Class classify(const RecView& r, int64_t L, int64_t* reach_r, int64_t* re
 }  // namespace
 
 struct kdl_bam {
-    std::vector<uint8_t> data;          // the inflated BAM byte stream
+    std::vector<uint8_t> data;          // the inflated BAM byte stream (plain gzip / uncompressed input) ...
+    std::unique_ptr<uint8_t[]> big;     // ... or, for BGZF, an UNINITIALISED buffer the inflating threads first-touch
+    const uint8_t* dptr = nullptr;
+    int64_t dsize = 0;
     int64_t first_record = 0;
     std::string text;                   // header text
     std::vector<std::string> ref_name;
@@ -292,7 +296,10 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
             outb.resize(have);
             h->data.swap(outb);
         } else {
-            h->data.resize(total);
+            h->big.reset(new (std::nothrow) uint8_t[total ? total : 1]);
+            if (!h->big) { delete h; return KDL_ERR_INVALID_ARG; }
+            h->dptr = h->big.get();
+            h->dsize = (int64_t)total;
             std::atomic<int> failed{0};
             parallel_for((int64_t)blks.size(), threads, [&](int64_t i, int) {
                 const Blk& b = blks[(size_t)i];
@@ -302,7 +309,7 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
                 if (inflateInit2(&zs, -15) != Z_OK) { failed = 1; return; }
                 zs.next_in = raw.data() + b.pay;
                 zs.avail_in = (uInt)b.pay_len;
-                zs.next_out = h->data.data() + b.out_off;
+                zs.next_out = h->big.get() + b.out_off;
                 zs.avail_out = b.isize;
                 const int rc = inflate(&zs, Z_FINISH);
                 if (rc != Z_STREAM_END || zs.avail_out != 0) failed = 1;
@@ -311,10 +318,12 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
             if (failed) { delete h; return KDL_ERR_INVALID_ARG; }
         }
     }
-    const std::vector<uint8_t>& d = h->data;
-    if (d.size() < 12 || std::memcmp(d.data(), "BAM\1", 4)) { delete h; return KDL_ERR_INVALID_ARG; }
+    if (!h->dptr) { h->dptr = h->data.data(); h->dsize = (int64_t)h->data.size(); }
+    const uint8_t* d = h->dptr;
+    const int64_t dn = h->dsize;
+    if (dn < 12 || std::memcmp(d, "BAM\1", 4)) { delete h; return KDL_ERR_INVALID_ARG; }
     const int64_t l_text = rd_i32(&d[4]);
-    if (l_text < 0 || 8 + l_text + 4 > (int64_t)d.size()) { delete h; return KDL_ERR_INVALID_ARG; }
+    if (l_text < 0 || 8 + l_text + 4 > dn) { delete h; return KDL_ERR_INVALID_ARG; }
     h->text.assign((const char*)&d[8], (size_t)l_text);
     const size_t nul = h->text.find('\0');
     if (nul != std::string::npos) h->text.resize(nul);
@@ -323,9 +332,9 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
     off += 4;
     if (n_ref < 0) { delete h; return KDL_ERR_INVALID_ARG; }
     for (int64_t k = 0; k < n_ref; ++k) {
-        if (off + 4 > (int64_t)d.size()) { delete h; return KDL_ERR_INVALID_ARG; }
+        if (off + 4 > dn) { delete h; return KDL_ERR_INVALID_ARG; }
         const int64_t l_name = rd_i32(&d[(size_t)off]);
-        if (l_name < 1 || off + 8 + l_name > (int64_t)d.size()) { delete h; return KDL_ERR_INVALID_ARG; }
+        if (l_name < 1 || off + 8 + l_name > dn) { delete h; return KDL_ERR_INVALID_ARG; }
         h->ref_name.emplace_back((const char*)&d[(size_t)off + 4], (size_t)l_name - 1);
         h->ref_len.push_back(rd_i32(&d[(size_t)(off + 4 + l_name)]));
         off += 8 + l_name;
@@ -356,8 +365,8 @@ int32_t kdl_bam_ref_len(const kdl_bam* h, int32_t ref_id) {
 // 11 longest simple read, 12 reads_sorted (valid after kdl_bam_fill).
 int kdl_bam_prepare(kdl_bam* h, const int32_t* ref_len, int threads, int64_t* info) {
     if (!h || !info) return KDL_ERR_INVALID_ARG;
-    const uint8_t* d = h->data.data();
-    const int64_t n_bytes = (int64_t)h->data.size();
+    const uint8_t* d = h->dptr;
+    const int64_t n_bytes = h->dsize;
     const int32_t n_ref = (int32_t)h->ref_name.size();
     if (ref_len) h->ref_len.assign(ref_len, ref_len + n_ref);
     // ---- the block_size chain (sequential: 4 bytes per record are touched)
@@ -475,7 +484,7 @@ int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* r
                  uint32_t* complex_idx, uint32_t* hard_idx, int64_t* info) {
     if (!h || !h->prepared || !ref_start || !seq_off || !l_seq || !seq_len || !cig_off || !stream || !info)
         return KDL_ERR_INVALID_ARG;
-    const uint8_t* d = h->data.data();
+    const uint8_t* d = h->dptr;
     const int32_t n_ref = (int32_t)h->ref_name.size();
     const int64_t n_tasks = (int64_t)h->chunk_lo.size() - 1;
     const int64_t n = h->n_kept;

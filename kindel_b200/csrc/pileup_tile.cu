@@ -29,23 +29,60 @@ namespace kdl {
 
 constexpr int W_CONSUMERS = 8;   // consumer warps (one 64-slot window each)
 constexpr int W_PRODUCERS = 4;   // producer warps
-constexpr int W_STAGES = 2;
+#ifndef KDL_W_STAGES
+#define KDL_W_STAGES 2  // measured on B200 (cfg 4): 2 stages 0.216 ms, 3 stages 0.243 ms, 4 stages 0.262 ms -- see TileCfg
+#endif
+constexpr int W_STAGES = KDL_W_STAGES;  // depth of the shared-memory ring
 constexpr int W_THREADS = 32 * (W_CONSUMERS + W_PRODUCERS);
 constexpr int W_PT = 32 * W_PRODUCERS;  // producer threads
-template <bool kCx> struct TileRegs { static constexpr int kProducer = 56, kConsumer = 88; };  // 128 * 56 + 256 * 88 <= 384 * 80
+// setmaxnreg per role: 128 * kProducer + 256 * kConsumer <= 384 * 80 (the launch bound's allocation)
+template <bool kCx> struct TileRegs { static constexpr int kProducer = kCx ? 64 : 56, kConsumer = 88; };
+static_assert(W_PT * TileRegs<true>::kProducer + 32 * W_CONSUMERS * TileRegs<true>::kConsumer <= W_THREADS * 80 &&
+              W_PT * TileRegs<false>::kProducer + 32 * W_CONSUMERS * TileRegs<false>::kConsumer <= W_THREADS * 80,
+              "register pool of the CTA");
 
 // kCx = false: batches without tile-eligible complex reads (no piece list, larger stages)
 template <bool kCx> struct TileCfg;
+// An item is sized so that the whole ring fits half an SM's shared memory.  A tile of deep short-read data is
+// several items, each a sub-range of the tile's (sorted) reads, and every item costs each consumer warp a wait, a
+// search and a partly filled last block: FEW LARGE items beat a deeper ring of small ones (the 3- and 4-stage
+// configurations are kept for that measurement, profiles/r02_ring_depth.txt).
+#if KDL_W_STAGES == 2
 template <> struct TileCfg<false> {
     static constexpr int kRmax = 512;    // reads per item
-    static constexpr int kCapW = 9216;   // words of seq4 per item (36 KB: ~485 reads of 150 bases)
+    static constexpr int kCapW = 9728;   // words of seq4 per item (38 KB: ~510 reads of 150 bases)
     static constexpr int kPcap = 0;      // pieces of complex reads per item
 };
 template <> struct TileCfg<true> {
     static constexpr int kRmax = 384;
-    static constexpr int kCapW = 7168;   // 28 KB
+    static constexpr int kCapW = 7680;   // 30 KB
     static constexpr int kPcap = 672;
 };
+#elif KDL_W_STAGES == 3
+template <> struct TileCfg<false> {
+    static constexpr int kRmax = 384;
+    static constexpr int kCapW = 6144;   // 24 KB
+    static constexpr int kPcap = 0;
+};
+template <> struct TileCfg<true> {
+    static constexpr int kRmax = 256;
+    static constexpr int kCapW = 5120;   // 20 KB
+    static constexpr int kPcap = 448;
+};
+#elif KDL_W_STAGES == 4
+template <> struct TileCfg<false> {
+    static constexpr int kRmax = 256;
+    static constexpr int kCapW = 4736;   // 18.5 KB: ~250 reads of 150 bases
+    static constexpr int kPcap = 0;
+};
+template <> struct TileCfg<true> {
+    static constexpr int kRmax = 256;
+    static constexpr int kCapW = 3328;   // 13 KB
+    static constexpr int kPcap = 320;
+};
+#else
+#error "KDL_W_STAGES must be 2, 3 or 4"
+#endif
 
 enum : int { ITEM_FIRST = 1, ITEM_LAST = 2, ITEM_EMPTY = 4, ITEM_END = 8 };
 
@@ -64,22 +101,23 @@ struct TileStage {
     // covers nothing (what idle lanes of a block read).
     int4 px[C::kPcap + 1];
     int gs[C::kRmax + 32];       // start slot relative to the tile (all reads: the array stays sorted)
-    // +1 at a piece's first slot, -1 behind its last.  Two of them, alternating by the stage's use count (`dz`):
-    // while an item's atomics go to one, the other -- which the consumers finished reading two items ago -- is
-    // cleaned, so the producers need no barrier between cleaning and counting (the full / empty mbarriers order it)
-    int diff[2][KDL_TILE + 32];
+    // coverage of the tile's slots by the item's reads / pieces, as a difference array PER WINDOW: +1 at a piece's
+    // first slot, -1 behind its last (unless that is a window's first slot), and carry[w] = pieces that cover the
+    // first slot of window w.  A consumer warp reads its own 64 + 1 entries and zeroes them again before it releases
+    // the stage, so the producers never clean and nobody sums across windows.
+    int diff[KDL_TILE + 32];
+    int carry[W_CONSUMERS];
     long long tile_slot;
     int n_sub;
     int flags;
     int n_px;
-    int dz;                      // which diff this item uses
+    int pad0;
 };
 
 template <class C>
 struct TileSmem {
     TileStage<C> st[W_STAGES];
     int raw[3][C::kRmax];          // producers: l_seq / ref_start / seq_off of the NEXT item's reads (cp.async)
-    int cov[W_CONSUMERS][F_WIN];   // consumers: coverage of the warp's window by the current item (private per warp)
     unsigned short queue[W_CONSUMERS][C::kPcap ? 64 : 4];  // consumers (kCx): indices of the pieces that overlap the warp's window
     int scan[W_PRODUCERS * 4 + 4];  // producers (kCx): per-group piece totals, cut counter
     uint64_t full[W_STAGES];       // producers -> consumers: 4 warp arrivals (metadata, pieces, coverage written)
@@ -90,9 +128,10 @@ static_assert(sizeof(TileSmem<TileCfg<false>>) <= 113 * 1024 && sizeof(TileSmem<
               "K1 must fit two CTAs per SM");
 static_assert(offsetof(TileStage<TileCfg<false>>, diff) % 16 == 0 && sizeof(TileStage<TileCfg<false>>) % 16 == 0 &&
               offsetof(TileStage<TileCfg<true>>, diff) % 16 == 0 && sizeof(TileStage<TileCfg<true>>) % 16 == 0 &&
-              (sizeof(int) * (KDL_TILE + 32)) % 16 == 0 &&
               offsetof(TileStage<TileCfg<true>>, px) % 16 == 0 && offsetof(TileStage<TileCfg<true>>, meta) % 16 == 0,
-              "128-bit shared loads of the difference array, the metadata and the pieces");
+              "128-bit shared accesses of the metadata and the pieces, 64-bit ones of the difference array");
+static_assert(TileCfg<false>::kRmax % W_PT == 0 && TileCfg<true>::kRmax % W_PT == 0, "reads per producer thread");
+static_assert(TileCfg<true>::kPcap >= KDL_TILE_MAXOPS && TileCfg<true>::kPcap < 1024, "one read's pieces fit; 10-bit piece slot");
 
 // kFlush: F_STORE = the weight columns hold stale data (first flush of a window stores, untouched tiles are stored
 // as zeros); F_ADD = add to what is there; F_ATOMIC = `split` CTAs share a tile, the table was zeroed, flush with REDs.
@@ -121,7 +160,8 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         }
     }
     for (int s = 0; s < W_STAGES; ++s) {
-        for (int k = tid; k < 2 * (KDL_TILE + 32); k += W_THREADS) (&sm.st[s].diff[0][0])[k] = 0;
+        for (int k = tid; k < KDL_TILE + 32; k += W_THREADS) sm.st[s].diff[k] = 0;
+        if (tid < W_CONSUMERS) sm.st[s].carry[tid] = 0;
         if (tid == 0) sm.st[s].px[W_PCAP] = make_int4(0x10000000, (int)smem_u32(sm.st[s].seq), 0, 0);
     }
     if (tid < W_PRODUCERS * 4 + 4) sm.scan[tid] = 0;
@@ -132,18 +172,17 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         reg_dealloc<TileRegs<kCx>::kProducer>();
         const int pw = warp - W_CONSUMERS;          // 0..3
         const int ptid = tid - 32 * W_CONSUMERS;    // 0..127
-        long long item = 0;
-        int stage_uses = 0;  // bit s: parity of the real (non-empty) items stage s has carried
-        auto acquire_stage = [&](long long it) -> Stage& {
-            const int s = (int)(it % W_STAGES);
-            const uint32_t round = (uint32_t)(it / W_STAGES);
-            if (round > 0) mbar_wait(&sm.empty[s], (round - 1) & 1u);  // consumers released its last use
-            return sm.st[s];
+        int ps = 0;           // the ring slot of the item being produced
+        uint32_t pph = 0;     // parity of that slot's round (flips when ps wraps)
+        bool wrapped = false;
+        auto acquire_stage = [&]() -> Stage& {
+            if (wrapped) mbar_wait_relaxed(&sm.empty[ps], pph ^ 1u);  // consumers released its last use
+            return sm.st[ps];
         };
-        auto publish = [&](long long it) {  // this warp's part of the item is written
-            const int s = (int)(it % W_STAGES);
+        auto publish = [&]() {  // this warp's part of the item is written; on to the next ring slot
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.full[s]);
+            if (lane == 0) mbar_arrive(&sm.full[ps]);
+            if (++ps == W_STAGES) { ps = 0; pph ^= 1u; wrapped = true; }
         };
 
         // The producers run a software pipeline of their own: while an item is prepared, the three metadata words
@@ -196,13 +235,12 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             part_of(u, w, plo, phi);
             if (plo >= phi) {
                 if (kFresh) {  // consumers must store zeros: a header-only item
-                    Stage& st = acquire_stage(item);
+                    Stage& st = acquire_stage();
                     if (ptid == 0) {
                         st.tile_slot = tile_slot; st.n_sub = 0; st.n_px = 0; st.flags = ITEM_FIRST | ITEM_LAST | ITEM_EMPTY;
-                        mbar_expect_tx(&sm.landed[(int)(item % W_STAGES)], 0);
+                        mbar_expect_tx(&sm.landed[ps], 0);
                     }
-                    publish(item);
-                    ++item;
+                    publish();
                 }
                 cp_async_wait_all();  // (a thread never has two prefetches in flight to the same words)
                 uint32_t nplo, nphi;
@@ -265,8 +303,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 }
                 // ---- stage + bulk copy first: the bytes fly while the metadata is written.  (If the piece list
                 // later cuts the item short the copy has fetched a little more than needed: harmless.)
-                Stage& st = acquire_stage(item);
-                const int stage_id = (int)(item % W_STAGES);
+                Stage& st = acquire_stage();
+                const int stage_id = ps;
+                const uint32_t stage_parity = pph;
                 const uint32_t seq_base = smem_u32(st.seq);
                 {
                     const long long n_words = skip ? 0 : (long long)(wend - wa);
@@ -283,13 +322,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         st.seq[wq] = wq < avail ? b.seq4[wa + wq] : 0u;  // (visible to all after the barriers below)
                     }
                 }
-                // this item's atomics go to diff[dz]; the other array still holds the stage's previous item's entries,
-                // which the consumers have finished with (they released the stage): clean it for the stage's next use
-                const int dz = (stage_uses >> stage_id) & 1;  // alternates per REAL item of the stage (header-only items skip)
-                stage_uses ^= 1 << stage_id;
-                int* diff = st.diff[dz];
-                for (int k = ptid; k < (KDL_TILE + 32) / 4; k += W_PT)
-                    reinterpret_cast<int4*>(st.diff[dz ^ 1])[k] = make_int4(0, 0, 0, 0);
                 // ---- complex reads: where each one's pieces go (exclusive prefix in read order of: M-op count in the
                 // low 16 bits, 1 per tile-eligible complex read above), and a cut of the item if they do not fit
                 int pre[PER];
@@ -360,6 +392,7 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
                     const int i = ptid + k * W_PT;
+                    int w0 = W_CONSUMERS, w1 = 0;  // a simple read's carries go to windows (w0, w1]
                     if (i < n_sub) {
                         long long g;
                         if (one_contig) {
@@ -375,8 +408,10 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         if (l[k] > 0) {  // simple read (bit 31 clear)
                             const int cs = gs < 0 ? 0 : gs, ce = gs + l[k] > KDL_TILE ? KDL_TILE : gs + l[k];
                             if (cs < ce) {
-                                atomicAdd(diff + cs, 1);
-                                atomicAdd(diff + ce, -1);
+                                atomicAdd(st.diff + cs, 1);
+                                if (ce & (F_WIN - 1)) atomicAdd(st.diff + ce, -1);
+                                w0 = cs >> 6;
+                                w1 = (ce - 1) >> 6;
                             }
                             en = make_int4(((gs + 7) >> 3) << 2, raddr, ((l[k] + 7) >> 3) << 2, ((-gs) & 7) << 2);
                         } else if (kCx && (lw & KDL_HARD) == 0) {
@@ -391,6 +426,15 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         st.gs[i] = gs;
                         st.meta[i + (i >> 3)] = en;
                     }
+                    // the warp's 32 consecutive (sorted) reads carry into the same few windows: one shared-memory
+                    // atomic per window and warp instead of 32 on one address
+                    int into = 0;
+#pragma unroll
+                    for (int w = 1; w < W_CONSUMERS; ++w) {
+                        const unsigned m = __ballot_sync(0xffffffffu, w0 < w && w <= w1);
+                        if (lane == w) into = __popc(m);
+                    }
+                    if (into) atomicAdd(st.carry + lane, into);
                 }
                 if (ptid < 40) {  // sentinels behind the last read
                     const int i = n_sub + ptid;
@@ -401,7 +445,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                     st.tile_slot = tile_slot;
                     st.n_sub = n_sub;
                     st.n_px = n_px;
-                    st.dz = dz;
                     st.flags = (first ? ITEM_FIRST : 0) | (last ? ITEM_LAST : 0);
                 }
                 if constexpr (kCx) {
@@ -410,7 +453,12 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         // bulk copy).  One thread per read: it only tracks the two cursors through the ops -- the
                         // insertion / deletion / clip updates of these reads are K1e's (pileup_general.cu), once per
                         // read instead of once per tile it touches.
-                        mbar_wait(&sm.landed[stage_id], (uint32_t)((item / W_STAGES) & 1));
+                        mbar_wait(&sm.landed[stage_id], stage_parity);
+                        // carries of this thread's pieces into windows 0..3 / 4..7, one byte each (<= PER reads of
+                        // <= KDL_TILE_MAXOPS pieces): a deep pileup puts every piece of the item across the same two or
+                        // three window borders, so they are summed per thread, then per warp, before they touch st.carry
+                        static_assert(PER * KDL_TILE_MAXOPS <= 255, "byte counters of the piece carries");
+                        uint32_t clo = 0, chi = 0;
 #pragma unroll 1
                         for (int i = ptid; i < n_sub; i += W_PT) {  // (its own entries: no barrier needed)
                             const int4 en = st.meta[i + (i >> 3)];
@@ -430,8 +478,11 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                                     const int s0 = r < 0 ? 0 : r, s1 = r + len > KDL_TILE ? KDL_TILE : r + len;
                                     if (s0 < s1) {
                                         const int v = r - q;  // slot of the read's base 0
-                                        atomicAdd(diff + s0, 1);
-                                        atomicAdd(diff + s1, -1);
+                                        atomicAdd(st.diff + s0, 1);
+                                        if (s1 & (F_WIN - 1)) atomicAdd(st.diff + s1, -1);
+                                        const uint32_t bits = ((2u << ((s1 - 1) >> 6)) - 1u) & ~((2u << (s0 >> 6)) - 1u);  // windows (w0, w1]
+                                        clo += ((bits & 0xFu) * 0x00204081u) & 0x01010101u;  // bit k -> byte k
+                                        chi += ((bits >> 4) * 0x00204081u) & 0x01010101u;
                                         st.px[pos++] = make_int4(((v + 7) >> 3) << 2, en.y, nbw << 2,
                                                                  (((-v) & 7) << 2) | (s0 << 8) | (s1 << 20));
                                     }
@@ -449,22 +500,33 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             }
                             while (pos < pend) st.px[pos++] = make_int4(0x10000000, (int)seq_base, 0, 0);  // covers nothing
                         }
+                        __syncwarp();
+                        uint32_t cw[4] = {clo & 0x00FF00FFu, (clo >> 8) & 0x00FF00FFu, chi & 0x00FF00FFu, (chi >> 8) & 0x00FF00FFu};
+#pragma unroll
+                        for (int d = 16; d; d >>= 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) cw[k] += __shfl_xor_sync(0xffffffffu, cw[k], d);  // 16-bit halves: <= 32 * 192
+                        }
+                        if (lane >= 1 && lane < W_CONSUMERS) {  // window `lane`: byte lane & 3 of clo (lane < 4) / chi
+                            const uint32_t pair = cw[(lane & 1) + ((lane >> 2) << 1)];
+                            const int v = (int)((lane & 2) ? pair >> 16 : pair & 0xFFFFu);
+                            if (v) atomicAdd(st.carry + lane, v);
+                        }
                     }
                 }
-                publish(item);
-                ++item;
+                publish();
                 first = false;
                 c0 = c1;
             }
             u = nu;
         }
         {   // END item
-            Stage& st = acquire_stage(item);
+            Stage& st = acquire_stage();
             if (ptid == 0) {
                 st.tile_slot = 0; st.n_sub = 0; st.n_px = 0; st.flags = ITEM_END;
-                mbar_expect_tx(&sm.landed[(int)(item % W_STAGES)], 0);
+                mbar_expect_tx(&sm.landed[ps], 0);
             }
-            publish(item);
+            publish();
         }
         return;
     }
@@ -476,9 +538,11 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
     const int p8b = (wlo >> 1) + 4 * (lane & 7);  // 4 * (lane's first slot / 8): byte offset of its word
     Planes acc;
     acc.clear();
-    int rawacc[8], covacc[8];
+    int rawacc[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { rawacc[k] = 0; covacc[k] = 0; }
+    for (int k = 0; k < 8; ++k) rawacc[k] = 0;
+    int2 dacc = make_int2(0, 0);  // the tile's items' difference entries of slots wlo + 2 lane, + 1 (summed: the scan is linear)
+    int cacc = 0;                 // ... and their carries into this window
     int blocks_since_flush = 0;
     uint32_t pend8 = 0;  // weight-8 carry of an odd block, waiting for its partner
     bool stored = false;
@@ -497,9 +561,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         if (++blocks_since_flush == F_FLUSH_BLOCKS) {
             acc.template ripple<3>(pend8);  // F_FLUSH_BLOCKS is odd: one carry is pending
             if (kFresh && !stored)
-                flush_window<F_STORE, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+                flush_window<F_STORE, false>(acc, rawacc, rawacc, counts, n_slots, tile_slot + wlo, lane);
             else
-                flush_window<kAdd, false>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
+                flush_window<kAdd, false>(acc, rawacc, rawacc, counts, n_slots, tile_slot + wlo, lane);  // (coverage unused)
             stored = true;
             blocks_since_flush = 0;
         }
@@ -529,9 +593,11 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         return __funnelshift_l(lw, hw, (uint32_t)mt.w);
     };
 
-    for (long long item = 0;; ++item) {
-        const int s = (int)(item % W_STAGES);
-        const uint32_t parity = (uint32_t)((item / W_STAGES) & 1);
+    int s = -1;
+    uint32_t parity = 1;
+    for (;;) {
+        if (++s == W_STAGES) s = 0;
+        if (s == 0) parity ^= 1u;
         mbar_wait(&sm.full[s], parity);
         mbar_wait(&sm.landed[s], parity);
         Stage& st = sm.st[s];
@@ -544,31 +610,15 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
             blocks_since_flush = 0;  // (already 0 after the previous tile's final flush)
         }
         if (n_sub > 0) {
-            {   // coverage of this warp's 64 slots by the item's reads / pieces: prefix sum of its difference array
-                const int* diff = st.diff[st.dz];
-                int pre = 0;
-                for (int k = 4 * lane; k < wlo; k += 128) {  // wlo is a multiple of 64, diff is 16-byte aligned
-                    const int4 v4 = *reinterpret_cast<const int4*>(diff + k);
-                    pre += (v4.x + v4.y) + (v4.z + v4.w);
-                }
-#pragma unroll
-                for (int d = 16; d; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
-                const int2 dd = *reinterpret_cast<const int2*>(diff + wlo + 2 * lane);
-                int run = dd.x + dd.y;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, run, d);
-                    if (lane >= d) run += o;
-                }
-                const int before = pre + run - dd.x - dd.y;
-                int* cw = sm.cov[warp];
-                *reinterpret_cast<int2*>(cw + 2 * lane) = make_int2(before + dd.x, before + dd.x + dd.y);
+            {   // this warp's difference entries of the item; zeroed again for the stage's next item
+                int2* dp = reinterpret_cast<int2*>(st.diff + wlo) + lane;
+                const int2 dd = *dp;
+                cacc += st.carry[warp];
+                dacc.x += dd.x;
+                dacc.y += dd.y;
                 __syncwarp();
-                const int4 ca = *reinterpret_cast<const int4*>(cw + 8 * (lane & 7));
-                const int4 cb = *reinterpret_cast<const int4*>(cw + 8 * (lane & 7) + 4);
-                __syncwarp();  // (the next item overwrites cw)
-                covacc[0] += ca.x; covacc[1] += ca.y; covacc[2] += ca.z; covacc[3] += ca.w;
-                covacc[4] += cb.x; covacc[5] += cb.y; covacc[6] += cb.z; covacc[7] += cb.w;
+                *dp = make_int2(0, 0);
+                if (lane == 0) st.carry[warp] = 0;
             }
             // ---- simple reads: those with start in (wlo - maxlen, wlo + 64), two lower bounds over the sorted starts
             int a, e;
@@ -641,6 +691,25 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
         if (lane == 0) mbar_arrive(&sm.empty[s]);
         if (flags & ITEM_LAST) {
             if (blocks_since_flush & 1) acc.template ripple<3>(pend8);
+            int covacc[8];  // coverage of the lane's 8 slots by the tile's reads / pieces: one scan of the summed entries
+            {
+                const int both = dacc.x + dacc.y;
+                int run = both;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, run, d);
+                    if (lane >= d) run += o;
+                }
+                const int c0 = cacc + run - dacc.y, c1 = cacc + run;  // slots wlo + 2 lane, + 1
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int src = 4 * (lane & 7) + k;
+                    covacc[2 * k] = __shfl_sync(0xffffffffu, c0, src);
+                    covacc[2 * k + 1] = __shfl_sync(0xffffffffu, c1, src);
+                }
+                dacc = make_int2(0, 0);
+                cacc = 0;
+            }
             if (kFresh && !stored) flush_window<F_STORE, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
             else flush_window<kAdd, true>(acc, rawacc, covacc, counts, n_slots, tile_slot + wlo, lane);
             if (kFresh && zero_rest) {
@@ -654,8 +723,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                 }
             }
             blocks_since_flush = 0;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) covacc[k] = 0;
         }
     }
 }

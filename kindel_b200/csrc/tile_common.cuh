@@ -132,9 +132,26 @@ __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
+#ifndef KDL_WAIT_HINT_NS
+#define KDL_WAIT_HINT_NS 0     // > 0: try_wait may suspend the thread for up to this long before it reports failure
+#endif
+#ifndef KDL_WAIT_SLEEP_NS
+#define KDL_WAIT_SLEEP_NS 0    // > 0: producers sleep this long between two failed polls (consumers always poll)
+#endif
+template <int kHintNs>
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    if (kHintNs > 0) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)kHintNs)
+            : "memory");
+    } else {
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
@@ -144,6 +161,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(smem_u32(bar)), "r"(parity)
             : "memory");
+    }
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try<KDL_WAIT_HINT_NS>(bar, parity)) {}
+}
+// the same for a waiter that is in nobody's way (a producer waiting for a free stage): its polls must not take issue
+// slots from the warps that count
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try<KDL_WAIT_HINT_NS>(bar, parity)) {
+        if (KDL_WAIT_SLEEP_NS > 0) __nanosleep(KDL_WAIT_SLEEP_NS);
     }
 }
 #endif  // KDL_HOST_EMU

@@ -392,7 +392,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
                     const int i = ptid + k * W_PT;
-                    int w0 = W_CONSUMERS, w1 = 0;  // a simple read's carries go to windows (w0, w1]
                     if (i < n_sub) {
                         long long g;
                         if (one_contig) {
@@ -410,8 +409,9 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                             if (cs < ce) {
                                 atomicAdd(st.diff + cs, 1);
                                 if (ce & (F_WIN - 1)) atomicAdd(st.diff + ce, -1);
-                                w0 = cs >> 6;
-                                w1 = (ce - 1) >> 6;
+                                // (the 32 sorted reads of a warp carry into the same two or three windows; summing them
+                                // with ballots first was measured slower than letting the atomics collide: 0.231 / 0.217 ms)
+                                for (int w = (cs >> 6) + 1; w <= ((ce - 1) >> 6); ++w) atomicAdd(st.carry + w, 1);
                             }
                             en = make_int4(((gs + 7) >> 3) << 2, raddr, ((l[k] + 7) >> 3) << 2, ((-gs) & 7) << 2);
                         } else if (kCx && (lw & KDL_HARD) == 0) {
@@ -426,15 +426,6 @@ pileup_tile_kernel(kdl_batch b, int32_t* __restrict__ counts, long long n_slots,
                         st.gs[i] = gs;
                         st.meta[i + (i >> 3)] = en;
                     }
-                    // the warp's 32 consecutive (sorted) reads carry into the same few windows: one shared-memory
-                    // atomic per window and warp instead of 32 on one address
-                    int into = 0;
-#pragma unroll
-                    for (int w = 1; w < W_CONSUMERS; ++w) {
-                        const unsigned m = __ballot_sync(0xffffffffu, w0 < w && w <= w1);
-                        if (lane == w) into = __popc(m);
-                    }
-                    if (into) atomicAdd(st.carry + lane, into);
                 }
                 if (ptid < 40) {  // sentinels behind the last read
                     const int i = n_sub + ptid;

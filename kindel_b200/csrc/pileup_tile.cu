@@ -8,12 +8,13 @@
 //     reads that can touch a tile are ONE index range and ONE byte range of seq4 (K0, tile_common.cuh); a tile
 //     is owned by one CTA (or, for small references piled deep, by `split` CTAs that share it by read range and
 //     flush with REDs), so the weight columns are written with plain 128-bit stores: no atomics, no memset.
-//   * Two CTAs per SM, each 4 PRODUCER + 8 CONSUMER warps over a two-stage shared-memory ring, the register
+//   * Two CTAs per SM, each 4 PRODUCER + 8 CONSUMER warps over a shared-memory ring (two stages), the register
 //     file re-balanced with setmaxnreg.  An ITEM is (tile, up to kRmax reads).  Producers: wait for a free stage,
-//     ONE 1-D bulk copy (TMA) of the item's bytes, per-read metadata, the +1/-1 coverage array and its prefix
-//     sums; they run one item ahead with the next item's metadata words in flight (cp.async).  Consumers: each
-//     warp owns a 64-slot window, each quarter-warp walks a different read (one funnel shift of two staged
-//     words per lane and read, 7 full adders per 8 reads), and flushes at the end of a tile.  Consumers never
+//     ONE 1-D bulk copy (TMA) of the item's bytes, per-read metadata, the coverage marks (+1 / -1 per window and the
+//     carries between windows, TileStage::diff); each thread prefetches the metadata words of the reads it will
+//     handle in the next item (cp.async), so the producers meet no barrier of their own in the simple path.
+//     Consumers: each warp owns a 64-slot window, each quarter-warp walks a different read (one funnel shift of two
+//     staged words per lane and read, 7 full adders per 8 reads), and flushes at the end of a tile.  Consumers never
 //     touch global memory except for the table stores and never meet a CTA-wide barrier.
 //   * Complex reads (indels, clips; include/kindel_b200.h) carry their CIGAR behind their bases in seq4, so it
 //     arrives with the bulk copy.  A producer thread tracks the two cursors through it once per (read, tile): every

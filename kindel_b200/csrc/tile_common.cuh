@@ -164,8 +164,13 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     }
     return done != 0;
 }
+#ifndef KDL_WAIT_SLEEP_CONS_NS
+#define KDL_WAIT_SLEEP_CONS_NS 0   // > 0: the same for the consumers' waits
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try<KDL_WAIT_HINT_NS>(bar, parity)) {}
+    while (!mbar_try<KDL_WAIT_HINT_NS>(bar, parity)) {
+        if (KDL_WAIT_SLEEP_CONS_NS > 0) __nanosleep(KDL_WAIT_SLEEP_CONS_NS);
+    }
 }
 // the same for a waiter that is in nobody's way (a producer waiting for a free stage): its polls must not take issue
 // slots from the warps that count

@@ -17,6 +17,6 @@ run() {  # name, extra args
   tail -c 300 gpurun_out/${TAG}_n${N}_$1.err
 }
 run cfg4 ""
-run cfg4_allreduce "--exchange allreduce --no-strong"
+[ "${SKIP_ALLREDUCE:-0}" = 1 ] || run cfg4_allreduce "--exchange allreduce --no-strong"
 run cfg5 "--workload cfg5_64x100kb_500x"
 ls -la gpurun_out | grep ${TAG}_n${N}

@@ -22,8 +22,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -34,6 +36,18 @@
 #include "../../include/kindel_b200.h"
 
 namespace {
+
+// KDL_BAM_TIMING=1: phase times of the decoder on stderr
+struct PhaseTimer {
+    const bool on = std::getenv("KDL_BAM_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[kdl_bam] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 inline int32_t rd_i32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); return v; }
 inline uint32_t rd_u32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
@@ -225,6 +239,7 @@ extern "C" {
 int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
     if (!path || !out) return KDL_ERR_INVALID_ARG;
     *out = nullptr;
+    PhaseTimer pt;
     FILE* fh = std::fopen(path, "rb");
     if (!fh) return KDL_ERR_INVALID_ARG;
     std::vector<uint8_t> raw;
@@ -237,6 +252,7 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
         if (sz && std::fread(raw.data(), 1, (size_t)sz, fh) != (size_t)sz) { std::fclose(fh); return KDL_ERR_INVALID_ARG; }
         std::fclose(fh);
     }
+    pt.lap("open: read file");
     kdl_bam* h = new (std::nothrow) kdl_bam();
     if (!h) return KDL_ERR_INVALID_ARG;
     const size_t n = raw.size();
@@ -296,6 +312,7 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
             outb.resize(have);
             h->data.swap(outb);
         } else {
+            pt.lap("open: BGZF header chain");
             h->big.reset(new (std::nothrow) uint8_t[total ? total : 1]);
             if (!h->big) { delete h; return KDL_ERR_INVALID_ARG; }
             h->dptr = h->big.get();
@@ -316,6 +333,7 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
                 inflateEnd(&zs);
             });
             if (failed) { delete h; return KDL_ERR_INVALID_ARG; }
+            pt.lap("open: inflate (threads)");
         }
     }
     if (!h->dptr) { h->dptr = h->data.data(); h->dsize = (int64_t)h->data.size(); }
@@ -369,59 +387,131 @@ int kdl_bam_prepare(kdl_bam* h, const int32_t* ref_len, int threads, int64_t* in
     const int64_t n_bytes = h->dsize;
     const int32_t n_ref = (int32_t)h->ref_name.size();
     if (ref_len) h->ref_len.assign(ref_len, ref_len + n_ref);
-    // ---- the block_size chain (sequential: 4 bytes per record are touched)
-    h->rec_off.clear();
-    for (int64_t off = h->first_record; off < n_bytes;) {
-        if (n_bytes - off < 36) return KDL_ERR_INVALID_ARG;
-        const int64_t bs = rd_i32(d + off);
-        if (bs < 32 || off + 4 + bs > n_bytes) return KDL_ERR_INVALID_ARG;
-        h->rec_off.push_back(off);
-        off += 4 + bs;
-    }
-    h->rec_off.push_back(n_bytes);
-    const int64_t n_rec = (int64_t)h->rec_off.size() - 1;
-    h->n_records = n_rec;
-    h->cls.assign((size_t)n_rec, Class{CLS_DROP, 0, 0});
-    // ---- parallel classify + count.  Tasks are contiguous record ranges, so "file order inside a contig" is
-    // task order then record order.
+    PhaseTimer pt;
+    // ---- records are found, filtered, classified and counted in ONE parallel pass over byte ranges of the stream.
+    // The block_size chain is sequential by nature, so every task but the first GUESSES its first record boundary
+    // (the first offset from which three consecutive plausible records follow); afterwards the chain is verified
+    // task by task -- a task whose guess is not where its predecessor's walk ended is simply walked again from there
+    // -- so the result never depends on the guess.  Tasks are byte ranges in file order, hence contiguous record
+    // ranges: "file order inside a contig" is task order then record order.
     if (threads < 1) threads = 1;
-    int64_t n_tasks = std::min<int64_t>(std::max<int64_t>(1, n_rec / 4096), (int64_t)threads * 4);
+    const int64_t body = n_bytes - h->first_record;
+    if (body < 0) return KDL_ERR_INVALID_ARG;
+    int64_t n_tasks = std::min<int64_t>(std::max<int64_t>(1, body / (256 << 10)), (int64_t)threads * 4);
     if ((int64_t)n_ref * n_tasks > (1ll << 24)) n_tasks = std::max<int64_t>(1, (1ll << 24) / std::max(1, n_ref));  // bound the cursor tables
-    h->chunk_lo.resize((size_t)n_tasks + 1);
-    for (int64_t t = 0; t <= n_tasks; ++t) h->chunk_lo[(size_t)t] = n_rec * t / n_tasks;
-    struct Acc { int64_t kept = 0, ops = 0, words = 0, first = -1; };
-    std::vector<Acc> acc((size_t)n_tasks * (size_t)std::max(1, n_ref));
-    struct Tot { int64_t cx = 0, hard = 0, aligned = 0, rr = 0, rl = 0, ms = 0; int bad = 0; };
-    std::vector<Tot> tot((size_t)n_tasks);
-    parallel_for(n_tasks, threads, [&](int64_t t, int) {
-        Acc* a = acc.data() + (size_t)t * (size_t)std::max(1, n_ref);
-        Tot& tt = tot[(size_t)t];
-        RecView r;
-        for (int64_t i = h->chunk_lo[(size_t)t]; i < h->chunk_lo[(size_t)t + 1]; ++i) {
-            const int64_t off = h->rec_off[(size_t)i];
-            if (!parse_record(d + off, h->rec_off[(size_t)i + 1] - off, &r)) { tt.bad = 1; return; }
-            if (r.ref_id < 0) continue;  // rname '*' is dropped wholesale (kindel.py:147-148)
-            if (r.ref_id >= n_ref) { tt.bad = 1; return; }
-            Acc& ac = a[r.ref_id];
-            if (ac.first < 0) ac.first = i;
-            if (!kept(r)) continue;
-            int64_t rr = 0, rl = 0, al = 0;
-            const Class c = classify(r, h->ref_len[(size_t)r.ref_id], &rr, &rl, &al);
-            h->cls[(size_t)i] = c;
-            ac.kept += 1;
-            ac.ops += r.n_cigar;
-            ac.words += ((int64_t)r.l_seq + 7) / 8 + (c.cls == CLS_SIMPLE ? 0 : 2 + (int64_t)r.n_cigar);
-            tt.aligned += al;
-            if (c.cls != CLS_SIMPLE) tt.cx += 1;
-            if (c.cls == CLS_HARD) tt.hard += 1;
-            if (c.cls == CLS_SIMPLE && rr > tt.ms) tt.ms = rr;
-            if (c.cls != CLS_HARD) { tt.rr = std::max(tt.rr, rr); tt.rl = std::max(tt.rl, rl); }
+    std::vector<int64_t> byte_lo((size_t)n_tasks + 1);
+    for (int64_t t = 0; t <= n_tasks; ++t) byte_lo[(size_t)t] = h->first_record + body * t / n_tasks;
+    struct Acc { int64_t kept = 0, ops = 0, words = 0, first = -1; };  // first: record index inside the task
+    const size_t row = (size_t)std::max(1, n_ref);
+    std::vector<Acc> acc((size_t)n_tasks * row);
+    struct Tot { int64_t cx = 0, hard = 0, aligned = 0, rr = 0, rl = 0, ms = 0; };
+    struct Task { std::vector<int64_t> off; std::vector<Class> cls; Tot tot; int64_t start = -1, end = -1; bool bad = false; };
+    std::vector<Task> task((size_t)n_tasks);
+    auto plausible = [&](int64_t off) -> int64_t {  // length of a believable record at `off`, 0 if none
+        if (n_bytes - off < 36) return 0;
+        const uint8_t* q = d + off + 4;
+        const int64_t bs = rd_i32(d + off);
+        if (bs < 32 || bs > (1 << 28) || off + 4 + bs > n_bytes) return 0;
+        const int32_t ref_id = rd_i32(q), pos = rd_i32(q + 4), l_seq = rd_i32(q + 16), next_ref = rd_i32(q + 20), next_pos = rd_i32(q + 24);
+        const int64_t l_name = q[8], n_cig = rd_u16(q + 12);
+        if (ref_id < -1 || ref_id >= n_ref || pos < -1 || next_ref < -1 || next_ref >= n_ref || next_pos < -1 || l_seq < 0 || l_name < 1) return 0;
+        if (32 + l_name + 4 * n_cig + ((int64_t)l_seq + 1) / 2 + l_seq > bs) return 0;
+        if (q[32 + l_name - 1] != 0) return 0;  // the read name is NUL-terminated
+        return 4 + bs;
+    };
+    auto guess = [&](int64_t lo, int64_t hi) -> int64_t {  // first offset in [lo, hi) that starts three plausible records
+        for (int64_t o = lo; o < hi; ++o) {
+            int64_t p = o;
+            int k = 0;
+            for (; k < 3 && p < n_bytes; ++k) {
+                const int64_t len = plausible(p);
+                if (!len) break;
+                p += len;
+            }
+            if (k == 3 || (k > 0 && p == n_bytes)) return o;
         }
+        return -1;
+    };
+    auto walk = [&](int64_t t, int64_t start) {  // the records that START in [start, byte_lo[t + 1])
+        Task& tk = task[(size_t)t];
+        Acc* a = acc.data() + (size_t)t * row;
+        for (size_t c = 0; c < row; ++c) a[c] = Acc{};
+        tk.off.clear(); tk.cls.clear(); tk.tot = Tot{}; tk.bad = false;
+        tk.start = start;
+        const int64_t stop = byte_lo[(size_t)t + 1];
+        const int64_t expect = (stop - start) / 96 + 16;
+        tk.off.reserve((size_t)expect); tk.cls.reserve((size_t)expect);
+        RecView r;
+        int64_t off = start;
+        while (off < stop) {
+            const int64_t used = parse_record(d + off, n_bytes - off, &r);
+            if (!used || r.ref_id >= n_ref) { tk.bad = true; break; }
+            Class c{CLS_DROP, 0, 0};
+            if (r.ref_id >= 0) {  // rname '*' is dropped wholesale (kindel.py:147-148)
+                Acc& ac = a[r.ref_id];
+                if (ac.first < 0) ac.first = (int64_t)tk.off.size();
+                if (kept(r)) {
+                    int64_t rr = 0, rl = 0, al = 0;
+                    c = classify(r, h->ref_len[(size_t)r.ref_id], &rr, &rl, &al);
+                    ac.kept += 1;
+                    ac.ops += r.n_cigar;
+                    ac.words += ((int64_t)r.l_seq + 7) / 8 + (c.cls == CLS_SIMPLE ? 0 : 2 + (int64_t)r.n_cigar);
+                    tk.tot.aligned += al;
+                    if (c.cls != CLS_SIMPLE) tk.tot.cx += 1;
+                    if (c.cls == CLS_HARD) tk.tot.hard += 1;
+                    if (c.cls == CLS_SIMPLE && rr > tk.tot.ms) tk.tot.ms = rr;
+                    if (c.cls != CLS_HARD) { tk.tot.rr = std::max(tk.tot.rr, rr); tk.tot.rl = std::max(tk.tot.rl, rl); }
+                }
+            }
+            tk.off.push_back(off);
+            tk.cls.push_back(c);
+            off += used;
+        }
+        tk.end = off;
+    };
+    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+        const int64_t start = t == 0 ? h->first_record : guess(byte_lo[(size_t)t], byte_lo[(size_t)t + 1]);
+        if (start >= 0) walk(t, start);
     });
+    pt.lap("prepare: walk + classify (threads)");
+    {   // verify the chain; repair what was guessed wrong
+        int64_t expected = h->first_record;
+        for (int64_t t = 0; t < n_tasks; ++t) {
+            Task& tk = task[(size_t)t];
+            if (expected >= byte_lo[(size_t)t + 1]) {  // no record starts inside this range
+                if (tk.start >= 0) walk(t, byte_lo[(size_t)t + 1]);  // (empties it)
+                tk.start = tk.end = expected;
+                continue;
+            }
+            if (tk.start != expected) walk(t, expected);
+            if (tk.bad) return KDL_ERR_INVALID_ARG;
+            expected = tk.end;
+        }
+        if (expected != n_bytes) return KDL_ERR_INVALID_ARG;
+    }
+    h->chunk_lo.assign((size_t)n_tasks + 1, 0);
+    for (int64_t t = 0; t < n_tasks; ++t) h->chunk_lo[(size_t)t + 1] = h->chunk_lo[(size_t)t] + (int64_t)task[(size_t)t].off.size();
+    const int64_t n_rec = h->chunk_lo[(size_t)n_tasks];
+    h->n_records = n_rec;
+    h->rec_off.resize((size_t)n_rec + 1);
+    h->cls.resize((size_t)n_rec);
+    h->rec_off[(size_t)n_rec] = n_bytes;
+    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+        const Task& tk = task[(size_t)t];
+        const size_t base = (size_t)h->chunk_lo[(size_t)t];
+        if (!tk.off.empty()) {
+            std::memcpy(h->rec_off.data() + base, tk.off.data(), tk.off.size() * sizeof(int64_t));
+            std::memcpy(h->cls.data() + base, tk.cls.data(), tk.cls.size() * sizeof(Class));
+        }
+        Acc* a = acc.data() + (size_t)t * row;
+        for (size_t c = 0; c < row; ++c)
+            if (a[c].first >= 0) a[c].first += (int64_t)base;  // -> index over all records
+    });
+    pt.lap("prepare: verify + gather");
     h->n_complex = h->n_hard = h->aligned = 0;
     h->reach_right = h->reach_left = h->max_simple = 0;
-    for (const Tot& tt : tot) {
-        if (tt.bad) return KDL_ERR_INVALID_ARG;
+    for (const Task& tk : task) {
+        const Tot& tt = tk.tot;
         h->n_complex += tt.cx; h->n_hard += tt.hard; h->aligned += tt.aligned;
         h->reach_right = std::max(h->reach_right, tt.rr); h->reach_left = std::max(h->reach_left, tt.rl);
         h->max_simple = std::max(h->max_simple, tt.ms);
@@ -488,6 +578,7 @@ int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* r
     const int32_t n_ref = (int32_t)h->ref_name.size();
     const int64_t n_tasks = (int64_t)h->chunk_lo.size() - 1;
     const int64_t n = h->n_kept;
+    PhaseTimer pt;
     std::vector<uint32_t> ins_n((size_t)std::max<int64_t>(n, 1), 0);  // I ops per kept read (final order)
     parallel_for(n_tasks, threads, [&](int64_t t, int) {
         std::vector<int64_t> cr(h->cur_read.begin() + t * n_ref, h->cur_read.begin() + (t + 1) * n_ref);
@@ -527,6 +618,7 @@ int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* r
         }
     });
     cig_off[n] = (uint32_t)h->op_off[h->order.size()];
+    pt.lap("fill: records (threads)");
     // ---- insertion-event rows (exclusive prefix of the I-op counts in read order), the complex / hard lists and the
     // coordinate-order check: one cheap sequential pass over the per-read arrays
     int64_t evt = 0, ncx = 0, nh = 0;
@@ -548,6 +640,7 @@ int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* r
         }
         evt += ins_n[(size_t)k];
     }
+    pt.lap("fill: events, lists, order");
     h->n_events = evt;
     h->reads_sorted = sorted_ok;
     info[8] = evt;

@@ -38,3 +38,16 @@ def test_opcode_census_proves_the_design_claims():
         f = ln.split()
         nums = [int(x) for x in f[-18:]]
         assert nums[1] >= 1 and nums[2] >= 10 and nums[3] >= 10 and nums[4] == 2 and nums[-1] == 0 and nums[-2] == 0
+
+
+def test_results_table_matches_the_readme():
+    """README.md's results block is the output of tools/results_table.py over profiles/: it cannot drift."""
+    res = _run("tools/results_table.py")
+    assert res.returncode == 0, res.stderr
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("|")]
+    assert len(lines) >= 8 and "cfg4_5Mb_200x" in res.stdout
+    readme = open(os.path.join(ROOT, "README.md")).read()
+    a = readme.index("<!-- results:begin")
+    b = readme.index("<!-- results:end -->")
+    block = readme[a:b].split("\n", 1)[1]
+    assert block.strip() == res.stdout.strip()

@@ -146,3 +146,39 @@ def test_engine_vs_c_oracle(tmp_path):
         np.testing.assert_array_equal(c.cpu().numpy(), counts, err_msg=str(seed))
         np.testing.assert_array_equal(e.cpu().numpy(), events, err_msg=str(seed))
         np.testing.assert_array_equal(engine.vote(c, 2).cpu().numpy(), coracle.vote(counts, 2), err_msg=str(seed))
+
+
+def test_cpp_bam_decoder_equals_the_numpy_flatten_on_fuzz_cases(tmp_path):
+    """The same random alignments as BAM through the C++ decoder (bam_host.cpp: filter, classification, inline CIGAR
+    blocks, index lists, reach) and as SAM text through bamio.finalize (numpy): every array of the device layout must
+    be identical, for several thread counts -- POS == 0, overhanging clips, exotic ops and bases, unmapped records and
+    the other edge cases the generator makes included."""
+    from oracle import samdecode as sd
+
+    ops = "MIDNSHP=X"
+    compared = 0
+    for seed in range(0, N_CASES, 2):
+        path = _load(tmp_path, seed)
+        try:
+            want = bamio.read_alignment(path)
+        except ValueError:
+            continue  # a base outside the BAM alphabet cannot be packed into 4 bits: no BAM of it exists either
+        header, records = sd.read_alignment_file(path)
+        names = [sn[3:] for sn in header["@SQ"]]
+        contigs = [(nm, int(header["@SQ"]["SN:" + nm][0][3:])) for nm in names]
+        recs = []
+        for r in records:
+            cig = [] if r.cigars == ((0, None),) else [(n << 4) | ops.index(o) for n, o in r.cigars]
+            recs.append((names.index(r.rname) if r.rname != "*" else -1, r.pos - 1, r.flag, cig, r.seq.upper() if r.seq != "*" else "*"))
+        bam = tmp_path / ("fuzz%d.bam" % seed)
+        bamio.write_bam(bam, contigs, recs, level=1)
+        for threads in (1, 5):
+            got = bamio.read_bam(bam, threads=threads)
+            assert got.contig_names == want.contig_names and got.n_records == want.n_records, seed
+            for f in ("contig_len", "contig_read_off", "contig_slot", "ref_start", "seq_len", "l_seq", "seq_off", "seq4",
+                      "cig_off", "cigar", "complex_idx", "hard_idx"):
+                np.testing.assert_array_equal(getattr(got, f), getattr(want, f), err_msg="seed %d %s" % (seed, f))
+            assert (got.n_events, got.reads_sorted, got.max_simple_len, got.reach_right, got.reach_left, got.aligned_bases) == \
+                   (want.n_events, want.reads_sorted, want.max_simple_len, want.reach_right, want.reach_left, want.aligned_bases), seed
+        compared += 1
+    assert compared > 100

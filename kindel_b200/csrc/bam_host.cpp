@@ -23,11 +23,14 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -53,26 +56,86 @@ inline int32_t rd_i32(const uint8_t* p) { int32_t v; std::memcpy(&v, p, 4); retu
 inline uint32_t rd_u32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
 inline uint16_t rd_u16(const uint8_t* p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
 
-template <class F>
-void parallel_for(int64_t n, int threads, F&& body) {  // body(task_index, thread_index), dynamic scheduling
-    if (threads < 1) threads = 1;
-    if (n <= 1 || threads == 1) {
-        for (int64_t i = 0; i < n; ++i) body(i, 0);
-        return;
+// The decoder's worker threads live as long as the handle: the four parallel phases of one decode reuse them.
+// (Spawning 64 threads per phase means ~60 stack mmaps and munmaps each time, which take the process's address-space
+// lock away from the very page faults the workers are busy with.)  run(n, body): body(task_index, worker_index) for
+// every task in [0, n), dynamic scheduling, the caller works too and returns when all tasks are done.
+class Pool {
+  public:
+    explicit Pool(int threads) {
+        const int extra = std::max(0, threads - 1);
+        for (int t = 0; t < extra; ++t) workers_.emplace_back([this, t] { loop(t + 1); });
     }
-    std::atomic<int64_t> next{0};
-    std::vector<std::thread> pool;
-    const int nt = (int)std::min<int64_t>(threads, n);
-    for (int t = 0; t < nt; ++t)
-        pool.emplace_back([&, t] {
-            for (;;) {
-                const int64_t i = next.fetch_add(1, std::memory_order_relaxed);
-                if (i >= n) break;
-                body(i, t);
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        wake_.notify_all();
+        for (auto& th : workers_) th.join();
+    }
+    Pool(const Pool&) = delete;
+    Pool& operator=(const Pool&) = delete;
+    int size() const { return (int)workers_.size() + 1; }
+
+    template <class F>
+    void run(int64_t n, int max_threads, F&& body) {
+        if (n <= 0) return;
+        const int helpers = (int)std::min<int64_t>(std::min<int64_t>((int64_t)workers_.size(), n - 1), std::max(0, max_threads - 1));
+        if (helpers <= 0) {
+            for (int64_t i = 0; i < n; ++i) body(i, 0);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            body_ = [&body](int64_t i, int t) { body(i, t); };
+            n_ = n;
+            next_.store(0, std::memory_order_relaxed);
+            wanted_ = helpers;   // workers 1..helpers take part in this generation
+            pending_ = helpers;
+            ++gen_;
+        }
+        wake_.notify_all();
+        drain(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        body_ = nullptr;
+    }
+
+  private:
+    void drain(int t) {
+        for (;;) {
+            const int64_t i = next_.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n_) break;
+            body_(i, t);
+        }
+    }
+    void loop(int t) {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                wake_.wait(lk, [&] { return stop_ || (gen_ != seen && t <= wanted_); });
+                if (stop_) return;
+                seen = gen_;
             }
-        });
-    for (auto& th : pool) th.join();
-}
+            drain(t);
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable wake_, done_;
+    std::function<void(int64_t, int)> body_;
+    std::atomic<int64_t> next_{0};
+    int64_t n_ = 0;
+    uint64_t gen_ = 0;
+    int wanted_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
 
 struct RecView {
     int32_t ref_id, pos, l_seq;
@@ -230,6 +293,7 @@ struct kdl_bam {
     int64_t reach_right = 0, reach_left = 0, max_simple = 0;
     int32_t reads_sorted = 1;
     bool prepared = false;
+    std::unique_ptr<Pool> pool;         // the worker threads of this handle (created by kdl_bam_open)
 };
 
 extern "C" {
@@ -255,6 +319,7 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
     pt.lap("open: read file");
     kdl_bam* h = new (std::nothrow) kdl_bam();
     if (!h) return KDL_ERR_INVALID_ARG;
+    h->pool.reset(new Pool(threads < 1 ? 1 : threads));
     const size_t n = raw.size();
     if (n >= 4 && !std::memcmp(raw.data(), "BAM\1", 4)) {
         h->data.swap(raw);
@@ -318,7 +383,7 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
             h->dptr = h->big.get();
             h->dsize = (int64_t)total;
             std::atomic<int> failed{0};
-            parallel_for((int64_t)blks.size(), threads, [&](int64_t i, int) {
+            h->pool->run((int64_t)blks.size(), threads, [&](int64_t i, int) {
                 const Blk& b = blks[(size_t)i];
                 if (!b.isize) return;
                 z_stream zs;
@@ -469,7 +534,7 @@ int kdl_bam_prepare(kdl_bam* h, const int32_t* ref_len, int threads, int64_t* in
         }
         tk.end = off;
     };
-    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+    h->pool->run(n_tasks, threads, [&](int64_t t, int) {
         const int64_t start = t == 0 ? h->first_record : guess(byte_lo[(size_t)t], byte_lo[(size_t)t + 1]);
         if (start >= 0) walk(t, start);
     });
@@ -496,7 +561,7 @@ int kdl_bam_prepare(kdl_bam* h, const int32_t* ref_len, int threads, int64_t* in
     h->rec_off.resize((size_t)n_rec + 1);
     h->cls.resize((size_t)n_rec);
     h->rec_off[(size_t)n_rec] = n_bytes;
-    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+    h->pool->run(n_tasks, threads, [&](int64_t t, int) {
         const Task& tk = task[(size_t)t];
         const size_t base = (size_t)h->chunk_lo[(size_t)t];
         if (!tk.off.empty()) {
@@ -580,7 +645,7 @@ int kdl_bam_fill(kdl_bam* h, int threads, const int64_t* contig_slot, int32_t* r
     const int64_t n = h->n_kept;
     PhaseTimer pt;
     std::vector<uint32_t> ins_n((size_t)std::max<int64_t>(n, 1), 0);  // I ops per kept read (final order)
-    parallel_for(n_tasks, threads, [&](int64_t t, int) {
+    h->pool->run(n_tasks, threads, [&](int64_t t, int) {
         std::vector<int64_t> cr(h->cur_read.begin() + t * n_ref, h->cur_read.begin() + (t + 1) * n_ref);
         std::vector<int64_t> co(h->cur_op.begin() + t * n_ref, h->cur_op.begin() + (t + 1) * n_ref);
         std::vector<int64_t> cw(h->cur_word.begin() + t * n_ref, h->cur_word.begin() + (t + 1) * n_ref);

@@ -454,10 +454,12 @@ def build_report(ref_id, weights, changes, cdr_patches, bam_path, realign, min_d
     else:
         depths = [w["A"] + w["C"] + w["G"] + w["T"] for w in weights]
         dmin, dmax = min(depths), max(depths)
-    sites = {"N": [], "I": [], "D": []}
-    for pos, change in enumerate(changes, start=1):
-        if change in sites:
-            sites[change].append(str(pos))
+    sites = getattr(changes, "sites", None)  # (a list built by _changes_list knows its sites already)
+    if sites is None:
+        sites = {"N": [], "I": [], "D": []}
+        for pos, change in enumerate(changes, start=1):
+            if change in sites:
+                sites[change].append(str(pos))
     patches = ["{}-{}: {}".format(r.start, r.end, r.seq) for r in cdr_patches] if cdr_patches else ""
     lines = [
         "========================= REPORT ===========================",
@@ -496,12 +498,23 @@ def bam_to_consensus(bam_path, realign=False, min_depth=1, min_overlap=9, clip_d
                               clip_decay_threshold, mask_ends, trim_ends, uppercase)
 
 
+class _Changes(list):
+    """The reference's `changes` list (None / 'D' / 'N' / 'I' per position) that also remembers where its few
+    non-None entries are, so the report needs no pass over millions of Nones."""
+
+    __slots__ = ("sites",)
+
+
 def _changes_list(calls):
     """Per-position change codes (None / 'D' / 'N' / 'I') of one contig's call bytes."""
     change = (calls >> 4) & 3
-    out = [None] * calls.shape[0]
-    for k in np.flatnonzero(change).tolist():
-        out[k] = _CHANGE_LUT[change[k]]
+    out = _Changes([None] * calls.shape[0])
+    at = np.flatnonzero(change)
+    out.sites = {"N": [], "I": [], "D": []}
+    for k, code in zip(at.tolist(), change[at].tolist()):
+        name = _CHANGE_LUT[code]
+        out[k] = name
+        out.sites[name].append(str(k + 1))
     return out
 
 

@@ -286,7 +286,9 @@ int kdl_ctx_last_timing(kdl_ctx* ctx, float* h2d_ms, float* kernel_ms, float* d2
  * Replaces the simplesam -> `samtools view` text round trip of kindel/kindel.py:136-145 for .bam input: BGZF blocks
  * inflated by zlib in C++ threads, records filtered (kindel.py:43-46), classified and written straight into the
  * layout above -- into caller-owned buffers, which may be pinned memory.
- *   kdl_bam_open     read + inflate + parse the header (text, reference dictionary)
+ *   kdl_bam_open     read + inflate + parse the header (text, reference dictionary).  Takes BGZF / gzip / plain BAM
+ *                    and SAM text (plain or gzip): text lines are turned into BAM records in threads by a strict
+ *                    parser that gives up (error) on anything unusual -- the caller then uses its own text reader
  *   kdl_bam_prepare  ref_len[n_ref] = contig lengths to classify against (the @SQ LN values the reference uses;
  *                    NULL = the binary dictionary's).  info[16] out: 0 records, 1 kept reads, 2 contigs seen,
  *                    3 CIGAR ops of kept reads, 4 words of seq4, 5 complex reads, 6 hard reads, 7 aligned bases,

@@ -597,7 +597,13 @@ def read_alignment(path) -> ReadBatch:
         magic = fh.read(4)
     if magic[:2] == b"\x1f\x8b" or magic == b"BAM\x01":
         return read_bam(path)
-    return read_sam(path)
+    # SAM text: the C++ decoder turns the lines into BAM records in threads and shares everything downstream.  Its
+    # parser is strict; whatever it refuses (an RNAME without @SQ line, a base that cannot be packed, odd integers ...)
+    # goes through the Python text reader below, which raises what the reference's path would
+    try:
+        return read_bam(path)
+    except ValueError:
+        return read_sam(path)
 
 
 # ------------------------------------------------------------------------------ BAM writing

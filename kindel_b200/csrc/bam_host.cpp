@@ -24,6 +24,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <climits>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -271,6 +272,231 @@ inline Class classify(const RecView& r, int64_t L, int64_t* reach_r, int64_t* re
     return c;
 }
 
+// ---- SAM text -> the BAM record stream (in memory) -------------------------------------------------------------
+// The reference reads SAM and BAM through the same reader (kindel.py:136-145), so the decoder takes text too: the
+// lines are turned into BAM records by the worker threads and everything downstream -- filter, classification,
+// layout -- is shared.  Anything this strict parser does not like (a field that is not a plain integer, an RNAME
+// without @SQ line, a base outside the BAM alphabet in a read that would be used, more than 65535 CIGAR ops, header
+// lines between records) makes it give up with an error; the Python caller then falls back to its own text reader,
+// which raises exactly what the reference's path would.
+struct SamRef { std::string name; int32_t len; };
+
+inline bool parse_int(const uint8_t* b, const uint8_t* e, int64_t* out) {
+    if (b == e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = *b == '-'; ++b; }
+    if (b == e || e - b > 18) return false;
+    int64_t v = 0;
+    for (; b < e; ++b) {
+        if (*b < '0' || *b > '9') return false;
+        v = v * 10 + (*b - '0');
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
+// 255 = not a BAM base code
+inline const uint8_t* base_codes() {
+    static const struct Tab {
+        uint8_t t[256];
+        Tab() {
+            std::memset(t, 255, sizeof t);
+            const char* nib = "=ACMGRSVTWYHKDBN";
+            for (int i = 0; i < 16; ++i) {
+                t[(uint8_t)nib[i]] = (uint8_t)i;
+                if (nib[i] >= 'A' && nib[i] <= 'Z') t[(uint8_t)(nib[i] + 32)] = (uint8_t)i;
+            }
+        }
+    } tab;
+    return tab.t;
+}
+
+bool looks_like_sam_text(const uint8_t* p, size_t n) {
+    if (n == 0) return false;
+    if (p[0] == '@') return n >= 3 && p[1] >= 'A' && p[1] <= 'Z' && p[2] >= 'A' && p[2] <= 'Z';
+    const uint8_t* nl = (const uint8_t*)std::memchr(p, '\n', std::min<size_t>(n, 1 << 16));
+    const uint8_t* end = nl ? nl : p + std::min<size_t>(n, 1 << 16);
+    int tabs = 0;
+    for (const uint8_t* q = p; q < end; ++q) {
+        if (*q == '\t') ++tabs;
+        else if (*q < 32 || *q > 126) return false;
+    }
+    return tabs >= 10;
+}
+
+// Returns KDL_OK and the BAM stream in `out`, or KDL_ERR_INVALID_ARG.
+int sam_text_to_bam(const uint8_t* p, size_t n, Pool& pool, int threads, std::vector<uint8_t>& out) {
+    // ---- header: the '@' lines at the top
+    size_t body = 0;
+    std::string text;
+    std::vector<SamRef> refs;
+    while (body < n && p[body] == '@') {
+        const uint8_t* nl = (const uint8_t*)std::memchr(p + body, '\n', n - body);
+        const size_t end = nl ? (size_t)(nl - p) : n;
+        size_t le = end;
+        if (le > body && p[le - 1] == '\r') --le;  // (text mode reading drops the \r of a CRLF file too)
+        const std::string line((const char*)p + body, le - body);
+        text += line;
+        text += '\n';
+        if (line.compare(0, 3, "@SQ") == 0) {
+            std::string sn;
+            int64_t ln = -1;
+            bool have_sn = false;
+            size_t f = line.find('\t');
+            while (f != std::string::npos) {
+                const size_t g = line.find('\t', f + 1);
+                const std::string field = line.substr(f + 1, g == std::string::npos ? std::string::npos : g - f - 1);
+                if (field.compare(0, 3, "SN:") == 0) { sn = field.substr(3); have_sn = true; }
+                else if (field.compare(0, 3, "LN:") == 0) {
+                    const uint8_t* b = (const uint8_t*)field.data() + 3;
+                    if (!parse_int(b, (const uint8_t*)field.data() + field.size(), &ln) || ln < 0 || ln > INT32_MAX) return KDL_ERR_INVALID_ARG;
+                }
+                f = g;
+            }
+            if (have_sn && ln >= 0) {
+                for (const SamRef& r : refs) if (r.name == sn) return KDL_ERR_INVALID_ARG;  // duplicate SN: not ours to resolve
+                refs.push_back({sn, (int32_t)ln});
+            }
+        }
+        body = nl ? end + 1 : n;
+    }
+    std::vector<std::pair<std::string, int32_t>> by_name;
+    by_name.reserve(refs.size());
+    for (size_t k = 0; k < refs.size(); ++k) by_name.emplace_back(refs[k].name, (int32_t)k);
+    std::sort(by_name.begin(), by_name.end());
+    auto ref_id_of = [&](const uint8_t* b, const uint8_t* e) -> int32_t {  // -1: '*', -2: unknown
+        if (e - b == 1 && *b == '*') return -1;
+        const std::string key((const char*)b, (size_t)(e - b));
+        auto it = std::lower_bound(by_name.begin(), by_name.end(), std::make_pair(key, (int32_t)INT32_MIN));
+        return (it != by_name.end() && it->first == key) ? it->second : -2;
+    };
+    // ---- records: byte ranges that end at line ends, one output vector per range
+    if (threads < 1) threads = 1;
+    const size_t len = n - body;
+    int64_t n_tasks = std::min<int64_t>(std::max<int64_t>(1, (int64_t)(len / (256 << 10))), (int64_t)threads * 4);
+    std::vector<size_t> cut((size_t)n_tasks + 1);
+    cut[0] = body;
+    for (int64_t t = 1; t < n_tasks; ++t) {
+        size_t at = body + len * (size_t)t / (size_t)n_tasks;
+        if (at < cut[(size_t)t - 1]) at = cut[(size_t)t - 1];
+        const uint8_t* nl = at < n ? (const uint8_t*)std::memchr(p + at, '\n', n - at) : nullptr;
+        cut[(size_t)t] = nl ? (size_t)(nl - p) + 1 : n;
+    }
+    cut[(size_t)n_tasks] = n;
+    std::vector<std::vector<uint8_t>> part((size_t)n_tasks);
+    std::atomic<int> failed{0};
+    const uint8_t* code = base_codes();
+    pool.run(n_tasks, threads, [&](int64_t t, int) {
+        std::vector<uint8_t>& o = part[(size_t)t];
+        o.reserve((cut[(size_t)t + 1] - cut[(size_t)t]) / 2 + 64);
+        std::vector<uint32_t> ops;
+        size_t at = cut[(size_t)t];
+        const size_t stop = cut[(size_t)t + 1];
+        while (at < stop) {
+            const uint8_t* nl = (const uint8_t*)std::memchr(p + at, '\n', stop - at);
+            size_t end = nl ? (size_t)(nl - p) : stop;
+            const size_t next = nl ? end + 1 : stop;
+            if (end > at && p[end - 1] == '\r') --end;
+            if (p[at] == '@') { failed = 1; return; }  // a header line between records: the text reader's case
+            const uint8_t* f[12];
+            int nf = 0;
+            f[nf++] = p + at;
+            for (const uint8_t* q = p + at; q < p + end && nf < 12; ++q)
+                if (*q == '\t') f[nf++] = q + 1;
+            if (nf < 11) { at = next; continue; }  // not a record line (the text reader skips it too)
+            auto fe = [&](int k) { return k + 1 < nf ? f[k + 1] - 1 : p + end; };  // end of field k (nf <= 12: field 11+ unused)
+            int64_t flag, pos;
+            if (!parse_int(f[1], fe(1), &flag) || !parse_int(f[3], fe(3), &pos) || flag < 0 || flag > 0xFFFF ||
+                pos < INT32_MIN + 1ll || pos > INT32_MAX) { failed = 1; return; }
+            const int32_t ref_id = ref_id_of(f[2], fe(2));
+            if (ref_id == -2) { failed = 1; return; }  // RNAME without @SQ line: KeyError in the reference
+            const uint8_t* sq = f[9];
+            const int64_t slen = fe(9) - f[9];
+            const bool used = ref_id >= 0 && !(flag & 4) && slen > 1;  // (kindel.py:43-46, :147-148)
+            ops.clear();
+            int64_t l_seq = 0;
+            if (used) {
+                const uint8_t* c = f[5];
+                const uint8_t* ce = fe(5);
+                if (!(ce - c == 1 && *c == '*')) {
+                    int64_t num = 0;
+                    for (; c < ce; ++c) {
+                        if (*c >= '0' && *c <= '9') {
+                            num = num * 10 + (*c - '0');
+                            if (num >= (1ll << 28)) { failed = 1; return; }
+                        } else {
+                            if (*c >= 128) { failed = 1; return; }
+                            const char* opc = "MIDNSHP=X";
+                            const char* hit = (const char*)std::memchr(opc, *c, 9);
+                            ops.push_back((uint32_t)(num << 4) | (hit ? (uint32_t)(hit - opc) : 15u));  // unknown op letters are no-ops
+                            num = 0;
+                        }
+                    }
+                }
+                if (ops.size() > 65535) { failed = 1; return; }
+                l_seq = slen;
+            }
+            const int64_t seq_bytes = (l_seq + 1) / 2;
+            const int64_t block_size = 32 + 1 + 4 * (int64_t)ops.size() + seq_bytes + l_seq;
+            if (block_size > (1ll << 28)) { failed = 1; return; }
+            const size_t base = o.size();
+            o.resize(base + 4 + (size_t)block_size);
+            uint8_t* w = o.data() + base;
+            const int32_t bs32 = (int32_t)block_size, pos0 = (int32_t)(pos - 1), lseq32 = (int32_t)l_seq, m1 = -1, zero = 0;
+            const uint16_t ncig = (uint16_t)ops.size(), flag16 = (uint16_t)flag, bin = 4680;
+            std::memcpy(w, &bs32, 4);
+            std::memcpy(w + 4, &ref_id, 4);
+            std::memcpy(w + 8, &pos0, 4);
+            w[12] = 1; w[13] = 0;                       // l_read_name (the NUL only), mapq
+            std::memcpy(w + 14, &bin, 2);
+            std::memcpy(w + 16, &ncig, 2);
+            std::memcpy(w + 18, &flag16, 2);
+            std::memcpy(w + 20, &lseq32, 4);
+            std::memcpy(w + 24, &m1, 4);
+            std::memcpy(w + 28, &m1, 4);
+            std::memcpy(w + 32, &zero, 4);
+            w[36] = 0;                                  // read name ""
+            uint8_t* q = w + 37;
+            if (!ops.empty()) std::memcpy(q, ops.data(), 4 * ops.size());
+            q += 4 * ops.size();
+            for (int64_t k = 0; k < l_seq; k += 2) {
+                const uint8_t hi = code[sq[k]], lo = k + 1 < l_seq ? code[sq[k + 1]] : 0;
+                if (hi == 255 || lo == 255) { failed = 1; return; }  // cannot be packed in 4 bits: ValueError upstairs
+                *q++ = (uint8_t)(hi << 4 | lo);
+            }
+            std::memset(q, 0xff, (size_t)l_seq);
+            at = next;
+        }
+    });
+    if (failed) return KDL_ERR_INVALID_ARG;
+    // ---- header + dictionary + the parts, back to back
+    size_t total = 12 + text.size();
+    for (const SamRef& r : refs) total += 8 + r.name.size() + 1;
+    std::vector<size_t> at((size_t)n_tasks + 1);
+    at[0] = total;
+    for (int64_t t = 0; t < n_tasks; ++t) at[(size_t)t + 1] = at[(size_t)t] + part[(size_t)t].size();
+    out.resize(at[(size_t)n_tasks]);
+    uint8_t* w = out.data();
+    std::memcpy(w, "BAM\1", 4);
+    const int32_t l_text = (int32_t)text.size(), n_ref = (int32_t)refs.size();
+    std::memcpy(w + 4, &l_text, 4);
+    std::memcpy(w + 8, text.data(), text.size());
+    w += 8 + text.size();
+    std::memcpy(w, &n_ref, 4);
+    w += 4;
+    for (const SamRef& r : refs) {
+        const int32_t l_name = (int32_t)r.name.size() + 1;
+        std::memcpy(w, &l_name, 4);
+        std::memcpy(w + 4, r.name.c_str(), (size_t)l_name);
+        std::memcpy(w + 4 + l_name, &r.len, 4);
+        w += 8 + l_name;
+    }
+    pool.run(n_tasks, threads, [&](int64_t t, int) {
+        if (!part[(size_t)t].empty()) std::memcpy(out.data() + at[(size_t)t], part[(size_t)t].data(), part[(size_t)t].size());
+    });
+    return KDL_OK;
+}
+
 }  // namespace
 
 struct kdl_bam {
@@ -323,6 +549,9 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
     const size_t n = raw.size();
     if (n >= 4 && !std::memcmp(raw.data(), "BAM\1", 4)) {
         h->data.swap(raw);
+    } else if (looks_like_sam_text(raw.data(), n)) {
+        if (sam_text_to_bam(raw.data(), n, *h->pool, threads, h->data) != KDL_OK) { delete h; return KDL_ERR_INVALID_ARG; }
+        pt.lap("open: SAM text -> records");
     } else {
         // BGZF: gzip members with a BC extra field holding the block size; the chain of headers is walked
         // sequentially (cheap), the payloads are inflated in parallel at their prefix-summed offsets
@@ -402,6 +631,15 @@ int kdl_bam_open(const char* path, int threads, kdl_bam** out) {
         }
     }
     if (!h->dptr) { h->dptr = h->data.data(); h->dsize = (int64_t)h->data.size(); }
+    if (h->dsize > 0 && std::memcmp(h->dptr, "BAM\1", h->dsize < 4 ? (size_t)h->dsize : 4) != 0 &&
+        looks_like_sam_text(h->dptr, (size_t)h->dsize)) {  // gzip-compressed SAM text
+        std::vector<uint8_t> conv;
+        if (sam_text_to_bam(h->dptr, (size_t)h->dsize, *h->pool, threads, conv) != KDL_OK) { delete h; return KDL_ERR_INVALID_ARG; }
+        h->data.swap(conv);
+        h->big.reset();
+        h->dptr = h->data.data();
+        h->dsize = (int64_t)h->data.size();
+    }
     const uint8_t* d = h->dptr;
     const int64_t dn = h->dsize;
     if (dn < 12 || std::memcmp(d, "BAM\1", 4)) { delete h; return KDL_ERR_INVALID_ARG; }

@@ -281,6 +281,14 @@ inline Class classify(const RecView& r, int64_t L, int64_t* reach_r, int64_t* re
 // which raises exactly what the reference's path would.
 struct SamRef { std::string name; int32_t len; };
 
+// a carriage return inside a line (text mode would break the line there) or a non-ASCII byte (text mode would have
+// to decode it): the Python reader's business
+inline bool odd_bytes(const uint8_t* b, const uint8_t* e) {
+    unsigned bad = 0;
+    for (; b < e; ++b) bad |= (unsigned)(*b == '\r') | (unsigned)(*b >> 7);
+    return bad != 0;
+}
+
 inline bool parse_int(const uint8_t* b, const uint8_t* e, int64_t* out) {
     if (b == e) return false;
     bool neg = false;
@@ -335,6 +343,7 @@ int sam_text_to_bam(const uint8_t* p, size_t n, Pool& pool, int threads, std::ve
         const size_t end = nl ? (size_t)(nl - p) : n;
         size_t le = end;
         if (le > body && p[le - 1] == '\r') --le;  // (text mode reading drops the \r of a CRLF file too)
+        if (odd_bytes(p + body, p + le)) return KDL_ERR_INVALID_ARG;
         const std::string line((const char*)p + body, le - body);
         text += line;
         text += '\n';
@@ -397,7 +406,8 @@ int sam_text_to_bam(const uint8_t* p, size_t n, Pool& pool, int threads, std::ve
             size_t end = nl ? (size_t)(nl - p) : stop;
             const size_t next = nl ? end + 1 : stop;
             if (end > at && p[end - 1] == '\r') --end;
-            if (p[at] == '@') { failed = 1; return; }  // a header line between records: the text reader's case
+            if (odd_bytes(p + at, p + end)) { failed = 1; return; }
+            if (end > at && p[at] == '@') { failed = 1; return; }  // a header line between records: the text reader's case
             const uint8_t* f[12];
             int nf = 0;
             f[nf++] = p + at;

@@ -54,6 +54,8 @@ CASES = {
     "sq_without_ln": "@SQ\tSN:a\n@SQ\tSN:b\tLN:30\n" + "r\t0\tb\t5\t60\t8M\t*\t0\t0\tACGTACGT\t*\n",
     "duplicate_sn": "@SQ\tSN:a\tLN:50\n@SQ\tSN:a\tLN:60\n" + REC,
     "huge_flag": HDR + "r\t70000\ta\t5\t60\t8M\t*\t0\t0\tACGTACGT\t*\n",
+    "lone_cr_inside_a_line": HDR + "r1\t0\ta\t3\t60\t7M\t*\t0\rD\t0\tCAACCTC\t*\n" + REC,   # text mode breaks the line at the CR
+    "non_ascii_qname": HDR + "r\u00e9\t0\ta\t5\t60\t8M\t*\t0\t0\tACGTACGT\t*\n",
 }
 
 

@@ -619,9 +619,15 @@ def weights_from_run(run, relative=False, confidence=True, confidence_alpha=0.01
     if confidence:
         cnt = consensus_depths.to_numpy()
         nobs = weights_df["depth"].to_numpy()
-        lower, upper = scipy.stats.beta.interval(1 - confidence_alpha, cnt + 0.5, nobs - cnt + 0.5)
-        weights_df["lower_ci"] = lower
-        weights_df["upper_ci"] = upper
+        # Jeffreys interval per (count, depth) pair (kindel.py:569-574,619-624): an elementwise function of two small
+        # integers, and megabases of positions share a few thousand distinct pairs -- evaluate those, gather the rest
+        # (the same scipy call on the same inputs: bit-identical to the per-row result)
+        base = int(nobs.max()) + 1 if len(nobs) else 1
+        pair, inverse = np.unique(cnt.astype(np.int64) * base + nobs.astype(np.int64), return_inverse=True)
+        ucnt, unobs = pair // base, pair % base
+        lower, upper = scipy.stats.beta.interval(1 - confidence_alpha, ucnt + 0.5, unobs - ucnt + 0.5)
+        weights_df["lower_ci"] = np.asarray(lower)[inverse]
+        weights_df["upper_ci"] = np.asarray(upper)[inverse]
     if relative:
         for nt in ["A", "C", "G", "T", "N"]:
             weights_df[[nt]] = rel[[nt]]

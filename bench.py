@@ -233,13 +233,8 @@ def cpu_sample_records(batch, target_bases=5.0e7):
     return recs, bases, window
 
 
-def cpu_reference_sample(batch):
-    """The reference's OWN functions (unmodified kindel/kindel.py, staged under baseline/_ref by
-    oracle/stage_reference.py; loaded through oracle/refload.py's import stubs): parse_records +
-    consensus_sequence (kindel.py:21-128, 384-430) on a bounded sample, single core -- the reference has no
-    parallelism (kindel/kindel.py:1-14 imports no threading / multiprocessing).  Falls back to the
-    reference-shaped CPython port (oracle/py_oracle.py) when no reference tree can be found; says which ran."""
-    recs, bases, window = cpu_sample_records(batch)
+def load_cpu_reference():
+    """(module or None, kind, description): the unmodified reference if a tree is found, else the port."""
     kind, how = "port", "oracle/py_oracle.py (reference-shaped CPython port; no reference tree found)"
     ref = None
     try:
@@ -253,6 +248,11 @@ def cpu_reference_sample(batch):
     except Exception as exc:  # noqa: BLE001
         how += " (loading the reference failed: %s)" % exc
         ref = None
+    return ref, kind, how
+
+
+def cpu_reference_pass(ref, recs, window):
+    """One pass of the reference's hot path over the sample; seconds."""
     t0 = time.perf_counter()
     if ref is not None:
         aln = ref.parse_records("ctg0", window, recs)
@@ -262,7 +262,18 @@ def cpu_reference_sample(batch):
 
         p = py_oracle.pileup(window, recs)
         py_oracle.vote(p, 1)
-    dt = time.perf_counter() - t0
+    return time.perf_counter() - t0
+
+
+def cpu_reference_sample(batch, target_bases=5.0e7):
+    """The reference's OWN functions (unmodified kindel/kindel.py, staged under baseline/_ref by
+    oracle/stage_reference.py; loaded through oracle/refload.py's import stubs): parse_records +
+    consensus_sequence (kindel.py:21-128, 384-430) on a bounded sample, single core -- the reference has no
+    parallelism (kindel/kindel.py:1-14 imports no threading / multiprocessing).  Falls back to the
+    reference-shaped CPython port (oracle/py_oracle.py) when no reference tree can be found; says which ran."""
+    recs, bases, window = cpu_sample_records(batch, target_bases)
+    ref, kind, how = load_cpu_reference()
+    dt = cpu_reference_pass(ref, recs, window)
     return {"value": bases / dt, "unit": UNIT, "cores": 1, "kind": kind,
             "sample": "%s; %d reads / %d aligned bases over the first %d positions of the workload, %.1f s"
                       % (how, len(recs), bases, window, dt)}
@@ -320,21 +331,33 @@ def host_side_timings(batch):
 
 
 def run_reference(args):
+    """`--impl reference`: W untimed + K timed passes of the reference's own parse_records + consensus_sequence over
+    a bounded sample of the workload, one host core (the reference has no parallelism).  The sample is sized so that
+    the K + W passes take about 2 minutes in all (at most 5e7 aligned bases, ~6 s, per pass)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     batch, total, _ = make_workload(args.workload)
-    reps = max(1, min(args.steps, 3))
-    vals = [cpu_reference_sample(batch) for _ in range(reps)]
-    best = max(vals, key=lambda v: v["value"])
-    v = statistics.median(x["value"] for x in vals)
+    passes = max(1, args.steps) + max(0, args.warmup)
+    target = min(5.0e7, max(2.0e6, 8.0e6 * 120.0 / passes))  # ~8e6 bases/s for the reference on this class of host
+    recs, bases, window = cpu_sample_records(batch, target)
+    ref, kind, how = load_cpu_reference()
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_pass(ref, recs, window)
+    times = [cpu_reference_pass(ref, recs, window) for _ in range(max(1, args.steps))]
+    dt = statistics.median(times)
+    v = bases / dt
     native = cpu_native_sample(batch)
+    cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": kind,
+           "sample": "%s; %d reads / %d aligned bases over the first %d positions of the workload per step, median of "
+                     "%d steps %.2f s (min %.2f, max %.2f)" % (how, len(recs), bases, window, len(times), dt, min(times), max(times))}
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
-        "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "reference is single-threaded CPython (kindel/kindel.py:1-14)"},
-        "cpu_baseline": dict(best, value=v),
+        "config": {"workload": args.workload, "note": "reference is single-threaded CPython (kindel/kindel.py:1-14); "
+                   "a step = one pass over a bounded sample of the workload"},
+        "cpu_baseline": cpu,
         "cpu_native_port": native,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"nproc": os.cpu_count()},

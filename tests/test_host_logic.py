@@ -328,3 +328,49 @@ def test_bam_decoder_finds_records_across_task_ranges(tmp_path):
         fh.write(bamio._bgzf_block(b"", 1))
     with pytest.raises(ValueError):
         bamio.read_bam(cut, threads=8)
+
+
+def test_long_cigar_in_the_cg_tag(tmp_path):
+    """A read whose real CIGAR sits in the CG:B,I tag behind the `<l_seq>S<span>N` placeholder (SAM spec 4.2.2; what
+    samtools -- and so the reference's reader -- expands) decodes like the same read with the CIGAR in place; other
+    tags before it (all aux types) are skipped correctly, and a placeholder without the tag stays what it says."""
+    import struct
+
+    def record(ref_id, pos0, cig, seq, aux=b""):
+        qname = b"q\x00"
+        packed = bamio.words_to_bam_bytes(bamio.encode_seq(seq), len(seq))
+        core = struct.pack("<iiBBHHHiiii", ref_id, pos0, len(qname), 60, 4680, len(cig), 0, len(seq), -1, -1, 0)
+        data = core + qname + struct.pack("<%dI" % len(cig), *cig) + packed + b"\xff" * len(seq) + aux
+        return struct.pack("<i", len(data)) + data
+
+    def bam(path, records):
+        ht = b"@SQ\tSN:c\tLN:400\n"
+        body = b"BAM\x01" + struct.pack("<i", len(ht)) + ht + struct.pack("<i", 1) + struct.pack("<i", 2) + b"c\x00" + struct.pack("<i", 400)
+        body += b"".join(records)
+        with open(path, "wb") as fh:
+            fh.write(bamio._bgzf_block(body, 1) + bamio._bgzf_block(b"", 1))
+
+    rng = np.random.default_rng(2)
+    seq = "".join("ACGT"[i] for i in rng.integers(0, 4, size=60))
+    real = [(5 << 4) | 4, (20 << 4), (3 << 4) | 1, (10 << 4), (4 << 4) | 2, (22 << 4)]       # 5S20M3I10M4D22M
+    span = 20 + 10 + 4 + 22
+    placeholder = [(60 << 4) | 4, (span << 4) | 3]                                              # 60S56N
+    aux_before = (b"NMi" + struct.pack("<i", 3) + b"XAA" + b"x" + b"XcC" + b"\x07" + b"XsS" + struct.pack("<H", 9) +
+                  b"MDZ" + b"20A35\x00" + b"XhH" + b"1AE3\x00" + b"XbBc" + struct.pack("<I", 3) + b"\x01\x02\x03" +
+                  b"XfBf" + struct.pack("<I", 2) + struct.pack("<ff", 1.0, 2.0) + b"Xff" + struct.pack("<f", 0.5))
+    cg = b"CGBI" + struct.pack("<I", len(real)) + struct.pack("<%dI" % len(real), *real)
+    plain = [record(0, 100, [(60 << 4)], seq)]
+    a = tmp_path / "inline.bam"
+    bam(a, plain + [record(0, 30, real, seq)])
+    b = tmp_path / "tagged.bam"
+    bam(b, plain + [record(0, 30, placeholder, seq, aux_before + cg + b"ZZi" + struct.pack("<i", 1))])
+    c = tmp_path / "untagged.bam"
+    bam(c, plain + [record(0, 30, placeholder, seq, aux_before)])
+    ba, bb, bc = bamio.read_bam(a), bamio.read_bam(b), bamio.read_bam(c)
+    for f in ("ref_start", "seq_len", "l_seq", "seq_off", "seq4", "cig_off", "cigar", "complex_idx", "hard_idx"):
+        np.testing.assert_array_equal(getattr(bb, f), getattr(ba, f), err_msg=f)
+    assert bb.cigar[bb.cig_off[1]:bb.cig_off[2]].tolist() == real
+    assert bc.cigar[bc.cig_off[1]:bc.cig_off[2]].tolist() == placeholder       # no tag: the placeholder is the CIGAR
+    ca, _ = coracle.pileup(ba)
+    cb, _ = coracle.pileup(bb)
+    np.testing.assert_array_equal(ca, cb)
